@@ -1,0 +1,187 @@
+/*
+ * vmtl_b200.h -- C ABI of libvmtl_b200.so: hand-written sm_100a CUDA kernels for the
+ * per-step multi-task hot path of kirilllzaitsev/vision_mtl.
+ *
+ * The reference is pure Python and has no FFI; the "interface each entry point replaces"
+ * is therefore the ATen op sequence behind a Python call site.  Citations are
+ * /root/reference paths (file:line).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - feature maps are NHWC ("channels_last"): a [B,C,H,W] map is a row-major
+ *     [npix = B*H*W, C] matrix, 16-byte aligned, C % 4 == 0;
+ *   - the caller owns every buffer, including workspaces (size them with the
+ *     *_workspace_bytes helpers); workspaces need no initialisation unless noted;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work, they never
+ *     synchronise, allocate or free;
+ *   - return value: 0 (VMTL_OK) or a negative VMTL_E* code; vmtl_strerror() names it.
+ *   - all floating point is fp32; reductions are accumulated in fp64 and are
+ *     deterministic (fixed-order two-stage reductions, integer atomics only).
+ */
+#ifndef VMTL_B200_H_
+#define VMTL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMTL_OK 0
+#define VMTL_EINVAL (-1)       /* bad argument value                       */
+#define VMTL_EALIGN (-2)       /* pointer / channel count not 16B friendly */
+#define VMTL_ECUDA (-3)        /* a CUDA runtime call or launch failed      */
+#define VMTL_EUNSUPPORTED (-4) /* shape outside what the kernels cover      */
+#define VMTL_EWORKSPACE (-5)   /* workspace too small                       */
+
+#define VMTL_MAX_TASKS 4
+
+/* cross-stitch modes */
+#define VMTL_XS_REFERENCE_DIAG 0 /* y[a] = alpha[a,a(,c)] * x[a]  -- what the reference einsum computes */
+#define VMTL_XS_FULL_MIX 1       /* y[a] = sum_b alpha[a,b(,c)] * x[b] */
+
+/* gate contraction precision */
+#define VMTL_GATE_FP32_FFMA 0 /* CUDA-core fp32 FMA contraction                        */
+#define VMTL_GATE_TC_3XTF32 1 /* tcgen05 kind::tf32, hi/lo split, 3 MMAs (fp32-grade) */
+#define VMTL_GATE_TC_TF32 2   /* tcgen05 kind::tf32, single pass                      */
+
+/* logits layouts for the *_logits loss kernels */
+#define VMTL_LAYOUT_NCHW 0
+#define VMTL_LAYOUT_NHWC 1
+
+int vmtl_version(void);
+const char* vmtl_strerror(int code);
+/* number of SMs of the current device (grid sizing); <0 on error */
+int vmtl_sm_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Cross-stitch unit.  Replaces torch.stack + torch.einsum at
+ * vision_mtl/models/cross_stitch_model.py:32-37 (forward) and :143-156 (call site), and
+ * their autograd backward.
+ *   x_host / y_host : host arrays of T device pointers, each an NHWC [npix, C] map
+ *   alpha           : [T,T] (channel_wise == 0) or [T,T,C] (channel_wise != 0)
+ * ---------------------------------------------------------------------------------- */
+int vmtl_xstitch_fwd(const float* const* x_host, float* const* y_host, const float* alpha, int T,
+                     int64_t npix, int C, int channel_wise, int mode, void* stream);
+
+size_t vmtl_xstitch_bwd_workspace_bytes(int T, int64_t npix, int C, int channel_wise);
+
+/* dx[b] = sum_a alpha[a,b]*dy[a];  dalpha[a,b(,c)] = sum_pixels dy[a]*x[b].
+ * In VMTL_XS_REFERENCE_DIAG mode only the diagonal is used / gets a gradient and the
+ * off-diagonal entries of dalpha are written as exact zeros (matches the reference).
+ * dx_host may be NULL (skip the input gradient). */
+int vmtl_xstitch_bwd(const float* const* dy_host, const float* const* x_host,
+                     float* const* dx_host, const float* alpha, float* dalpha, int T,
+                     int64_t npix, int C, int channel_wise, int mode, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * MTAN attention gate:  y = s * sigmoid(BN(h @ W^T + bias)).
+ * Replaces conv2 -> bn2 -> sigmoid -> mul at vision_mtl/models/mtan_model.py:71-75
+ * (encoder) and :158-162 (decoder).
+ *   h [M,K]  hidden activations (K % 32 == 0, K <= 256; the reference uses K = 128)
+ *   s [M,N]  shared features    (N % 16 == 0, 16 <= N <= 256)
+ *   W [N,K], bias/gamma/beta/running_mean/running_var [N]
+ * training != 0: batch statistics (biased var for normalisation, unbiased for the
+ *   running update, momentum as nn.BatchNorm2d); z = h@W^T+bias is written to save_z and
+ *   (mean, invstd) to save_mean/save_invstd for the backward.  running_* may be NULL.
+ * training == 0: running statistics, single pass, save_* may be NULL.
+ * ---------------------------------------------------------------------------------- */
+/* backward != 0: size for vmtl_gate_bwd, else for vmtl_gate_fwd */
+size_t vmtl_gate_workspace_bytes(int64_t M, int K, int N, int precision, int backward);
+
+int vmtl_gate_fwd(const float* h, const float* s, const float* W, const float* bias,
+                  const float* gamma, const float* beta, float* running_mean,
+                  float* running_var, float momentum, float eps, int training, int precision,
+                  int64_t M, int K, int N, float* y, float* save_z, float* save_mean,
+                  float* save_invstd, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the training-mode gate (formulas: SURVEY Appendix B).
+ * Inputs: dy, h, s, saved z/mean/invstd.  Outputs: dh [M,K], ds [M,N], dW [N,K],
+ * dbias/dgamma/dbeta [N].  dh or ds may be NULL to skip them.  training == 0 uses
+ * running statistics passed in save_mean/save_invstd (dz = gamma*invstd*du). */
+int vmtl_gate_bwd(const float* dy, const float* h, const float* s, const float* z,
+                  const float* W, const float* gamma, const float* beta, const float* save_mean,
+                  const float* save_invstd, int training, int precision, int64_t M, int K,
+                  int N, float* dh, float* ds, float* dW, float* dbias, float* dgamma,
+                  float* dbeta, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Segmentation head fused with cross-entropy, argmax and the confusion matrix.
+ * Replaces nn.Conv2d(32,C,1) (mtan_model.py:367-376,401-404), F.softmax + argmax
+ * (lit_module.py:137-138), nn.CrossEntropyLoss (lit_module.py:31,123) and the
+ * torchmetrics confusion statistics (lit_module.py:109-111).
+ *   feat [P,Cin] NHWC (Cin % 4 == 0, Cin <= 64), W [C,Cin], b [C], target int64 [P]
+ *   out (double[2]) : {sum of per-pixel losses over valid pixels, n_valid}
+ *   loss (float[1]) : out[0]/out[1]   (mean over valid pixels; NaN when n_valid == 0)
+ *   pred            : optional uint8 [P] argmax (lowest index wins ties)
+ *   conf            : optional int64 [C,C], rows = target; ACCUMULATED (+=)
+ * Pixels with target == ignore_index (or outside [0,C)) contribute to nothing.
+ * ---------------------------------------------------------------------------------- */
+size_t vmtl_loss_workspace_bytes(int64_t P);
+
+int vmtl_head_ce_fwd(const float* feat, const float* W, const float* b, const int64_t* target,
+                     int64_t P, int Cin, int C, int64_t ignore_index, double* out, float* loss,
+                     uint8_t* pred, int64_t* conf, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* dfeat [P,Cin], dW [C,Cin], db [C] for loss = mean CE; logits are recomputed from feat.
+ * gscale (float[1], device): upstream dL/dloss.  n_valid comes from out[1] of the forward. */
+int vmtl_head_ce_bwd(const float* feat, const float* W, const float* b, const int64_t* target,
+                     int64_t P, int Cin, int C, int64_t ignore_index, const double* fwd_out,
+                     const float* gscale, float* dfeat, float* dW, float* db, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* Same loss/argmax/confusion on precomputed logits (basic / csnet 3x3 heads,
+ * basic_model.py:30-41, model_utils.py:125-130).  layout: VMTL_LAYOUT_NCHW
+ * ([B,C,HW], P = B*HW) or VMTL_LAYOUT_NHWC ([P,C]). */
+int vmtl_ce_logits_fwd(const float* logits, const int64_t* target, int64_t P, int64_t HW, int C,
+                       int layout, int64_t ignore_index, double* out, float* loss, uint8_t* pred,
+                       int64_t* conf, void* workspace, size_t workspace_bytes, void* stream);
+
+int vmtl_ce_logits_bwd(const float* logits, const int64_t* target, int64_t P, int64_t HW, int C,
+                       int layout, int64_t ignore_index, const double* fwd_out,
+                       const float* gscale, float* dlogits, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Depth head fused with sigmoid, the SILog loss moments and the depth error sums.
+ * Replaces nn.Conv2d(32,1,1) (mtan_model.py:367-376), sigmoid+permute
+ * (lit_module.py:139), SILogLoss.forward (losses.py:14-36) and MeanAbsoluteError
+ * (lit_module.py:68,112).
+ *   feat [P,Cin] (Cin == 1: feat already holds the depth logits, w/b ignored -> basic/csnet)
+ *   out (double[8]) : {n_mask, sum g, sum g^2, sum|p-t| (all px), sum|p-t|/t (masked),
+ *                      mean g, D = var_unbiased(g) + 0.15*mean(g)^2, P}
+ *   scalars (float[3]) : {silog = 10*sqrt(D), mae = sum|p-t|/P, abs_rel}
+ *   pred : optional float [P] = sigmoid(depth logit)
+ * ---------------------------------------------------------------------------------- */
+int vmtl_head_silog_fwd(const float* feat, const float* w, const float* b, const float* target,
+                        int64_t P, int Cin, float min_depth, double* out, float* scalars,
+                        float* pred, void* workspace, size_t workspace_bytes, void* stream);
+
+/* dfeat [P,Cin], dw [Cin], db [1] for loss = silog; gscale: upstream dL/dsilog (device). */
+int vmtl_head_silog_bwd(const float* feat, const float* w, const float* b, const float* target,
+                        int64_t P, int Cin, float min_depth, const double* fwd_out,
+                        const float* gscale, float* dfeat, float* dw, float* db,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Validation reductions (torchmetrics call sites lit_module.py:106-118).
+ * ---------------------------------------------------------------------------------- */
+/* conf[target, pred] += 1 for every pixel with 0 <= target,pred < C and target != ignore_index.
+ * pred_is_u8 != 0: pred is uint8 [P]; else int64 [P]. */
+int vmtl_confusion_accum(const void* pred, int pred_is_u8, const int64_t* target, int64_t P, int C,
+                         int64_t ignore_index, int64_t* conf, void* stream);
+
+/* out (double[4]) = {P, sum|p-t|, n(t > min_depth), sum |p-t|/t over t > min_depth} */
+int vmtl_depth_err_sums(const float* pred, const float* target, int64_t P, float min_depth,
+                        double* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* metrics (float[3]) = {accuracy (micro), jaccard (macro, absent = 0), F1 (weighted)}
+ * from an int64 [C,C] confusion matrix (lit_module.py:48-67 configuration). */
+int vmtl_seg_metrics(const int64_t* conf, int C, float* metrics, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMTL_B200_H_ */

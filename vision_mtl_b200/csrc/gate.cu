@@ -1,0 +1,477 @@
+// MTAN attention gate  y = s * sigmoid(BN(h @ W^T + bias))  -- entry points, the streaming
+// (HBM-bound) phases and the fp32 CUDA-core contraction.  The tensor-core contraction lives
+// in gate_tc.cu.
+//
+// Reference: conv2 -> bn2 -> sigmoid -> mul at vision_mtl/models/mtan_model.py:71-75 (encoder)
+// and :158-162 (decoder): five ATen kernels and four materialised [M,N] intermediates.
+//
+// BatchNorm is in TRAINING mode on the measured path, so z = h W^T + b needs its
+// per-channel batch statistics before the gate can be emitted:
+//   fwd  phase 1 : contraction, writes z, per-CTA column partials (sum z, sum z^2)
+//        finalize: fp64 fixed-order reduction -> mean, invstd, running-stat update, (A,B)
+//        phase 2 : y = s * sigmoid(A*z + B)                       streams z,s -> y
+//   bwd  phase A : ds = dy*a ; per-channel sum du, sum du*zhat    streams dy,s,z -> ds
+//        finalize: dbeta, dgamma (and c1 = dbeta/M, c2 = dgamma/M)
+//        phase B : dz = gamma*invstd*(du - c1 - zhat*c2) ; dh = dz W ; dW = dz^T h ; db = sum dz
+// Algorithmic bytes (train): fwd 4M(K + 4N), bwd 4M(2K + 7N)  (K = 128).
+#include <math.h>
+
+#include "gate_internal.cuh"
+
+namespace vmtl {
+
+constexpr int kEwThreads = 256;
+
+struct EwMap {
+  int rows, r, g;
+  bool active;
+};
+__device__ __forceinline__ EwMap ew_map(int C4) {
+  EwMap m;
+  m.rows = kEwThreads / C4;
+  m.r = threadIdx.x / C4;
+  m.g = threadIdx.x - m.r * C4;
+  m.active = m.r < m.rows;
+  return m;
+}
+static int ew_grid(int64_t M, int N) {
+  const int rows = kEwThreads / (N / 4);
+  int64_t want = (M + rows - 1) / rows;
+  int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+__device__ __forceinline__ float4 ld4(const float* p, int64_t i4) {
+  return ldg_stream(reinterpret_cast<const float4*>(p) + i4);
+}
+__device__ __forceinline__ void st4(float* p, int64_t i4, const float4& v) {
+  stg_stream(reinterpret_cast<float4*>(p) + i4, v);
+}
+__device__ __forceinline__ float4 ldc4(const float* p, int g) {
+  return reinterpret_cast<const float4*>(p)[g];
+}
+
+// block reduction over the `rows` threads sharing a channel group; writes one partial row
+template <int NV>
+__device__ __forceinline__ void ew_block_reduce(const float4 (&acc)[NV], const EwMap& m, int C4,
+                                                float* partial_row /* [NV][4*C4] */) {
+  __shared__ float4 s_red[kEwThreads * NV];
+  if (m.active) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s_red[(m.r * C4 + m.g) * NV + i] = acc[i];
+  }
+  __syncthreads();
+  if (m.r == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 s = s_red[m.g * NV + i];
+      for (int rr = 1; rr < m.rows; ++rr) {
+        const float4 v = s_red[(rr * C4 + m.g) * NV + i];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      reinterpret_cast<float4*>(partial_row)[i * C4 + m.g] = s;
+    }
+  }
+}
+
+// ---- forward, column statistics of z (fp32 FFMA path only; the TC kernel fuses this) -----
+__global__ void __launch_bounds__(kEwThreads)
+    gate_colstats_kernel(const float* __restrict__ z, int64_t M, int C4, float* __restrict__ partial) {
+  const EwMap m = ew_map(C4);
+  float4 acc[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
+  if (m.active) {
+    for (int64_t p = (int64_t)blockIdx.x * m.rows + m.r; p < M; p += (int64_t)gridDim.x * m.rows) {
+      const float4 v = ld4(z, p * C4 + m.g);
+      acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+      acc[1].x = fmaf(v.x, v.x, acc[1].x); acc[1].y = fmaf(v.y, v.y, acc[1].y);
+      acc[1].z = fmaf(v.z, v.z, acc[1].z); acc[1].w = fmaf(v.w, v.w, acc[1].w);
+    }
+  }
+  ew_block_reduce<2>(acc, m, C4, partial + (int64_t)blockIdx.x * 8 * C4);
+}
+
+// partial [nparts][2][N] -> mean, invstd, coefA/B, running statistics (nn.BatchNorm2d rules:
+// biased variance normalises, unbiased variance feeds running_var)
+__global__ void gate_fwd_stats_finalize(const float* __restrict__ partial, int nparts, int64_t M, int N,
+                                        float eps, float momentum, int training,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        float* __restrict__ running_mean, float* __restrict__ running_var,
+                                        float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                        float* __restrict__ coefA, float* __restrict__ coefB,
+                                        float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  double mean, var;
+  if (training) {
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < nparts; ++k) {
+      s += (double)partial[(int64_t)k * 2 * N + c];
+      q += (double)partial[(int64_t)k * 2 * N + N + c];
+    }
+    mean = s / (double)M;
+    var = q / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    if (running_mean) running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+    if (running_var) {
+      const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+      running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const double inv = 1.0 / sqrt(var + (double)eps);
+  const double a = (double)gamma[c] * inv;
+  mean_out[c] = (float)mean;
+  invstd_out[c] = (float)inv;
+  coefA[c] = (float)a;
+  coefB[c] = (float)((double)beta[c] - mean * a);
+  if (save_mean) save_mean[c] = (float)mean;
+  if (save_invstd) save_invstd[c] = (float)inv;
+}
+
+// ---- forward phase 2: y = s * sigmoid(A*z + B) ------------------------------------------
+__device__ __forceinline__ float4 gate_act(const float4& z, const float4& A, const float4& B) {
+  return make_float4(sigmoidf_acc(fmaf(A.x, z.x, B.x)), sigmoidf_acc(fmaf(A.y, z.y, B.y)),
+                     sigmoidf_acc(fmaf(A.z, z.z, B.z)), sigmoidf_acc(fmaf(A.w, z.w, B.w)));
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+    gate_apply_kernel(const float* __restrict__ z, const float* __restrict__ s, int64_t M, int C4,
+                      const float* __restrict__ coefA, const float* __restrict__ coefB,
+                      float* __restrict__ y) {
+  const EwMap m = ew_map(C4);
+  if (!m.active) return;
+  const float4 A = ldc4(coefA, m.g), B = ldc4(coefB, m.g);
+  const int64_t step = (int64_t)gridDim.x * m.rows;
+  int64_t p = (int64_t)blockIdx.x * m.rows + m.r;
+  for (; p + step < M; p += 2 * step) {
+    const int64_t i0 = p * C4 + m.g, i1 = (p + step) * C4 + m.g;
+    const float4 z0 = ld4(z, i0), s0 = ld4(s, i0), z1 = ld4(z, i1), s1 = ld4(s, i1);
+    const float4 a0 = gate_act(z0, A, B), a1 = gate_act(z1, A, B);
+    st4(y, i0, make_float4(s0.x * a0.x, s0.y * a0.y, s0.z * a0.z, s0.w * a0.w));
+    st4(y, i1, make_float4(s1.x * a1.x, s1.y * a1.y, s1.z * a1.z, s1.w * a1.w));
+  }
+  for (; p < M; p += step) {
+    const int64_t i0 = p * C4 + m.g;
+    const float4 z0 = ld4(z, i0), s0 = ld4(s, i0);
+    const float4 a0 = gate_act(z0, A, B);
+    st4(y, i0, make_float4(s0.x * a0.x, s0.y * a0.y, s0.z * a0.z, s0.w * a0.w));
+  }
+}
+
+// ---- backward phase A: ds, sum du, sum du*zhat -------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+    gate_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ s,
+                          const float* __restrict__ z, int64_t M, int C4,
+                          const float* __restrict__ coefA, const float* __restrict__ coefB,
+                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                          float* __restrict__ ds, float* __restrict__ partial) {
+  const EwMap m = ew_map(C4);
+  float4 acc[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
+  if (m.active) {
+    const float4 A = ldc4(coefA, m.g), B = ldc4(coefB, m.g), mu = ldc4(mean, m.g), rs = ldc4(invstd, m.g);
+    for (int64_t p = (int64_t)blockIdx.x * m.rows + m.r; p < M; p += (int64_t)gridDim.x * m.rows) {
+      const int64_t i = p * C4 + m.g;
+      const float4 g = ld4(dy, i), sv = ld4(s, i), zv = ld4(z, i);
+      const float4 a = gate_act(zv, A, B);
+      if (ds) st4(ds, i, make_float4(g.x * a.x, g.y * a.y, g.z * a.z, g.w * a.w));
+      const float dux = g.x * sv.x * a.x * (1.f - a.x), duy = g.y * sv.y * a.y * (1.f - a.y);
+      const float duz = g.z * sv.z * a.z * (1.f - a.z), duw = g.w * sv.w * a.w * (1.f - a.w);
+      acc[0].x += dux; acc[0].y += duy; acc[0].z += duz; acc[0].w += duw;
+      acc[1].x = fmaf(dux, (zv.x - mu.x) * rs.x, acc[1].x);
+      acc[1].y = fmaf(duy, (zv.y - mu.y) * rs.y, acc[1].y);
+      acc[1].z = fmaf(duz, (zv.z - mu.z) * rs.z, acc[1].z);
+      acc[1].w = fmaf(duw, (zv.w - mu.w) * rs.w, acc[1].w);
+    }
+  }
+  ew_block_reduce<2>(acc, m, C4, partial + (int64_t)blockIdx.x * 8 * C4);
+}
+
+__global__ void gate_bwd_stats_finalize(const float* __restrict__ partial, int nparts, int64_t M, int N,
+                                        int training, float* __restrict__ dgamma,
+                                        float* __restrict__ dbeta, float* __restrict__ c1,
+                                        float* __restrict__ c2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  double sb = 0.0, sg = 0.0;
+  for (int k = 0; k < nparts; ++k) {
+    sb += (double)partial[(int64_t)k * 2 * N + c];
+    sg += (double)partial[(int64_t)k * 2 * N + N + c];
+  }
+  dbeta[c] = (float)sb;
+  dgamma[c] = (float)sg;
+  c1[c] = training ? (float)(sb / (double)M) : 0.f;
+  c2[c] = training ? (float)(sg / (double)M) : 0.f;
+}
+
+// ---- backward: materialise dz (fp32 FFMA path) + db partials ------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+    gate_bwd_dz_kernel(const float* __restrict__ dy, const float* __restrict__ s,
+                       const float* __restrict__ z, int64_t M, int C4, const float* __restrict__ coefA,
+                       const float* __restrict__ coefB, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, const float* __restrict__ c1,
+                       const float* __restrict__ c2, float* __restrict__ dz,
+                       float* __restrict__ partial) {
+  const EwMap m = ew_map(C4);
+  float4 acc[1] = {make_float4(0, 0, 0, 0)};
+  if (m.active) {
+    const float4 A = ldc4(coefA, m.g), B = ldc4(coefB, m.g), mu = ldc4(mean, m.g), rs = ldc4(invstd, m.g);
+    const float4 k1 = ldc4(c1, m.g), k2 = ldc4(c2, m.g);
+    for (int64_t p = (int64_t)blockIdx.x * m.rows + m.r; p < M; p += (int64_t)gridDim.x * m.rows) {
+      const int64_t i = p * C4 + m.g;
+      const float4 g = ld4(dy, i), sv = ld4(s, i), zv = ld4(z, i);
+      const float4 a = gate_act(zv, A, B);
+      float4 d;
+      d.x = A.x * (g.x * sv.x * a.x * (1.f - a.x) - k1.x - (zv.x - mu.x) * rs.x * k2.x);
+      d.y = A.y * (g.y * sv.y * a.y * (1.f - a.y) - k1.y - (zv.y - mu.y) * rs.y * k2.y);
+      d.z = A.z * (g.z * sv.z * a.z * (1.f - a.z) - k1.z - (zv.z - mu.z) * rs.z * k2.z);
+      d.w = A.w * (g.w * sv.w * a.w * (1.f - a.w) - k1.w - (zv.w - mu.w) * rs.w * k2.w);
+      st4(dz, i, d);
+      acc[0].x += d.x; acc[0].y += d.y; acc[0].z += d.z; acc[0].w += d.w;
+    }
+  }
+  ew_block_reduce<1>(acc, m, C4, partial + (int64_t)blockIdx.x * 4 * C4);
+}
+
+// out[j] = fixed-order fp64 sum over nparts rows of length `len`
+__global__ void rows_sum_finalize(const float* __restrict__ partial, int nparts, int len,
+                                  float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= len) return;
+  double s = 0.0;
+  for (int k = 0; k < nparts; ++k) s += (double)partial[(int64_t)k * len + j];
+  out[j] = (float)s;
+}
+
+// ---- fp32 CUDA-core contraction (VMTL_GATE_FP32_FFMA) --------------------------------------
+// C[i][j] = sum_k A(i,k) * B(k,j) (+ bias[j]);  A(i,k) = A[i*lai + k*lak], B(k,j) = B[k*lbk + j*lbj].
+// 64x64 tile, 16-deep k slices, 4x4 register tile per thread.  gridDim.z > 1: split-K, each
+// z-slice writes its own [Mdim x ldc] partial at C + z*slice_stride.
+__global__ void __launch_bounds__(256)
+    sgemm64_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                   const float* __restrict__ bias, int64_t Mdim, int Ndim, int64_t Kdim, int64_t lai,
+                   int64_t lak, int64_t lbk, int64_t lbj, int ldc, int64_t kchunk,
+                   int64_t slice_stride) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t i0 = (int64_t)blockIdx.x * 64;
+  const int j0 = blockIdx.y * 64;
+  const int64_t kbeg = (int64_t)blockIdx.z * kchunk;
+  const int64_t kend = kbeg + kchunk < Kdim ? kbeg + kchunk : Kdim;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  // loader mapping: make the unit-stride dimension run across consecutive threads
+  const bool a_k_fast = (lak == 1);
+  const bool b_j_fast = (lbj == 1);
+  for (int64_t k0 = kbeg; k0 < kend; k0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int lin = threadIdx.x + e * 256;  // 0..1023
+      int ai, ak;
+      if (a_k_fast) { ak = lin & 15; ai = lin >> 4; } else { ai = lin & 63; ak = lin >> 6; }
+      const int64_t gi = i0 + ai, gk = k0 + ak;
+      As[ak][ai] = (gi < Mdim && gk < kend) ? A[gi * lai + gk * lak] : 0.f;
+      int bj, bk;
+      if (b_j_fast) { bj = lin & 63; bk = lin >> 6; } else { bk = lin & 15; bj = lin >> 4; }
+      const int gj = j0 + bj;
+      const int64_t gk2 = k0 + bk;
+      Bs[bk][bj] = (gj < Ndim && gk2 < kend) ? B[gk2 * lbk + (int64_t)gj * lbj] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a4[4] = {av.x, av.y, av.z, av.w};
+      const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], b4[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+  float* Cz = C + (int64_t)blockIdx.z * slice_stride;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int64_t gi = i0 + ty * 4 + a;
+    if (gi >= Mdim) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int gj = j0 + tx * 4 + b;
+      if (gj < Ndim) Cz[gi * ldc + gj] = acc[a][b] + (bias ? bias[gj] : 0.f);
+    }
+  }
+}
+
+static int sgemm64(const float* A, const float* B, float* C, const float* bias, int64_t Mdim, int Ndim,
+                   int64_t Kdim, int64_t lai, int64_t lak, int64_t lbk, int64_t lbj, int ldc, int splits,
+                   int64_t slice_stride, cudaStream_t st) {
+  dim3 grid((unsigned)((Mdim + 63) / 64), (unsigned)((Ndim + 63) / 64), (unsigned)splits);
+  int64_t kchunk = (Kdim + splits - 1) / splits;
+  kchunk = (kchunk + 15) / 16 * 16;
+  sgemm64_kernel<<<grid, 256, 0, st>>>(A, B, C, bias, Mdim, Ndim, Kdim, lai, lak, lbk, lbj, ldc, kchunk,
+                                       slice_stride);
+  return launch_status();
+}
+
+static int gate_check(int64_t M, int K, int N, int precision) {
+  if (M < 1 || K < 32 || N < 16) return VMTL_EINVAL;
+  if (K % 32 != 0 || K > 256 || N % 16 != 0 || N > 256) return VMTL_EUNSUPPORTED;
+  if (precision != VMTL_GATE_FP32_FFMA && precision != VMTL_GATE_TC_3XTF32 && precision != VMTL_GATE_TC_TF32)
+    return VMTL_EINVAL;
+  return VMTL_OK;
+}
+
+}  // namespace vmtl
+
+using namespace vmtl;
+
+extern "C" size_t vmtl_gate_workspace_bytes(int64_t M, int K, int N, int precision, int backward) {
+  if (gate_check(M, K, N, precision) != VMTL_OK) return 0;
+  return gate_ws_floats(M, K, N, precision, backward, nullptr, nullptr) * sizeof(float) + 256;
+}
+
+extern "C" int vmtl_gate_fwd(const float* h, const float* s, const float* W, const float* bias,
+                             const float* gamma, const float* beta, float* running_mean,
+                             float* running_var, float momentum, float eps, int training, int precision,
+                             int64_t M, int K, int N, float* y, float* save_z, float* save_mean,
+                             float* save_invstd, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = gate_check(M, K, N, precision);
+  if (rc != VMTL_OK) return rc;
+  if (!h || !s || !W || !bias || !gamma || !beta || !y || !workspace) return VMTL_EINVAL;
+  if (training && !save_z) return VMTL_EINVAL;
+  if (!training && (!running_mean || !running_var)) return VMTL_EINVAL;
+  if (!aligned16(h) || !aligned16(s) || !aligned16(W) || !aligned16(y) || !aligned16(workspace) ||
+      (save_z && !aligned16(save_z)))
+    return VMTL_EALIGN;
+  GateWs ws;
+  const size_t need = gate_ws_floats(M, K, N, precision, 0, &ws, static_cast<float*>(workspace));
+  if (workspace_bytes < need * sizeof(float)) return VMTL_EWORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C4 = N / 4;
+  const int split3 = precision == VMTL_GATE_TC_3XTF32;
+
+  if (!training) {
+    gate_fwd_stats_finalize<<<(N + 127) / 128, 128, 0, st>>>(nullptr, 0, M, N, eps, momentum, 0, gamma,
+                                                             beta, running_mean, running_var, ws.mean,
+                                                             ws.invstd, ws.coefA, ws.coefB, save_mean,
+                                                             save_invstd);
+    if ((rc = launch_status()) != VMTL_OK) return rc;
+    if (precision != VMTL_GATE_FP32_FFMA)
+      return gate_tc_fwd_eval(h, s, W, bias, ws.coefA, ws.coefB, M, K, N, split3, y, st);
+    if (!save_z) return VMTL_EINVAL;  // the CUDA-core path needs a z buffer even in eval mode
+    float* zbuf = save_z;
+    rc = sgemm64(h, W, zbuf, bias, M, N, K, K, 1, 1, K, N, 1, 0, st);
+    if (rc != VMTL_OK) return rc;
+    gate_apply_kernel<<<ew_grid(M, N), kEwThreads, 0, st>>>(zbuf, s, M, C4, ws.coefA, ws.coefB, y);
+    return launch_status();
+  }
+
+  int nparts = 0;
+  if (precision != VMTL_GATE_FP32_FFMA) {
+    rc = gate_tc_fwd_gemm(h, W, bias, M, K, N, split3, save_z, ws.partial, ws.partial_rows, &nparts, st);
+    if (rc != VMTL_OK) return rc;
+  } else {
+    rc = sgemm64(h, W, save_z, bias, M, N, K, K, 1, 1, K, N, 1, 0, st);
+    if (rc != VMTL_OK) return rc;
+    nparts = ew_grid(M, N);
+    gate_colstats_kernel<<<nparts, kEwThreads, 0, st>>>(save_z, M, C4, ws.partial);
+    if ((rc = launch_status()) != VMTL_OK) return rc;
+  }
+  gate_fwd_stats_finalize<<<(N + 127) / 128, 128, 0, st>>>(ws.partial, nparts, M, N, eps, momentum, 1,
+                                                           gamma, beta, running_mean, running_var,
+                                                           ws.mean, ws.invstd, ws.coefA, ws.coefB,
+                                                           save_mean, save_invstd);
+  if ((rc = launch_status()) != VMTL_OK) return rc;
+  gate_apply_kernel<<<ew_grid(M, N), kEwThreads, 0, st>>>(save_z, s, M, C4, ws.coefA, ws.coefB, y);
+  return launch_status();
+}
+
+// coefA/B from saved statistics (backward re-derives them instead of trusting workspace reuse)
+__global__ void gate_coef_from_saved(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     int N, float* __restrict__ coefA, float* __restrict__ coefB,
+                                     float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  const float a = gamma[c] * invstd[c];
+  coefA[c] = a;
+  coefB[c] = beta[c] - mean[c] * a;
+  mean_out[c] = mean[c];
+  invstd_out[c] = invstd[c];
+}
+
+extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, const float* z,
+                             const float* W, const float* gamma, const float* beta,
+                             const float* save_mean, const float* save_invstd, int training,
+                             int precision, int64_t M, int K, int N, float* dh, float* ds, float* dW,
+                             float* dbias, float* dgamma, float* dbeta, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  int rc = gate_check(M, K, N, precision);
+  if (rc != VMTL_OK) return rc;
+  if (!dy || !h || !s || !z || !W || !gamma || !beta || !save_mean || !save_invstd || !dW || !dbias ||
+      !dgamma || !dbeta || !workspace)
+    return VMTL_EINVAL;
+  if (!aligned16(dy) || !aligned16(h) || !aligned16(s) || !aligned16(z) || !aligned16(W) ||
+      !aligned16(workspace) || (dh && !aligned16(dh)) || (ds && !aligned16(ds)))
+    return VMTL_EALIGN;
+  GateWs ws;
+  const size_t need = gate_ws_floats(M, K, N, precision, 1, &ws, static_cast<float*>(workspace));
+  if (workspace_bytes < need * sizeof(float)) return VMTL_EWORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C4 = N / 4;
+  const int split3 = precision == VMTL_GATE_TC_3XTF32;
+
+  gate_coef_from_saved<<<(N + 127) / 128, 128, 0, st>>>(gamma, beta, save_mean, save_invstd, N, ws.coefA,
+                                                        ws.coefB, ws.mean, ws.invstd);
+  if ((rc = launch_status()) != VMTL_OK) return rc;
+  // phase A
+  const int nparts = ew_grid(M, N);
+  gate_bwd_stats_kernel<<<nparts, kEwThreads, 0, st>>>(dy, s, z, M, C4, ws.coefA, ws.coefB, ws.mean,
+                                                       ws.invstd, ds, ws.partial);
+  if ((rc = launch_status()) != VMTL_OK) return rc;
+  gate_bwd_stats_finalize<<<(N + 127) / 128, 128, 0, st>>>(ws.partial, nparts, M, N, training, dgamma,
+                                                           dbeta, ws.c1, ws.c2);
+  if ((rc = launch_status()) != VMTL_OK) return rc;
+
+  // phase B
+  if (precision != VMTL_GATE_FP32_FFMA) {
+    int nslots = 0;
+    // db partials reuse ws.partial (phase A has been consumed by the finalize above)
+    rc = gate_tc_bwd_gemm(dy, h, s, z, W, ws, gamma, M, K, N, split3, dh, ws.gemm_partial, ws.gemm_slots,
+                          &nslots, ws.partial, st);
+    if (rc != VMTL_OK) return rc;
+    rows_sum_finalize<<<(N * K + 127) / 128, 128, 0, st>>>(ws.gemm_partial, nslots, N * K, dW);
+    if ((rc = launch_status()) != VMTL_OK) return rc;
+    rows_sum_finalize<<<(N + 127) / 128, 128, 0, st>>>(ws.partial, nslots, N, dbias);
+    return launch_status();
+  }
+  gate_bwd_dz_kernel<<<nparts, kEwThreads, 0, st>>>(dy, s, z, M, C4, ws.coefA, ws.coefB, ws.mean,
+                                                    ws.invstd, ws.c1, ws.c2, ws.dz, ws.partial);
+  if ((rc = launch_status()) != VMTL_OK) return rc;
+  rows_sum_finalize<<<(N + 127) / 128, 128, 0, st>>>(ws.partial, nparts, N, dbias);
+  if ((rc = launch_status()) != VMTL_OK) return rc;
+  if (dh) {
+    // dh[M,K] = dz[M,N] @ W[N,K]
+    rc = sgemm64(ws.dz, W, dh, nullptr, M, K, N, N, 1, K, 1, K, 1, 0, st);
+    if (rc != VMTL_OK) return rc;
+  }
+  // dW[N,K] = dz^T[N,M] @ h[M,K]   (split-K over M, fixed-order second stage)
+  int splits = ws.gemm_slots;
+  const int64_t max_splits = (M + 255) / 256;
+  if (splits > max_splits) splits = (int)max_splits;
+  const int tiles = ((N + 63) / 64) * ((K + 63) / 64);
+  int per = (sm_count() * 2) / tiles;
+  if (per < 1) per = 1;
+  if (splits > per) splits = per;
+  rc = sgemm64(ws.dz, h, ws.gemm_partial, nullptr, N, K, M, 1, N, K, 1, K, splits, (int64_t)N * K, st);
+  if (rc != VMTL_OK) return rc;
+  rows_sum_finalize<<<(N * K + 127) / 128, 128, 0, st>>>(ws.gemm_partial, splits, N * K, dW);
+  return launch_status();
+}

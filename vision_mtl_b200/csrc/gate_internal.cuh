@@ -1,0 +1,65 @@
+// Internal interface between gate.cu (entry points, streaming kernels, fp32 FFMA GEMM) and
+// gate_tc.cu (tcgen05 / TMEM contraction kernels).
+#pragma once
+
+#include "vmtl_common.cuh"
+
+namespace vmtl {
+
+// Caller-provided workspace, carved identically by every gate entry point.
+struct GateWs {
+  float* coefA;  // [N] gamma*invstd
+  float* coefB;  // [N] beta - mean*gamma*invstd
+  float* c1;     // [N] dbeta/M   (train) or 0 (eval)
+  float* c2;     // [N] dgamma/M  (train) or 0 (eval)
+  float* mean;   // [N] statistics used for normalisation (batch or running)
+  float* invstd; // [N]
+  float* partial;       // [partial_rows][2N] per-block column partials
+  int partial_rows;
+  float* gemm_partial;  // [gemm_slots][N*K] split-K / per-CTA dW partials
+  int gemm_slots;
+  float* dz;            // [M,N] (fp32 FFMA backward only)
+};
+
+inline size_t gate_ws_floats(int64_t M, int K, int N, int precision, int backward, GateWs* ws,
+                             float* base) {
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    float* p = base ? base + off : nullptr;
+    off += (n + 63) / 64 * 64;  // keep every region 256-byte aligned
+    return p;
+  };
+  GateWs w{};
+  w.coefA = take(N);
+  w.coefB = take(N);
+  w.c1 = take(N);
+  w.c2 = take(N);
+  w.mean = take(N);
+  w.invstd = take(N);
+  w.partial_rows = sm_count() * 8;
+  w.partial = take((size_t)w.partial_rows * 2 * N);
+  w.gemm_slots = backward ? sm_count() * 2 : 0;
+  w.gemm_partial = take((size_t)w.gemm_slots * N * K);
+  w.dz = (backward && precision == VMTL_GATE_FP32_FFMA) ? take((size_t)M * N) : nullptr;
+  if (ws) *ws = w;
+  return off;
+}
+
+// tcgen05 kernels (gate_tc.cu).  Return VMTL_EUNSUPPORTED for shapes they do not cover.
+// Forward phase 1: z = h @ W^T + bias -> save_z, per-CTA column partials (sum, sumsq) into
+// ws.partial rows [0, *nparts).  EVAL variant applies the folded BN + sigmoid + product
+// directly and writes y.
+int gate_tc_fwd_gemm(const float* h, const float* W, const float* bias, int64_t M, int K, int N,
+                     int split3, float* z_out, float* partial, int partial_rows, int* nparts,
+                     cudaStream_t st);
+int gate_tc_fwd_eval(const float* h, const float* s, const float* W, const float* bias,
+                     const float* coefA, const float* coefB, int64_t M, int K, int N, int split3,
+                     float* y, cudaStream_t st);
+// Backward phase B: dz recomputed per tile from (dy, s, z); dh = dz @ W ; dW partial per CTA;
+// db partial per CTA.
+int gate_tc_bwd_gemm(const float* dy, const float* h, const float* s, const float* z, const float* W,
+                     const GateWs& ws, const float* gamma, int64_t M, int K, int N, int split3,
+                     float* dh, float* dw_partial, int slots, int* nslots, float* db_partial,
+                     cudaStream_t st);
+
+}  // namespace vmtl

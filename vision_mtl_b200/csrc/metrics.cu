@@ -1,0 +1,268 @@
+// Validation reductions: integer confusion matrix, depth error sums, derived seg metrics.
+//
+// Replaces the torchmetrics 0.7.3 forward() calls at vision_mtl/lit_module.py:106-118
+// (Accuracy / JaccardIndex / FBetaScore / MeanAbsoluteError, configured at :48-69), which
+// one-hot expand preds and targets (1.9 GB of traffic at B=32) to derive statistics that are
+// all functions of one C x C integer matrix.
+//
+// confusion_accum : algorithmic bytes = P*(8 + 8) (int64 pred) or P*(1 + 8) (uint8 pred).
+//                   per-warp shared-memory histograms (uint32) -> int64 global atomics.
+//                   Integer arithmetic only: bit-exact and order independent.
+// depth_err_sums  : algorithmic bytes = P*8.  fp64 accumulation, fixed-order 2-stage sum.
+#include "vmtl_common.cuh"
+
+namespace vmtl {
+
+constexpr int kConfThreads = 256;
+constexpr int kConfWarps = kConfThreads / 32;
+
+__device__ __forceinline__ void conf_count(unsigned int* hist, int64_t t, int64_t p, int C,
+                                           int64_t ignore_index) {
+  if (t != ignore_index && (uint64_t)t < (uint64_t)C && (uint64_t)p < (uint64_t)C)
+    atomicAdd(&hist[(int)t * C + (int)p], 1u);
+}
+
+template <bool U8>
+__global__ void __launch_bounds__(kConfThreads)
+    confusion_kernel(const void* __restrict__ pred_v, const int64_t* __restrict__ target, int64_t P,
+                     int C, int64_t ignore_index, unsigned long long* __restrict__ conf,
+                     int nhist) {
+  extern __shared__ unsigned int s_hist[];  // [nhist][C*C]
+  const int CC = C * C;
+  for (int i = threadIdx.x; i < nhist * CC; i += blockDim.x) s_hist[i] = 0u;
+  __syncthreads();
+  unsigned int* hist = s_hist + ((threadIdx.x >> 5) % nhist) * CC;
+
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+  if (U8) {
+    const uint8_t* pred = static_cast<const uint8_t*>(pred_v);
+    const bool vec = (((uintptr_t)pred | (uintptr_t)target) & 15u) == 0;
+    int64_t done = 0;
+    if (vec) {
+      const int64_t n16 = P / 16;
+      const uint4* p16 = reinterpret_cast<const uint4*>(pred);
+      const longlong2* t2 = reinterpret_cast<const longlong2*>(target);
+      for (int64_t i = tid; i < n16; i += nthr) {
+        uint4 pv = __ldg(p16 + i);
+        longlong2 tv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tv[k] = ldg_stream(t2 + i * 8 + k);
+        const unsigned int pw[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const unsigned int word = pw[k >> 1];
+          const int sh = (k & 1) * 16;
+          conf_count(hist, tv[k].x, (word >> sh) & 0xffu, C, ignore_index);
+          conf_count(hist, tv[k].y, (word >> (sh + 8)) & 0xffu, C, ignore_index);
+        }
+      }
+      done = n16 * 16;
+    }
+    for (int64_t i = done + tid; i < P; i += nthr)
+      conf_count(hist, target[i], pred[i], C, ignore_index);
+  } else {
+    const int64_t* pred = static_cast<const int64_t*>(pred_v);
+    const bool vec = (((uintptr_t)pred | (uintptr_t)target) & 15u) == 0;
+    int64_t done = 0;
+    if (vec) {
+      const int64_t n2 = P / 2;
+      const longlong2* p2 = reinterpret_cast<const longlong2*>(pred);
+      const longlong2* t2 = reinterpret_cast<const longlong2*>(target);
+      int64_t i = tid;
+      for (; i + 3 * nthr < n2; i += 4 * nthr) {
+        longlong2 pv[4], tv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          pv[k] = ldg_stream(p2 + i + k * nthr);
+          tv[k] = ldg_stream(t2 + i + k * nthr);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          conf_count(hist, tv[k].x, pv[k].x, C, ignore_index);
+          conf_count(hist, tv[k].y, pv[k].y, C, ignore_index);
+        }
+      }
+      for (; i < n2; i += nthr) {
+        longlong2 pv = ldg_stream(p2 + i), tv = ldg_stream(t2 + i);
+        conf_count(hist, tv.x, pv.x, C, ignore_index);
+        conf_count(hist, tv.y, pv.y, C, ignore_index);
+      }
+      done = n2 * 2;
+    }
+    for (int64_t i = done + tid; i < P; i += nthr)
+      conf_count(hist, target[i], pred[i], C, ignore_index);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CC; i += blockDim.x) {
+    unsigned long long s = 0;
+    for (int h = 0; h < nhist; ++h) s += s_hist[h * CC + i];
+    if (s) atomicAdd(conf + i, s);
+  }
+}
+
+// ---- depth error sums -------------------------------------------------------------------
+__device__ __forceinline__ void derr_acc(float p, float t, float min_depth, double& sabs,
+                                         double& nval, double& srel) {
+  const float d = fabsf(p - t);
+  sabs += (double)d;
+  if (t > min_depth) {
+    nval += 1.0;
+    srel += (double)(d / t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    depth_err_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t P,
+                     float min_depth, double* __restrict__ partial) {
+  double sabs = 0.0, nval = 0.0, srel = 0.0;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+  const bool vec = (((uintptr_t)pred | (uintptr_t)target) & 15u) == 0;
+  int64_t done = 0;
+  if (vec) {
+    const int64_t n4 = P / 4;
+    const float4* p4 = reinterpret_cast<const float4*>(pred);
+    const float4* t4 = reinterpret_cast<const float4*>(target);
+    int64_t i = tid;
+    for (; i + nthr < n4; i += 2 * nthr) {
+      float4 a0 = ldg_stream(p4 + i), b0 = ldg_stream(t4 + i);
+      float4 a1 = ldg_stream(p4 + i + nthr), b1 = ldg_stream(t4 + i + nthr);
+      derr_acc(a0.x, b0.x, min_depth, sabs, nval, srel);
+      derr_acc(a0.y, b0.y, min_depth, sabs, nval, srel);
+      derr_acc(a0.z, b0.z, min_depth, sabs, nval, srel);
+      derr_acc(a0.w, b0.w, min_depth, sabs, nval, srel);
+      derr_acc(a1.x, b1.x, min_depth, sabs, nval, srel);
+      derr_acc(a1.y, b1.y, min_depth, sabs, nval, srel);
+      derr_acc(a1.z, b1.z, min_depth, sabs, nval, srel);
+      derr_acc(a1.w, b1.w, min_depth, sabs, nval, srel);
+    }
+    for (; i < n4; i += nthr) {
+      float4 a0 = ldg_stream(p4 + i), b0 = ldg_stream(t4 + i);
+      derr_acc(a0.x, b0.x, min_depth, sabs, nval, srel);
+      derr_acc(a0.y, b0.y, min_depth, sabs, nval, srel);
+      derr_acc(a0.z, b0.z, min_depth, sabs, nval, srel);
+      derr_acc(a0.w, b0.w, min_depth, sabs, nval, srel);
+    }
+    done = n4 * 4;
+  }
+  for (int64_t i = done + tid; i < P; i += nthr) derr_acc(pred[i], target[i], min_depth, sabs, nval, srel);
+
+  __shared__ double s_w[3][8];
+  sabs = warp_sum(sabs);
+  nval = warp_sum(nval);
+  srel = warp_sum(srel);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    s_w[0][warp] = sabs;
+    s_w[1][warp] = nval;
+    s_w[2][warp] = srel;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += s_w[threadIdx.x][w];
+    partial[(int64_t)blockIdx.x * 3 + threadIdx.x] = s;
+  }
+}
+
+__global__ void depth_err_finalize(const double* __restrict__ partial, int nblocks, int64_t P,
+                                   double* __restrict__ out) {
+  // one warp; lane k<3 sums column k in fixed order
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * 3 + threadIdx.x];
+    if (threadIdx.x == 0) {
+      out[0] = (double)P;
+      out[1] = s;
+    } else if (threadIdx.x == 1) {
+      out[2] = s;
+    } else {
+      out[3] = s;
+    }
+  }
+}
+
+// ---- derived segmentation metrics -----------------------------------
+__global__ void seg_metrics_kernel(const long long* __restrict__ conf, int C, float* __restrict__ m) {
+  __shared__ double s_tp[64], s_row[64], s_col[64];
+  const int c = threadIdx.x;
+  if (c < C) {
+    double row = 0.0, col = 0.0;
+    for (int k = 0; k < C; ++k) {
+      row += (double)conf[c * C + k];
+      col += (double)conf[k * C + c];
+    }
+    s_tp[c] = (double)conf[c * C + c];
+    s_row[c] = row;
+    s_col[c] = col;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double total = 0.0, tp_sum = 0.0, iou_sum = 0.0, f_w = 0.0;
+    for (int k = 0; k < C; ++k) {
+      const double tp = s_tp[k], row = s_row[k], col = s_col[k];
+      total += row;
+      tp_sum += tp;
+      const double uni = row + col - tp;
+      iou_sum += uni > 0.0 ? tp / uni : 0.0;
+      const double den = row + col;  // 2tp + fn + fp
+      const double f1 = den > 0.0 ? 2.0 * tp / den : 0.0;
+      f_w += f1 * row;
+    }
+    m[0] = (float)(tp_sum / total);
+    m[1] = (float)(iou_sum / (double)C);
+    m[2] = (float)(f_w / total);
+  }
+}
+
+}  // namespace vmtl
+
+using namespace vmtl;
+
+extern "C" int vmtl_confusion_accum(const void* pred, int pred_is_u8, const int64_t* target, int64_t P,
+                                    int C, int64_t ignore_index, int64_t* conf, void* stream) {
+  if (!pred || !target || !conf || P < 0 || C < 1) return VMTL_EINVAL;
+  if (C > 64 || (pred_is_u8 && C > 256)) return VMTL_EUNSUPPORTED;
+  if (P == 0) return VMTL_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int CC = C * C;
+  int nhist = kConfWarps;
+  while (nhist > 1 && (size_t)nhist * CC * sizeof(unsigned int) > 40 * 1024) nhist >>= 1;
+  const size_t smem = (size_t)nhist * CC * sizeof(unsigned int);
+  const int per_thread = pred_is_u8 ? 16 : 8;
+  int64_t want = (P + (int64_t)kConfThreads * per_thread - 1) / ((int64_t)kConfThreads * per_thread);
+  int64_t cap = (int64_t)sm_count() * 4;
+  const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+  unsigned long long* c = reinterpret_cast<unsigned long long*>(conf);
+  if (pred_is_u8)
+    confusion_kernel<true><<<grid, kConfThreads, smem, st>>>(pred, target, P, C, ignore_index, c, nhist);
+  else
+    confusion_kernel<false><<<grid, kConfThreads, smem, st>>>(pred, target, P, C, ignore_index, c, nhist);
+  return launch_status();
+}
+
+extern "C" int vmtl_depth_err_sums(const float* pred, const float* target, int64_t P, float min_depth,
+                                   double* out, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  if (!pred || !target || !out || !workspace || P < 0) return VMTL_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t want = (P + 256 * 8 - 1) / (256 * 8);
+  int64_t cap = (int64_t)sm_count() * 4;
+  const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+  if (workspace_bytes < (size_t)grid * 3 * sizeof(double)) return VMTL_EWORKSPACE;
+  double* partial = static_cast<double*>(workspace);
+  depth_err_kernel<<<grid, 256, 0, st>>>(pred, target, P, min_depth, partial);
+  int rc = launch_status();
+  if (rc != VMTL_OK) return rc;
+  depth_err_finalize<<<1, 32, 0, st>>>(partial, grid, P, out);
+  return launch_status();
+}
+
+extern "C" int vmtl_seg_metrics(const int64_t* conf, int C, float* metrics, void* stream) {
+  if (!conf || !metrics || C < 1) return VMTL_EINVAL;
+  if (C > 64) return VMTL_EUNSUPPORTED;
+  seg_metrics_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(conf), C, metrics);
+  return launch_status();
+}

@@ -1,0 +1,419 @@
+// Cross-stitch unit, forward and backward, NHWC float4 streaming kernels.
+//
+// Replaces torch.stack + torch.einsum("aa(c),abcij->abcij") and its autograd backward
+// (reference: vision_mtl/models/cross_stitch_model.py:32-37, call site :143-156).
+//
+// Data layout: T task feature maps, each a row-major [npix, C] fp32 matrix (NHWC), read
+// through T separate pointers -- the [T,B,C,H,W] stack copy of the reference never exists.
+// Both kernels are pure HBM streams:
+//   fwd : 2*4*T*npix*C bytes (read x, write y)
+//   bwd : 3*4*T*npix*C bytes (read dy and x, write dx) + the alpha-gradient reduction,
+//         which is a per-thread register accumulation (each thread owns one float4 channel
+//         group for its whole life), a shared-memory / warp-shuffle block reduction and a
+//         fixed-order fp64 second stage -> deterministic.
+#include "vmtl_common.cuh"
+
+namespace vmtl {
+
+struct XsFwdArgs {
+  const float4* x[VMTL_MAX_TASKS];
+  float4* y[VMTL_MAX_TASKS];
+};
+struct XsBwdArgs {
+  const float4* dy[VMTL_MAX_TASKS];
+  const float4* x[VMTL_MAX_TASKS];
+  float4* dx[VMTL_MAX_TASKS];
+};
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4_mul(const float4& a, const float4& b) {
+  return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+}
+__device__ __forceinline__ void f4_fma(float4& acc, const float4& a, const float4& b) {
+  acc.x = fmaf(a.x, b.x, acc.x);
+  acc.y = fmaf(a.y, b.y, acc.y);
+  acc.z = fmaf(a.z, b.z, acc.z);
+  acc.w = fmaf(a.w, b.w, acc.w);
+}
+__device__ __forceinline__ float4 f4_splat(float v) { return make_float4(v, v, v, v); }
+
+// ------------------------------------------------------------------ forward
+template <int T, bool DIAG, bool CW>
+__global__ void __launch_bounds__(256)
+    xstitch_fwd_kernel(XsFwdArgs a, const float* __restrict__ alpha, int64_t n4, int C4) {
+  extern __shared__ float4 s_alpha[];  // CW: [T*T][C4]
+  float w[T][T];
+  if (CW) {
+    const float4* al4 = reinterpret_cast<const float4*>(alpha);
+    for (int i = threadIdx.x; i < T * T * C4; i += blockDim.x) s_alpha[i] = al4[i];
+    __syncthreads();
+  } else {
+#pragma unroll
+    for (int i = 0; i < T; ++i)
+#pragma unroll
+      for (int j = 0; j < T; ++j) w[i][j] = alpha[i * T + j];
+  }
+  constexpr int U = (T <= 2) ? 4 : (T <= 4 ? 2 : 1);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int c = (int)(i % C4);
+  const int cstep = (int)(stride % C4);
+
+  auto mix = [&](const float4 (&xin)[T], int cg, int64_t idx) {
+#pragma unroll
+    for (int o = 0; o < T; ++o) {
+      float4 r;
+      if (DIAG) {
+        r = CW ? f4_mul(s_alpha[(o * T + o) * C4 + cg], xin[o])
+               : f4_mul(f4_splat(w[o][o]), xin[o]);
+      } else {
+        r = f4_zero();
+#pragma unroll
+        for (int b = 0; b < T; ++b) {
+          if (CW)
+            f4_fma(r, s_alpha[(o * T + b) * C4 + cg], xin[b]);
+          else
+            f4_fma(r, f4_splat(w[o][b]), xin[b]);
+        }
+      }
+      stg_stream(a.y[o] + idx, r);
+    }
+  };
+
+  for (; i + (U - 1) * stride < n4; i += U * stride) {
+    float4 xin[U][T];
+    int cg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) xin[u][t] = ldg_stream(a.x[t] + i + u * stride);
+      cg[u] = c;
+      c += cstep;
+      if (c >= C4) c -= C4;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) mix(xin[u], cg[u], i + u * stride);
+  }
+  for (; i < n4; i += stride) {
+    float4 xin[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) xin[t] = ldg_stream(a.x[t] + i);
+    mix(xin, c, i);
+    c += cstep;
+    if (c >= C4) c -= C4;
+  }
+}
+
+// ------------------------------------------------------------------ backward
+// Thread layout: threadIdx.x = r*cgw + gl ; gl = float4 channel group inside this block's
+// channel slice (blockIdx.y selects the slice), r = pixel row inside one pass.  One pass
+// covers `rows` consecutive pixels -> rows*cgw consecutive float4 when the slice is the
+// whole channel range, i.e. fully coalesced 128-bit accesses.
+template <int T, bool DIAG, bool CW>
+__global__ void __launch_bounds__(512)
+    xstitch_bwd_kernel(XsBwdArgs a, const float* __restrict__ alpha, float* __restrict__ partial,
+                       int64_t npix, int C4, int cgw, int rows, int write_dx) {
+  constexpr int NACC = DIAG ? T : T * T;
+  extern __shared__ float4 s_red[];
+  const int t = threadIdx.x;
+  const int r = t / cgw;
+  const int gl = t - r * cgw;
+  const int g = blockIdx.y * cgw + gl;
+  const bool active = (r < rows) && (g < C4);
+
+  float4 w[T][T];
+#pragma unroll
+  for (int i = 0; i < T; ++i)
+#pragma unroll
+    for (int j = 0; j < T; ++j) {
+      if (CW) {
+        w[i][j] = active ? reinterpret_cast<const float4*>(alpha)[(i * T + j) * C4 + g] : f4_zero();
+      } else {
+        w[i][j] = f4_splat(alpha[i * T + j]);
+      }
+    }
+
+  float4 acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = f4_zero();
+
+  if (active) {
+    const int64_t pstep = (int64_t)gridDim.x * rows;
+    for (int64_t p = (int64_t)blockIdx.x * rows + r; p < npix; p += pstep) {
+      const int64_t idx = p * C4 + g;
+      float4 dy[T], xv[T];
+#pragma unroll
+      for (int i = 0; i < T; ++i) dy[i] = ldg_stream(a.dy[i] + idx);
+#pragma unroll
+      for (int i = 0; i < T; ++i) xv[i] = ldg_stream(a.x[i] + idx);
+      if (write_dx) {
+#pragma unroll
+        for (int b = 0; b < T; ++b) {
+          float4 d;
+          if (DIAG) {
+            d = f4_mul(w[b][b], dy[b]);
+          } else {
+            d = f4_zero();
+#pragma unroll
+            for (int o = 0; o < T; ++o) f4_fma(d, w[o][b], dy[o]);
+          }
+          stg_stream(a.dx[b] + idx, d);
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < T; ++o) {
+        if (DIAG) {
+          f4_fma(acc[o], dy[o], xv[o]);
+        } else {
+#pragma unroll
+          for (int b = 0; b < T; ++b) f4_fma(acc[o * T + b], dy[o], xv[b]);
+        }
+      }
+    }
+  }
+
+  if (CW) {
+    // block reduction over the `rows` threads that share a channel group
+    if (r < rows) {
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) s_red[(r * cgw + gl) * NACC + i] = acc[i];
+    }
+    __syncthreads();
+    if (r == 0 && g < C4) {
+      float4* out = reinterpret_cast<float4*>(partial) + (int64_t)blockIdx.x * NACC * C4;
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) {
+        float4 s = s_red[gl * NACC + i];
+        for (int rr = 1; rr < rows; ++rr) {
+          const float4 v = s_red[(rr * cgw + gl) * NACC + i];
+          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        out[i * C4 + g] = s;
+      }
+    }
+  } else {
+    // layer-wise alpha: every lane contributes to the same T*T scalars -> warp shuffles
+    float* s_f = reinterpret_cast<float*>(s_red);
+    const int warp = t >> 5, lane = t & 31, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+      float v = acc[i].x + acc[i].y + acc[i].z + acc[i].w;
+      v = warp_sum(v);
+      if (lane == 0) s_f[warp * NACC + i] = v;
+    }
+    __syncthreads();
+    if (t < NACC) {
+      float s = 0.f;
+      for (int wi = 0; wi < nwarp; ++wi) s += s_f[wi * NACC + t];
+      partial[(int64_t)blockIdx.x * NACC + t] = s;
+    }
+  }
+}
+
+// second stage: fixed-order fp64 sum over the per-block partials
+template <bool DIAG>
+__global__ void xstitch_dalpha_finalize(const float* __restrict__ partial, float* __restrict__ dalpha,
+                                        int nblocks, int T, int Cdim /* C or 1 */) {
+  const int n = T * T * Cdim;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int c = j % Cdim;
+  const int ab = j / Cdim;
+  const int o = ab / T, b = ab % T;
+  const int nacc = DIAG ? T : T * T;
+  int src;
+  if (DIAG) {
+    if (o != b) {
+      dalpha[j] = 0.f;  // exact zeros, as autograd gives for the reference einsum
+      return;
+    }
+    src = o * Cdim + c;
+  } else {
+    src = ab * Cdim + c;
+  }
+  double s = 0.0;
+  const int64_t rowlen = (int64_t)nacc * Cdim;
+  for (int k = 0; k < nblocks; ++k) s += (double)partial[k * rowlen + src];
+  dalpha[j] = (float)s;
+}
+
+struct XsBwdPlan {
+  int cgw, rows, nchunk, threads, gridx;
+  int64_t npix_eff;
+  int c4_eff;
+  size_t smem, partial_bytes;
+};
+
+static XsBwdPlan xs_bwd_plan(int T, int64_t npix, int C, int channel_wise, int mode) {
+  XsBwdPlan p;
+  const int nacc_max = T * T;
+  (void)mode;
+  if (channel_wise) {
+    p.c4_eff = C / 4;
+    p.npix_eff = npix;
+    const int target = 256;
+    if (p.c4_eff <= 512) {
+      p.cgw = p.c4_eff;
+      p.nchunk = 1;
+    } else {
+      p.nchunk = (p.c4_eff + 255) / 256;
+      p.cgw = (p.c4_eff + p.nchunk - 1) / p.nchunk;
+    }
+    p.rows = p.cgw >= target ? 1 : target / p.cgw;
+  } else {
+    // layer-wise alpha: the channel position is irrelevant, stream the flat float4 array
+    p.c4_eff = 1;
+    p.npix_eff = npix * (C / 4);
+    p.cgw = 1;
+    p.nchunk = 1;
+    p.rows = 256;
+  }
+  p.threads = ((p.rows * p.cgw + 31) / 32) * 32;
+  int64_t want = (p.npix_eff + p.rows - 1) / p.rows;
+  int64_t cap = (int64_t)sm_count() * (p.threads <= 256 ? 4 : 2);
+  if (T >= 3) cap = (int64_t)sm_count() * 2;
+  p.gridx = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+  p.smem = channel_wise ? (size_t)p.rows * p.cgw * nacc_max * sizeof(float4)
+                        : (size_t)(p.threads / 32) * nacc_max * sizeof(float);
+  p.partial_bytes = (size_t)p.gridx * nacc_max * (channel_wise ? C : 1) * sizeof(float);
+  return p;
+}
+
+template <int T>
+static int xs_fwd_launch(const XsFwdArgs& a, const float* alpha, int64_t n4, int C4, int cw,
+                         int mode, cudaStream_t st) {
+  const int threads = 256;
+  constexpr int U = (T <= 2) ? 4 : (T <= 4 ? 2 : 1);
+  int64_t want = (n4 + (int64_t)threads * U - 1) / ((int64_t)threads * U);
+  int64_t cap = (int64_t)sm_count() * 8;
+  int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+  size_t smem = cw ? (size_t)T * T * C4 * sizeof(float4) : 0;
+  if (smem > 160 * 1024) return VMTL_EUNSUPPORTED;
+#define VMTL_XS_FWD(DIAG, CWB)                                                                   \
+  do {                                                                                           \
+    if (smem > 48 * 1024)                                                                        \
+      cudaFuncSetAttribute(xstitch_fwd_kernel<T, DIAG, CWB>,                                     \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+    xstitch_fwd_kernel<T, DIAG, CWB><<<grid, threads, smem, st>>>(a, alpha, n4, C4);             \
+  } while (0)
+  const bool diag = (mode == VMTL_XS_REFERENCE_DIAG);
+  if (diag && cw) VMTL_XS_FWD(true, true);
+  else if (diag && !cw) VMTL_XS_FWD(true, false);
+  else if (!diag && cw) VMTL_XS_FWD(false, true);
+  else VMTL_XS_FWD(false, false);
+#undef VMTL_XS_FWD
+  return launch_status();
+}
+
+template <int T>
+static int xs_bwd_launch(const XsBwdArgs& a, const float* alpha, float* dalpha, int64_t npix, int C,
+                         int cw, int mode, float* partial, const XsBwdPlan& p, int write_dx,
+                         cudaStream_t st) {
+  dim3 grid(p.gridx, p.nchunk);
+#define VMTL_XS_BWD(DIAG, CWB)                                                                   \
+  do {                                                                                           \
+    if (p.smem > 48 * 1024)                                                                      \
+      cudaFuncSetAttribute(xstitch_bwd_kernel<T, DIAG, CWB>,                                     \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);            \
+    xstitch_bwd_kernel<T, DIAG, CWB><<<grid, p.threads, p.smem, st>>>(                           \
+        a, alpha, partial, p.npix_eff, p.c4_eff, p.cgw, p.rows, write_dx);                       \
+  } while (0)
+  const bool diag = (mode == VMTL_XS_REFERENCE_DIAG);
+  if (diag && cw) VMTL_XS_BWD(true, true);
+  else if (diag && !cw) VMTL_XS_BWD(true, false);
+  else if (!diag && cw) VMTL_XS_BWD(false, true);
+  else VMTL_XS_BWD(false, false);
+#undef VMTL_XS_BWD
+  int rc = launch_status();
+  if (rc != VMTL_OK) return rc;
+  const int cdim = cw ? C : 1;
+  const int n = T * T * cdim;
+  if (diag)
+    xstitch_dalpha_finalize<true><<<(n + 127) / 128, 128, 0, st>>>(partial, dalpha, p.gridx, T, cdim);
+  else
+    xstitch_dalpha_finalize<false><<<(n + 127) / 128, 128, 0, st>>>(partial, dalpha, p.gridx, T, cdim);
+  return launch_status();
+}
+
+static int xs_check(int T, int64_t npix, int C, int mode) {
+  if (T < 1 || T > VMTL_MAX_TASKS || npix < 0 || C < 4) return VMTL_EINVAL;
+  if (C % 4 != 0) return VMTL_EALIGN;
+  if (mode != VMTL_XS_REFERENCE_DIAG && mode != VMTL_XS_FULL_MIX) return VMTL_EINVAL;
+  return VMTL_OK;
+}
+
+}  // namespace vmtl
+
+using namespace vmtl;
+
+extern "C" int vmtl_xstitch_fwd(const float* const* x_host, float* const* y_host, const float* alpha,
+                                int T, int64_t npix, int C, int channel_wise, int mode,
+                                void* stream) {
+  int rc = xs_check(T, npix, C, mode);
+  if (rc != VMTL_OK) return rc;
+  if (!x_host || !y_host || !alpha) return VMTL_EINVAL;
+  XsFwdArgs a{};
+  for (int t = 0; t < T; ++t) {
+    if (!x_host[t] || !y_host[t]) return VMTL_EINVAL;
+    if (!aligned16(x_host[t]) || !aligned16(y_host[t])) return VMTL_EALIGN;
+    a.x[t] = reinterpret_cast<const float4*>(x_host[t]);
+    a.y[t] = reinterpret_cast<float4*>(y_host[t]);
+  }
+  if (channel_wise && !aligned16(alpha)) return VMTL_EALIGN;
+  if (npix == 0) return VMTL_OK;
+  const int C4 = C / 4;
+  const int64_t n4 = npix * C4;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (T) {
+    case 1: return xs_fwd_launch<1>(a, alpha, n4, C4, channel_wise, mode, st);
+    case 2: return xs_fwd_launch<2>(a, alpha, n4, C4, channel_wise, mode, st);
+    case 3: return xs_fwd_launch<3>(a, alpha, n4, C4, channel_wise, mode, st);
+    case 4: return xs_fwd_launch<4>(a, alpha, n4, C4, channel_wise, mode, st);
+    default: return VMTL_EUNSUPPORTED;
+  }
+}
+
+extern "C" size_t vmtl_xstitch_bwd_workspace_bytes(int T, int64_t npix, int C, int channel_wise) {
+  if (xs_check(T, npix, C, VMTL_XS_FULL_MIX) != VMTL_OK) return 0;
+  XsBwdPlan p = xs_bwd_plan(T, npix < 1 ? 1 : npix, C, channel_wise, VMTL_XS_FULL_MIX);
+  return p.partial_bytes + 256;
+}
+
+extern "C" int vmtl_xstitch_bwd(const float* const* dy_host, const float* const* x_host,
+                                float* const* dx_host, const float* alpha, float* dalpha, int T,
+                                int64_t npix, int C, int channel_wise, int mode, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  int rc = xs_check(T, npix, C, mode);
+  if (rc != VMTL_OK) return rc;
+  if (!dy_host || !x_host || !alpha || !dalpha || !workspace) return VMTL_EINVAL;
+  XsBwdArgs a{};
+  for (int t = 0; t < T; ++t) {
+    if (!dy_host[t] || !x_host[t]) return VMTL_EINVAL;
+    if (!aligned16(dy_host[t]) || !aligned16(x_host[t])) return VMTL_EALIGN;
+    a.dy[t] = reinterpret_cast<const float4*>(dy_host[t]);
+    a.x[t] = reinterpret_cast<const float4*>(x_host[t]);
+    if (dx_host) {
+      if (!dx_host[t]) return VMTL_EINVAL;
+      if (!aligned16(dx_host[t])) return VMTL_EALIGN;
+      a.dx[t] = reinterpret_cast<float4*>(dx_host[t]);
+    }
+  }
+  if ((channel_wise && !aligned16(alpha)) || !aligned16(workspace)) return VMTL_EALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (npix == 0) {
+    const size_t n = (size_t)T * T * (channel_wise ? C : 1);
+    return cudaMemsetAsync(dalpha, 0, n * sizeof(float), st) == cudaSuccess ? VMTL_OK : VMTL_ECUDA;
+  }
+  XsBwdPlan p = xs_bwd_plan(T, npix, C, channel_wise, mode);
+  if (workspace_bytes < p.partial_bytes) return VMTL_EWORKSPACE;
+  if (p.smem > 200 * 1024) return VMTL_EUNSUPPORTED;
+  float* partial = static_cast<float*>(workspace);
+  const int write_dx = dx_host != nullptr;
+  switch (T) {
+    case 1: return xs_bwd_launch<1>(a, alpha, dalpha, npix, C, channel_wise, mode, partial, p, write_dx, st);
+    case 2: return xs_bwd_launch<2>(a, alpha, dalpha, npix, C, channel_wise, mode, partial, p, write_dx, st);
+    case 3: return xs_bwd_launch<3>(a, alpha, dalpha, npix, C, channel_wise, mode, partial, p, write_dx, st);
+    case 4: return xs_bwd_launch<4>(a, alpha, dalpha, npix, C, channel_wise, mode, partial, p, write_dx, st);
+    default: return VMTL_EUNSUPPORTED;
+  }
+}

@@ -1,0 +1,471 @@
+"""Host-side operators over the C ABI of ``libvmtl_b200.so``.
+
+Every function here enqueues hand-written sm_100a kernels on torch's current CUDA stream;
+PyTorch is used for device memory, streams and autograd plumbing only.  There is no CPU or
+eager fallback: non-CUDA tensors raise.
+
+Layout: feature maps are NHWC (``torch.channels_last``); a ``[B,C,H,W]`` channels-last
+tensor is the row-major ``[B*H*W, C]`` matrix the kernels stream.
+"""
+from __future__ import annotations
+
+import ctypes
+from contextlib import contextmanager
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+XS_REFERENCE_DIAG = 0
+XS_FULL_MIX = 1
+GATE_FP32_FFMA = 0
+GATE_TC_3XTF32 = 1
+GATE_TC_TF32 = 2
+LAYOUT_NCHW = 0
+LAYOUT_NHWC = 1
+
+_XS_MODES = {"reference_diag": XS_REFERENCE_DIAG, "full_mix": XS_FULL_MIX}
+_GATE_PRECISIONS = {"fp32_ffma": GATE_FP32_FFMA, "tc_3xtf32": GATE_TC_3XTF32, "tc_tf32": GATE_TC_TF32}
+
+# default contraction precision of the gate; tests and bench may override
+default_gate_precision = "tc_3xtf32"
+
+
+# --------------------------------------------------------------------------------------
+# launch accounting + optional per-launch CUDA-event timing (bench.py roofline numbers)
+# --------------------------------------------------------------------------------------
+class _Prof:
+    enabled = False
+    records: list = []  # (name, algorithmic_bytes, start_event, end_event)
+    launches = 0  # kernels launched by this library since the last reset
+
+
+# kernels enqueued by one C call (for the `gpu_launches` claim in bench.py)
+_KERNELS_PER_CALL = {
+    "xstitch_fwd": 1, "xstitch_bwd": 2, "gate_fwd": 3, "gate_bwd": 6, "head_ce_fwd": 2,
+    "head_ce_bwd": 2, "ce_logits_fwd": 2, "ce_logits_bwd": 1, "head_silog_fwd": 2,
+    "head_silog_bwd": 2, "confusion_accum": 1, "depth_err_sums": 2, "seg_metrics": 1,
+}
+
+
+def reset_launch_count() -> None:
+    _Prof.launches = 0
+
+
+def launch_count() -> int:
+    return _Prof.launches
+
+
+@contextmanager
+def kernel_timing():
+    """Record a CUDA-event pair around every library call made inside the block."""
+    _Prof.enabled = True
+    _Prof.records = []
+    try:
+        yield _Prof.records
+    finally:
+        _Prof.enabled = False
+
+
+def summarize_timing(records) -> dict:
+    """name -> {calls, ms, bytes, gbps}; call after torch.cuda.synchronize()."""
+    out: dict = {}
+    for name, nbytes, e0, e1 in records:
+        d = out.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0})
+        d["calls"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["bytes"] += nbytes
+    for d in out.values():
+        d["gbps"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+    return out
+
+
+def _call(name: str, algo_bytes: int, *args) -> None:
+    fn = getattr(_lib.load(), "vmtl_" + name)
+    _Prof.launches += _KERNELS_PER_CALL.get(name, 1)
+    if _Prof.enabled:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _Prof.records.append((name, algo_bytes, e0, e1))
+    else:
+        rc = fn(*args)
+    _lib.check(rc, "vmtl_" + name)
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.VmtlError(
+                "vision_mtl_b200 ops run on CUDA (sm_100a) only; got a tensor on " + str(t.device)
+            )
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Channels-last view of a [B,C,H,W] fp32 tensor (no copy when already NHWC)."""
+    if x.dim() != 4:
+        raise ValueError("expected a [B,C,H,W] tensor")
+    if x.dtype != torch.float32:
+        raise TypeError("vision_mtl_b200 kernels are fp32")
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def _ptr_array(ts: Sequence[torch.Tensor]):
+    arr = (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    return arr
+
+
+# --------------------------------------------------------------------------------------
+# Cross-stitch
+# --------------------------------------------------------------------------------------
+def xstitch_forward(xs: Sequence[torch.Tensor], alpha: torch.Tensor, mode: int) -> list:
+    T = len(xs)
+    xs = [_nhwc(x) for x in xs]
+    _need_cuda(alpha, *xs)
+    B, C, H, W = xs[0].shape
+    ys = [torch.empty_like(x) for x in xs]
+    npix = B * H * W
+    cw = 1 if alpha.dim() == 3 else 0
+    a = alpha.detach().contiguous()
+    xa, ya = _ptr_array(xs), _ptr_array(ys)
+    _call("xstitch_fwd", 2 * 4 * T * npix * C, xa, ya, _p(a), T, npix, C, cw, mode, _stream())
+    return ys
+
+
+def xstitch_backward(dys, xs, alpha: torch.Tensor, mode: int, need_dx: bool = True):
+    T = len(xs)
+    dys = [_nhwc(d) for d in dys]
+    B, C, H, W = xs[0].shape
+    npix = B * H * W
+    cw = 1 if alpha.dim() == 3 else 0
+    a = alpha.detach().contiguous()
+    dalpha = torch.empty_like(a)
+    dxs = [torch.empty_like(x) for x in xs] if need_dx else None
+    lib = _lib.load()
+    ws = _workspace(lib.vmtl_xstitch_bwd_workspace_bytes(T, npix, C, cw), a.device)
+    dya, xa = _ptr_array(dys), _ptr_array(xs)
+    dxa = _ptr_array(dxs) if need_dx else None
+    _call("xstitch_bwd", (3 if need_dx else 2) * 4 * T * npix * C, dya, xa, dxa, _p(a), _p(dalpha), T,
+          npix, C, cw, mode, _p(ws), ws.numel(), _stream())
+    return dxs, dalpha
+
+
+class CrossStitchFunction(torch.autograd.Function):
+    """y[a] = sum_b alpha[a,b(,c)] x[b] (or the reference's diagonal-only variant)."""
+
+    @staticmethod
+    def forward(ctx, alpha, mode, *xs):
+        xs = [_nhwc(x) for x in xs]
+        ys = xstitch_forward(xs, alpha, mode)
+        ctx.mode = mode
+        ctx.need_dx = any(x.requires_grad for x in xs)
+        ctx.save_for_backward(alpha, *xs)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        alpha, *xs = ctx.saved_tensors
+        dys = [torch.zeros_like(x) if d is None else d for d, x in zip(dys, xs)]
+        dxs, dalpha = xstitch_backward(dys, xs, alpha, ctx.mode, ctx.need_dx)
+        if dxs is None:
+            dxs = [None] * len(xs)
+        return (dalpha, None, *dxs)
+
+
+def cross_stitch(xs: Sequence[torch.Tensor], alpha: torch.Tensor, mode: str = "reference_diag"):
+    return list(CrossStitchFunction.apply(alpha, _XS_MODES[mode], *xs))
+
+
+# --------------------------------------------------------------------------------------
+# MTAN attention gate
+# --------------------------------------------------------------------------------------
+class GateFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, s, weight, bias, gamma, beta, running_mean, running_var, training, momentum,
+                eps, precision):
+        h = _nhwc(h)
+        s = _nhwc(s)
+        _need_cuda(h, s, weight)
+        B, K, H, W = h.shape
+        N = s.shape[1]
+        M = B * H * W
+        w2 = weight.detach().reshape(N, K).contiguous()
+        y = torch.empty_like(s)
+        z = torch.empty_like(s)
+        mean = torch.empty(N, dtype=torch.float32, device=h.device)
+        invstd = torch.empty(N, dtype=torch.float32, device=h.device)
+        lib = _lib.load()
+        ws = _workspace(lib.vmtl_gate_workspace_bytes(M, K, N, precision, 0), h.device)
+        nbytes = 4 * M * (K + (4 * N if training else 2 * N))
+        _call("gate_fwd", nbytes, _p(h), _p(s), _p(w2), _p(bias.detach()), _p(gamma.detach()),
+              _p(beta.detach()), _p(running_mean), _p(running_var), float(momentum), float(eps),
+              1 if training else 0, precision, M, K, N, _p(y), _p(z), _p(mean), _p(invstd), _p(ws),
+              ws.numel(), _stream())
+        ctx.training = bool(training)
+        ctx.precision = precision
+        ctx.dims = (M, K, N)
+        ctx.wshape = weight.shape
+        ctx.save_for_backward(h, s, z, w2, gamma, beta, mean, invstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, s, z, w2, gamma, beta, mean, invstd = ctx.saved_tensors
+        M, K, N = ctx.dims
+        dy = _nhwc(dy)
+        need_dh, need_ds = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dh = torch.empty_like(h) if need_dh else None
+        ds = torch.empty_like(s) if need_ds else None
+        dW = torch.empty_like(w2)
+        dbias = torch.empty(N, dtype=torch.float32, device=h.device)
+        dgamma = torch.empty_like(dbias)
+        dbeta = torch.empty_like(dbias)
+        lib = _lib.load()
+        ws = _workspace(lib.vmtl_gate_workspace_bytes(M, K, N, ctx.precision, 1), h.device)
+        nbytes = 4 * M * (2 * K + 7 * N)
+        _call("gate_bwd", nbytes, _p(dy), _p(h), _p(s), _p(z), _p(w2), _p(gamma.detach()),
+              _p(beta.detach()), _p(mean), _p(invstd), 1 if ctx.training else 0, ctx.precision, M, K, N,
+              _p(dh), _p(ds), _p(dW), _p(dbias), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream())
+        return (dh, ds, dW.reshape(ctx.wshape), dbias, dgamma, dbeta, None, None, None, None, None, None)
+
+
+def attention_gate(h, s, weight, bias, gamma, beta, running_mean, running_var, training: bool,
+                   momentum: float = 0.1, eps: float = 1e-5, precision: Optional[str] = None):
+    """``s * sigmoid(batch_norm(conv1x1(h)))`` in NHWC; updates running stats in place."""
+    prec = _GATE_PRECISIONS[precision or default_gate_precision]
+    return GateFunction.apply(h, s, weight, bias, gamma, beta, running_mean, running_var, training,
+                              momentum, eps, prec)
+
+
+# --------------------------------------------------------------------------------------
+# Heads fused with losses / metrics
+# --------------------------------------------------------------------------------------
+def _loss_ws(P: int, device) -> torch.Tensor:
+    return _workspace(_lib.load().vmtl_loss_workspace_bytes(P), device)
+
+
+class HeadCEFunction(torch.autograd.Function):
+    """1x1 seg head + mean cross-entropy (+ argmax, + confusion matrix accumulation)."""
+
+    @staticmethod
+    def forward(ctx, feat, weight, bias, target, ignore_index, conf, want_pred):
+        feat = _nhwc(feat)
+        _need_cuda(feat, weight, target)
+        B, Cin, H, W = feat.shape
+        C = weight.shape[0]
+        P = B * H * W
+        w2 = weight.detach().reshape(C, Cin).contiguous()
+        tgt = target.contiguous()
+        if tgt.dtype != torch.int64:
+            raise TypeError("segmentation target must be int64")
+        out = torch.empty(2, dtype=torch.float64, device=feat.device)
+        loss = torch.empty((), dtype=torch.float32, device=feat.device)
+        pred = torch.empty((B, H, W), dtype=torch.uint8, device=feat.device) if want_pred else None
+        ws = _loss_ws(P, feat.device)
+        _call("head_ce_fwd", P * (4 * Cin + 8 + (1 if want_pred else 0)), _p(feat), _p(w2),
+              _p(bias.detach()), _p(tgt), P, Cin, C, int(ignore_index), _p(out), _p(loss), _p(pred),
+              _p(conf), _p(ws), ws.numel(), _stream())
+        ctx.ignore_index = int(ignore_index)
+        ctx.wshape = weight.shape
+        ctx.save_for_backward(feat, w2, bias, tgt, out)
+        if pred is None:
+            pred = torch.empty(0, dtype=torch.uint8, device=feat.device)
+        ctx.mark_non_differentiable(pred)
+        return loss, pred
+
+    @staticmethod
+    def backward(ctx, gloss, _gpred):
+        feat, w2, bias, tgt, out = ctx.saved_tensors
+        B, Cin, H, W = feat.shape
+        C = w2.shape[0]
+        P = B * H * W
+        g = gloss.detach().to(torch.float32).contiguous()
+        dfeat = torch.empty_like(feat) if ctx.needs_input_grad[0] else None
+        dW = torch.empty_like(w2)
+        db = torch.empty(C, dtype=torch.float32, device=feat.device)
+        ws = _loss_ws(P, feat.device)
+        _call("head_ce_bwd", P * (8 * Cin + 8), _p(feat), _p(w2), _p(bias.detach()), _p(tgt), P, Cin, C,
+              ctx.ignore_index, _p(out), _p(g), _p(dfeat), _p(dW), _p(db), _p(ws), ws.numel(), _stream())
+        return dfeat, dW.reshape(ctx.wshape), db, None, None, None, None
+
+
+def head_cross_entropy(feat, weight, bias, target, ignore_index: int = -100,
+                       conf: Optional[torch.Tensor] = None, want_pred: bool = True):
+    """Returns (loss, pred uint8 [B,H,W]); ``conf`` (int64 [C,C]) is accumulated in place."""
+    return HeadCEFunction.apply(feat, weight, bias, target, ignore_index, conf, want_pred)
+
+
+def _logits_layout(logits: torch.Tensor):
+    if logits.dim() != 4 or logits.dtype != torch.float32:
+        raise TypeError("expected fp32 [B,C,H,W] logits")
+    if logits.is_contiguous():
+        return logits, LAYOUT_NCHW
+    if logits.is_contiguous(memory_format=torch.channels_last):
+        return logits, LAYOUT_NHWC
+    return logits.contiguous(), LAYOUT_NCHW
+
+
+class CELogitsFunction(torch.autograd.Function):
+    """Mean cross-entropy (+ argmax, + confusion) on precomputed logits, NCHW or NHWC."""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index, conf, want_pred):
+        logits, layout = _logits_layout(logits)
+        _need_cuda(logits, target)
+        B, C, H, W = logits.shape
+        P, HW = B * H * W, H * W
+        tgt = target.contiguous()
+        if tgt.dtype != torch.int64:
+            raise TypeError("segmentation target must be int64")
+        out = torch.empty(2, dtype=torch.float64, device=logits.device)
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        pred = torch.empty((B, H, W), dtype=torch.uint8, device=logits.device) if want_pred else None
+        ws = _loss_ws(P, logits.device)
+        _call("ce_logits_fwd", P * (4 * C + 8 + (1 if want_pred else 0)), _p(logits), _p(tgt), P, HW, C,
+              layout, int(ignore_index), _p(out), _p(loss), _p(pred), _p(conf), _p(ws), ws.numel(),
+              _stream())
+        ctx.ignore_index = int(ignore_index)
+        ctx.layout = layout
+        ctx.save_for_backward(logits, tgt, out)
+        if pred is None:
+            pred = torch.empty(0, dtype=torch.uint8, device=logits.device)
+        ctx.mark_non_differentiable(pred)
+        return loss, pred
+
+    @staticmethod
+    def backward(ctx, gloss, _gpred):
+        logits, tgt, out = ctx.saved_tensors
+        B, C, H, W = logits.shape
+        P, HW = B * H * W, H * W
+        g = gloss.detach().to(torch.float32).contiguous()
+        dlogits = torch.empty_like(logits)
+        _call("ce_logits_bwd", P * (8 * C + 8), _p(logits), _p(tgt), P, HW, C, ctx.layout,
+              ctx.ignore_index, _p(out), _p(g), _p(dlogits), _stream())
+        return dlogits, None, None, None, None
+
+
+def cross_entropy_logits(logits, target, ignore_index: int = -100,
+                         conf: Optional[torch.Tensor] = None, want_pred: bool = True):
+    return CELogitsFunction.apply(logits, target, ignore_index, conf, want_pred)
+
+
+class HeadSilogFunction(torch.autograd.Function):
+    """1x1 depth head + sigmoid + SILog (+ MAE, abs-rel, predictions).
+
+    ``weight is None``: ``feat`` is already the [B,1,H,W] depth logit (basic / csnet)."""
+
+    @staticmethod
+    def forward(ctx, feat, weight, bias, target, min_depth, want_pred):
+        has_head = weight is not None
+        feat = _nhwc(feat) if has_head else feat.contiguous()
+        _need_cuda(feat, target)
+        B, Cin, H, W = feat.shape
+        P = B * H * W
+        tgt = target.contiguous()
+        if tgt.dtype != torch.float32 or tgt.numel() != P:
+            raise TypeError("depth target must be fp32 with B*H*W elements")
+        w1 = weight.detach().reshape(Cin).contiguous() if has_head else None
+        out = torch.empty(8, dtype=torch.float64, device=feat.device)
+        scalars = torch.empty(3, dtype=torch.float32, device=feat.device)
+        pred = torch.empty((B, H, W, 1), dtype=torch.float32, device=feat.device) if want_pred else None
+        ws = _loss_ws(P, feat.device)
+        _call("head_silog_fwd", P * (4 * Cin + 4 + (4 if want_pred else 0)), _p(feat), _p(w1),
+              _p(bias.detach() if has_head else None), _p(tgt), P, Cin, float(min_depth), _p(out),
+              _p(scalars), _p(pred), _p(ws), ws.numel(), _stream())
+        ctx.min_depth = float(min_depth)
+        ctx.has_head = has_head
+        ctx.wshape = weight.shape if has_head else None
+        if has_head:
+            ctx.save_for_backward(feat, tgt, out, w1, bias)
+        else:
+            ctx.save_for_backward(feat, tgt, out)
+        if pred is None:
+            pred = torch.empty(0, dtype=torch.float32, device=feat.device)
+        ctx.mark_non_differentiable(pred)
+        return scalars, pred
+
+    @staticmethod
+    def backward(ctx, gscalars, _gpred):
+        gsilog = gscalars[0:1]  # only silog (scalars[0]) is differentiable; mae/abs_rel are metrics
+        if ctx.has_head:
+            feat, tgt, out, w1, bias = ctx.saved_tensors
+        else:
+            feat, tgt, out = ctx.saved_tensors
+            w1 = bias = None
+        B, Cin, H, W = feat.shape
+        P = B * H * W
+        g = gsilog.detach().to(torch.float32).contiguous()
+        need_dfeat = ctx.needs_input_grad[0] or not ctx.has_head
+        dfeat = torch.empty_like(feat) if need_dfeat else None
+        dw = torch.empty(Cin, dtype=torch.float32, device=feat.device) if ctx.has_head else None
+        db = torch.empty(1, dtype=torch.float32, device=feat.device) if ctx.has_head else None
+        ws = _loss_ws(P, feat.device)
+        _call("head_silog_bwd", P * (8 * Cin + 4), _p(feat), _p(w1),
+              _p(bias.detach() if bias is not None else None), _p(tgt), P, Cin, ctx.min_depth, _p(out),
+              _p(g), _p(dfeat), _p(dw), _p(db), _p(ws), ws.numel(), _stream())
+        if ctx.has_head:
+            return dfeat, dw.reshape(ctx.wshape), db, None, None, None
+        return dfeat, None, None, None, None, None
+
+
+def head_silog(feat, weight, bias, target, min_depth: float = 1e-3, want_pred: bool = True):
+    """Returns (silog, mae, abs_rel, pred [B,H,W,1]); only silog carries a gradient."""
+    scalars, pred = HeadSilogFunction.apply(feat, weight, bias, target, min_depth, want_pred)
+    return scalars[0], scalars[1].detach(), scalars[2].detach(), pred
+
+
+# --------------------------------------------------------------------------------------
+# Validation reductions
+# --------------------------------------------------------------------------------------
+def confusion_accumulate(pred: torch.Tensor, target: torch.Tensor, num_classes: int,
+                         conf: Optional[torch.Tensor] = None, ignore_index: int = -100) -> torch.Tensor:
+    """conf[target, pred] += 1 (int64 [C,C], rows = target); bit-exact integer arithmetic."""
+    _need_cuda(pred, target)
+    if conf is None:
+        conf = torch.zeros((num_classes, num_classes), dtype=torch.int64, device=pred.device)
+    pred = pred.contiguous()
+    target = target.contiguous()
+    if target.dtype != torch.int64 or pred.dtype not in (torch.uint8, torch.int64):
+        raise TypeError("pred must be uint8/int64 and target int64")
+    P = target.numel()
+    is_u8 = pred.dtype == torch.uint8
+    _call("confusion_accum", P * (9 if is_u8 else 16), _p(pred), 1 if is_u8 else 0, _p(target), P,
+          num_classes, int(ignore_index), _p(conf), _stream())
+    return conf
+
+
+def depth_error_sums(pred: torch.Tensor, target: torch.Tensor, min_depth: float = 1e-3) -> torch.Tensor:
+    """float64 [4] = {P, sum|p-t|, n(t>min_depth), sum|p-t|/t}."""
+    _need_cuda(pred, target)
+    pred = pred.contiguous()
+    target = target.contiguous()
+    P = pred.numel()
+    out = torch.empty(4, dtype=torch.float64, device=pred.device)
+    ws = _loss_ws(P, pred.device)
+    _call("depth_err_sums", P * 8, _p(pred), _p(target), P, float(min_depth), _p(out), _p(ws), ws.numel(),
+          _stream())
+    return out
+
+
+def seg_metrics(conf: torch.Tensor) -> torch.Tensor:
+    """float32 [3] = {accuracy (micro), jaccard (macro, absent=0), F1 (weighted)} on device."""
+    _need_cuda(conf)
+    C = conf.shape[0]
+    m = torch.empty(3, dtype=torch.float32, device=conf.device)
+    _call("seg_metrics", 8 * C * C, _p(conf.contiguous()), C, _p(m), _stream())
+    return m
