@@ -1,0 +1,88 @@
+"""Deterministic, RNG-free test data shared by the golden generator, the oracle tests and the
+GPU parity tests.  TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).
+
+Values come from a 31-bit linear congruential sequence in integer arithmetic, so the same
+tensors are rebuilt bit-for-bit on any machine without storing them: golden files only have to
+hold the reference's OUTPUTS.
+"""
+from __future__ import annotations
+
+import zlib
+
+import numpy as np
+import torch
+
+_A, _C, _M = 1103515245, 12345, 2**31
+
+
+def lcg_uniform(n: int, seed: int) -> np.ndarray:
+    """n values in [-0.5, 0.5), float64, from x_{k+1} = (A x_k + C) mod 2^31 (vectorised jump)."""
+    # closed form of k LCG steps is awkward to vectorise exactly; use a counter-based variant:
+    # x_k = (A * ((seed + k) mod M) * ((seed + k) mod M | 1) + C) mod M, still pure integer math.
+    k = (np.arange(n, dtype=np.uint64) + np.uint64(seed % _M)) % np.uint64(_M)
+    x = (np.uint64(_A) * ((k * (k | np.uint64(1))) % np.uint64(_M)) + np.uint64(_C)) % np.uint64(_M)
+    x = (x * np.uint64(2654435761)) % np.uint64(_M)  # decorrelate neighbouring counters
+    return x.astype(np.float64) / float(_M) - 0.5
+
+
+def key_seed(key: str, salt: int = 0) -> int:
+    return (zlib.crc32(key.encode()) + 7919 * salt) % _M
+
+
+def tensor(shape, key: str, scale: float = 1.0, salt: int = 0) -> torch.Tensor:
+    n = int(np.prod(shape)) if len(shape) else 1
+    v = lcg_uniform(n, key_seed(key, salt)) * (2.0 * scale)
+    return torch.from_numpy(v.astype(np.float32)).reshape(tuple(shape))
+
+
+def labels(shape, num_classes: int, key: str) -> torch.Tensor:
+    n = int(np.prod(shape))
+    v = (lcg_uniform(n, key_seed(key)) + 0.5) * num_classes
+    return torch.from_numpy(np.clip(v.astype(np.int64), 0, num_classes - 1)).reshape(tuple(shape))
+
+
+def fill_state_dict(sd: dict, salt: int = 0) -> dict:
+    """A well-conditioned value for every entry of a state_dict, keyed by NAME (independent of
+    module construction order, which differs between the reference and the product)."""
+    out = {}
+    for k, v in sd.items():
+        shape = tuple(v.shape)
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.zeros_like(v)
+        elif k.endswith("running_mean"):
+            out[k] = tensor(shape, k, 0.1, salt)
+        elif k.endswith("running_var"):
+            out[k] = 1.0 + tensor(shape, k, 0.3, salt).abs()
+        elif v.dim() == 1 and k.endswith("weight"):  # BatchNorm scale
+            out[k] = 1.0 + tensor(shape, k, 0.2, salt)
+        elif v.dim() == 1:  # any bias
+            out[k] = tensor(shape, k, 0.1, salt)
+        elif k.endswith("weights"):  # cross-stitch alphas: U(0,1) like reset_parameters
+            out[k] = tensor(shape, k, 0.5, salt) + 0.5
+        else:  # conv / transposed-conv kernels: variance-preserving uniform
+            fan_in = int(np.prod(shape[1:])) if v.dim() > 1 else shape[0]
+            out[k] = tensor(shape, k, float(np.sqrt(3.0 / max(fan_in, 1))), salt)
+        out[k] = out[k].to(v.dtype)
+    return out
+
+
+def image_batch(B: int, H: int, W: int, num_classes: int, key: str = "batch", depth_zero_frac: float = 0.2) -> dict:
+    """Synthetic Cityscapes-shaped batch: img U(0,1), mask randint(0,C), depth U(0,0.5)
+    with a fraction of exact zeros, layouts as the reference datasets produce them."""
+    img = tensor((B, 3, H, W), key + "/img", 0.5) + 0.5
+    mask = labels((B, H, W), num_classes, key + "/mask")
+    depth = (tensor((B, H, W, 1), key + "/depth", 0.25) + 0.25).clamp_min(0.0)
+    zero = (tensor((B, H, W, 1), key + "/zero", 0.5) + 0.5) < depth_zero_frac
+    depth = torch.where(zero, torch.zeros_like(depth), depth)
+    return {"img": img, "mask": mask, "depth": depth}
+
+
+def summarize(t: torch.Tensor, k: int = 8) -> np.ndarray:
+    """Compact, order-sensitive fingerprint of a tensor: [sum, l2, first k, strided k]."""
+    f = t.detach().double().reshape(-1)
+    n = f.numel()
+    head = f[:k]
+    stride = max(n // k, 1)
+    samp = f[::stride][:k]
+    pad = lambda x: torch.cat([x, torch.zeros(k - x.numel(), dtype=torch.float64)])  # noqa: E731
+    return torch.cat([f.sum().reshape(1), f.norm().reshape(1), pad(head), pad(samp)]).numpy()

@@ -1,0 +1,149 @@
+"""Golden-vector generator: runs the UNMODIFIED reference (imported from /root/reference behind
+``oracle/ref_shims.py``) on deterministic inputs and writes its outputs to ``tests/golden/``.
+
+    python -m oracle.make_golden
+
+Only runs where the reference tree exists (the build container); the fixtures it writes are
+committed and travel.  Inputs and weights are NOT stored: ``oracle/fixtures.py`` rebuilds them
+bit-for-bit from names, so the files hold reference outputs only.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+from oracle import fixtures as FX  # noqa: E402
+from oracle import ref_shims  # noqa: E402
+
+GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
+
+XSTITCH_CASES = [  # (name, T, B, C, H, W, channel_wise)
+    ("t2_cw", 2, 2, 8, 4, 6, True),
+    ("t2_lw", 2, 2, 8, 4, 6, False),
+    ("t3_cw", 3, 1, 12, 3, 5, True),
+]
+MTAN_CASES = {  # name -> (hidden, first_channel, levels, B, H, W, classes)
+    "mtan_h128": (128, 32, 2, 2, 32, 64, 19),
+    "mtan_h64": (64, 32, 2, 2, 16, 32, 14),
+}
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def gen_xstitch(ref, out):
+    for name, T, B, C, H, W, cw in XSTITCH_CASES:
+        layer = ref["CrossStitchLayer"](T, C if cw else None)
+        layer.load_state_dict(FX.fill_state_dict(layer.state_dict()))
+        x = FX.tensor((T, B, C, H, W), f"xs/{name}/x").requires_grad_(True)
+        dy = FX.tensor((T, B, C, H, W), f"xs/{name}/dy")
+        y = layer(x)
+        y.backward(dy)
+        out[f"xs/{name}/y"] = _np(y)
+        out[f"xs/{name}/dx"] = _np(x.grad)
+        out[f"xs/{name}/dw"] = _np(layer.weights.grad)
+
+
+def gen_silog(ref, out):
+    crit = ref["SILogLoss"]()
+    logit = FX.tensor((2, 8, 16, 1), "silog/logit", 2.0).requires_grad_(True)
+    b = FX.image_batch(2, 8, 16, 19, "silog")
+    pred = torch.sigmoid(logit)
+    loss = crit(pred, b["depth"])
+    loss.backward()
+    out["silog/loss"] = _np(loss)
+    out["silog/dlogit"] = _np(logit.grad)
+
+
+def gen_mtan(ref, out):
+    for name, (hid, first, levels, B, H, W, C) in MTAN_CASES.items():
+        torch.manual_seed(0)
+        net = ref["MTANMiniUnet"](3, {"depth": 1, "segm": C}, task_subnets_hidden_channels=hid,
+                                  encoder_first_channel=first, encoder_num_channels=levels)
+        net.load_state_dict(FX.fill_state_dict(net.state_dict()))
+        batch = FX.image_batch(B, H, W, C, name)
+        # --- one training step of the reference path: lit_module.py:78-81,120-144 restated with the
+        #     reference's own loss classes (lit_module itself needs pytorch_lightning/torchmetrics)
+        net.train()
+        raw = net(batch["img"])
+        depth_pred = torch.sigmoid(raw["depth"]).permute(0, 2, 3, 1)
+        preds = torch.argmax(F.softmax(raw["segm"], dim=1), dim=1)
+        loss_segm = nn.CrossEntropyLoss()(raw["segm"], batch["mask"])
+        loss_depth = ref["SILogLoss"]()(depth_pred, batch["depth"])
+        loss = 1.0 * loss_segm + 1.0 * loss_depth
+        loss.backward()
+        out[f"{name}/segm_logits"] = _np(raw["segm"]).astype(np.float32)
+        out[f"{name}/depth_logits"] = _np(raw["depth"]).astype(np.float32)
+        out[f"{name}/preds"] = _np(preds).astype(np.int16)
+        out[f"{name}/losses"] = np.array([loss.item(), loss_segm.item(), loss_depth.item()], dtype=np.float64)
+        out[f"{name}/mae"] = np.array([(depth_pred - batch["depth"]).abs().mean().item()])
+        for k, p_ in net.named_parameters():
+            out[f"{name}/grad/{k}"] = FX.summarize(p_.grad)
+        for k, b_ in net.named_buffers():
+            out[f"{name}/buf/{k}"] = FX.summarize(b_.float())
+        # --- eval-mode forward (running statistics), predict() path training_lit.py:198
+        net.eval()
+        with torch.no_grad():
+            raw_e = net(batch["img"])
+        out[f"{name}/eval_segm"] = FX.summarize(raw_e["segm"], 16)
+        out[f"{name}/eval_depth"] = FX.summarize(raw_e["depth"], 16)
+
+
+def gen_csnet(ref, out):
+    """Reference CSNet class over the stand-in backbone (smp/timm are not installable)."""
+    from vision_mtl_b200.utils.model_utils import get_model_with_dense_preds
+
+    for name, cw in (("csnet_cw", True), ("csnet_lw", False)):
+        torch.manual_seed(0)
+        models = {
+            "depth": get_model_with_dense_preds(segm_classes=1, activation=None,
+                                                backbone_params=dict(encoder_weights=None)),
+            "segm": get_model_with_dense_preds(segm_classes=19, activation=None,
+                                               backbone_params=dict(encoder_weights=None)),
+        }
+        net = ref["CSNet"](models, channel_wise_stitching=cw)
+        net.load_state_dict(FX.fill_state_dict(net.state_dict()))
+        batch = FX.image_batch(2, 64, 64, 19, name)
+        net.train()
+        raw = net(batch["img"])
+        loss_segm = nn.CrossEntropyLoss()(raw["segm"], batch["mask"])
+        depth_pred = torch.sigmoid(raw["depth"]).permute(0, 2, 3, 1)
+        loss_depth = ref["SILogLoss"]()(depth_pred, batch["depth"])
+        (loss_segm + loss_depth).backward()
+        out[f"{name}/segm_logits"] = _np(raw["segm"]).astype(np.float32)
+        out[f"{name}/depth_logits"] = _np(raw["depth"]).astype(np.float32)
+        out[f"{name}/losses"] = np.array([loss_segm.item() + loss_depth.item(), loss_segm.item(), loss_depth.item()])
+        out[f"{name}/stitch_channels"] = np.array(getattr(net, "stitch_channels", []), dtype=np.int64)
+        out[f"{name}/stitch_names"] = np.array(list(net.cross_stitch_layers.keys()))
+        for k, p_ in net.named_parameters():
+            if p_.grad is not None:
+                out[f"{name}/grad/{k}"] = FX.summarize(p_.grad)
+
+
+def main():
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.backends.mkldnn.enabled = True
+    ref = ref_shims.load()
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for fname, gens in (("kernels.npz", (gen_xstitch, gen_silog)), ("mtan.npz", (gen_mtan,)),
+                        ("csnet.npz", (gen_csnet,))):
+        out = {}
+        for g in gens:
+            g(ref, out)
+        path = os.path.join(GOLDEN_DIR, fname)
+        np.savez_compressed(path, **out)
+        print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

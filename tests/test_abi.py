@@ -1,0 +1,110 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
+``include/vmtl_b200.h`` declares; the host-side surface mirrors the reference's class surface."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(REPO, "include", "vmtl_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vmtl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from vision_mtl_b200 import _lib, build
+
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    names = header_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in vmtl_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes signature table and header disagree"
+    typed = _lib.load()
+    assert typed.vmtl_version() >= 100
+    assert typed.vmtl_strerror(-5).decode() == "workspace too small"
+    assert typed.vmtl_strerror(0).decode() == "ok"
+    # sizing helpers are host-only and must work without a GPU
+    assert typed.vmtl_xstitch_bwd_workspace_bytes(2, 1 << 20, 32, 1) > 0
+    assert typed.vmtl_gate_workspace_bytes(1 << 20, 128, 32, 1, 1) > 4 * (1 << 20) * 32
+    assert typed.vmtl_gate_workspace_bytes(1 << 20, 100, 32, 1, 1) == 0  # unsupported K
+    assert typed.vmtl_loss_workspace_bytes(1 << 20) > 0
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly off-GPU instead of silently computing elsewhere."""
+    from vision_mtl_b200 import _lib, ops
+
+    x = [torch.randn(1, 4, 2, 2), torch.randn(1, 4, 2, 2)]
+    with pytest.raises(_lib.VmtlError):
+        ops.cross_stitch(x, torch.rand(2, 2), "reference_diag")
+    with pytest.raises(_lib.VmtlError):
+        ops.confusion_accumulate(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64), 3)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(REPO, "vision_mtl_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_reference_class_surface():
+    from vision_mtl_b200.lit_module import MTLModule
+    from vision_mtl_b200.losses import SILogLoss
+    from vision_mtl_b200.models import (AttentionModuleDecoder, AttentionModuleEncoder, BasicMTLModel,
+                                        CrossStitchLayer, CSNet, MTANMiniUnet)
+
+    def params(fn):
+        return list(inspect.signature(fn).parameters)[1:]
+
+    assert params(CrossStitchLayer.__init__)[:2] == ["num_tasks", "num_channels"]
+    assert params(CSNet.__init__)[:2] == ["models", "channel_wise_stitching"]
+    assert params(AttentionModuleEncoder.__init__) == ["shared_1_channels", "out_channels", "shared_2_channels",
+                                                       "prev_layer_out_channels", "hidden_channels"]
+    assert params(AttentionModuleEncoder.forward) == ["conv1_shared", "conv2_shared", "prev_layer_outs"]
+    assert params(AttentionModuleDecoder.__init__) == ["shared_1_channels", "shared_2_channels",
+                                                       "prev_layer_out_channels", "out_channels", "hidden_channels"]
+    assert params(AttentionModuleDecoder.forward) == ["conv1_shared", "prev_layer_outs", "conv2_shared"]
+    assert params(MTANMiniUnet.__init__) == ["in_channels", "map_tasks_to_num_channels",
+                                             "task_subnets_hidden_channels", "encoder_first_channel",
+                                             "encoder_num_channels"]
+    assert params(BasicMTLModel.__init__) == ["segm_classes", "activation", "encoder_name", "encoder_weights",
+                                              "decoder_first_channel", "num_decoder_layers", "in_channels"]
+    assert params(SILogLoss.forward) == ["pred", "target", "mask", "interpolate", "min_depth"]
+    assert params(MTLModule.__init__)[:7] == ["model", "num_classes", "optim_dict", "lr", "device",
+                                              "loss_segm_weight", "loss_depth_weight"]
+    for m in ("shared_step", "training_step", "validation_step", "test_step", "predict_step", "calc_losses",
+              "calc_metrics", "postprocess_raw_out", "update_step_stats", "on_train_epoch_end",
+              "on_validation_epoch_end", "on_predict_epoch_end", "transfer_batch_to_device",
+              "configure_optimizers"):
+        assert callable(getattr(MTLModule, m))
+    layer = CrossStitchLayer(3, 8)
+    assert layer.weights.shape == (3, 3, 8) and 0 <= float(layer.weights.min()) and float(layer.weights.max()) <= 1
+    assert CrossStitchLayer(2).weights.shape == (2, 2)
+
+
+def test_csnet_plan_and_state_dict_keys():
+    from vision_mtl_b200.models import CSNet
+    from vision_mtl_b200.utils.model_utils import get_model_with_dense_preds
+
+    models = {"depth": get_model_with_dense_preds(1, None, dict(encoder_weights=None)),
+              "segm": get_model_with_dense_preds(19, None, dict(encoder_weights=None))}
+    net = CSNet(models, channel_wise_stitching=True)
+    assert net.stitch_channels == [16, 24, 40, 80, 112, 160, 1072, 296, 152, 80, 32]
+    keys = net.state_dict().keys()
+    assert "cross_stitch_layers.0_encoder_model_blocks_1.weights" in keys
+    assert "cross_stitch_layers.0_decoder_blocks_4.weights" in keys
+    assert any(k.startswith("models.segm.0.encoder.model.conv_stem") for k in keys)
+    ops_ = [op for op, _ in net._plan]
+    assert ops_.count("stitch") == 11 and ops_.count("save_skip") == 4 and ops_.count("cat_skip") == 4
+    assert ops_.count("upsample2") == 1

@@ -315,3 +315,6 @@ def test_gate_fwd_bwd(B, N, H, W, training, precision):
         assert p[1].grad.abs().max().item() <= 1e-4 * max(bn.bias.grad.abs().max().item(), 1e-30) + 1e-6
     else:
         assert_rel(p[1].grad, conv.bias.grad, what="dbias")
+        with torch.no_grad():  # inference: the tensor-core path fuses the whole gate into one pass
+            y2 = ops.attention_gate(hd, sd, p[0], p[1], p[2], p[3], rmd, rvd, False, 0.1, 1e-5, precision)
+        assert_rel(y2, yr, what="y (no_grad eval)")

@@ -363,11 +363,16 @@ extern "C" int vmtl_gate_fwd(const float* h, const float* s, const float* W, con
                                                              ws.invstd, ws.coefA, ws.coefB, save_mean,
                                                              save_invstd);
     if ((rc = launch_status()) != VMTL_OK) return rc;
-    if (precision != VMTL_GATE_FP32_FFMA)
+    if (precision != VMTL_GATE_FP32_FFMA && !save_z)  // inference: single fused pass, z never stored
       return gate_tc_fwd_eval(h, s, W, bias, ws.coefA, ws.coefB, M, K, N, split3, y, st);
     if (!save_z) return VMTL_EINVAL;  // the CUDA-core path needs a z buffer even in eval mode
     float* zbuf = save_z;
-    rc = sgemm64(h, W, zbuf, bias, M, N, K, K, 1, 1, K, N, 1, 0, st);
+    if (precision != VMTL_GATE_FP32_FFMA) {
+      int unused = 0;  // a backward will follow: keep z (batch partials are computed but unused)
+      rc = gate_tc_fwd_gemm(h, W, bias, M, K, N, split3, zbuf, ws.partial, ws.partial_rows, &unused, st);
+    } else {
+      rc = sgemm64(h, W, zbuf, bias, M, N, K, K, 1, 1, K, N, 1, 0, st);
+    }
     if (rc != VMTL_OK) return rc;
     gate_apply_kernel<<<ew_grid(M, N), kEwThreads, 0, st>>>(zbuf, s, M, C4, ws.coefA, ws.coefB, y);
     return launch_status();
@@ -446,11 +451,14 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, co
     // db partials reuse ws.partial (phase A has been consumed by the finalize above)
     rc = gate_tc_bwd_gemm(dy, h, s, z, W, ws, gamma, M, K, N, split3, dh, ws.gemm_partial, ws.gemm_slots,
                           &nslots, ws.partial, st);
-    if (rc != VMTL_OK) return rc;
-    rows_sum_finalize<<<(N * K + 127) / 128, 128, 0, st>>>(ws.gemm_partial, nslots, N * K, dW);
-    if ((rc = launch_status()) != VMTL_OK) return rc;
-    rows_sum_finalize<<<(N + 127) / 128, 128, 0, st>>>(ws.partial, nslots, N, dbias);
-    return launch_status();
+    if (rc == VMTL_OK) {
+      rows_sum_finalize<<<(N * K + 127) / 128, 128, 0, st>>>(ws.gemm_partial, nslots, N * K, dW);
+      if ((rc = launch_status()) != VMTL_OK) return rc;
+      rows_sum_finalize<<<(N + 127) / 128, 128, 0, st>>>(ws.partial, nslots, N, dbias);
+      return launch_status();
+    }
+    if (rc != VMTL_EUNSUPPORTED) return rc;
+    // shape not covered by the tensor-core backward: CUDA-core contraction below
   }
   gate_bwd_dz_kernel<<<nparts, kEwThreads, 0, st>>>(dy, s, z, M, C4, ws.coefA, ws.coefB, ws.mean,
                                                     ws.invstd, ws.c1, ws.c2, ws.dz, ws.partial);

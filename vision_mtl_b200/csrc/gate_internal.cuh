@@ -40,7 +40,8 @@ inline size_t gate_ws_floats(int64_t M, int K, int N, int precision, int backwar
   w.partial = take((size_t)w.partial_rows * 2 * N);
   w.gemm_slots = backward ? sm_count() * 2 : 0;
   w.gemm_partial = take((size_t)w.gemm_slots * N * K);
-  w.dz = (backward && precision == VMTL_GATE_FP32_FFMA) ? take((size_t)M * N) : nullptr;
+  (void)precision;
+  w.dz = backward ? take((size_t)M * N) : nullptr;
   if (ws) *ws = w;
   return off;
 }

@@ -222,9 +222,10 @@ using namespace vmtl;
 
 extern "C" int vmtl_confusion_accum(const void* pred, int pred_is_u8, const int64_t* target, int64_t P,
                                     int C, int64_t ignore_index, int64_t* conf, void* stream) {
-  if (!pred || !target || !conf || P < 0 || C < 1) return VMTL_EINVAL;
+  if (!conf || P < 0 || C < 1) return VMTL_EINVAL;
   if (C > 64 || (pred_is_u8 && C > 256)) return VMTL_EUNSUPPORTED;
-  if (P == 0) return VMTL_OK;
+  if (P == 0) return VMTL_OK;  // empty batch: nothing to count (pointers may be null)
+  if (!pred || !target) return VMTL_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int CC = C * C;
   int nhist = kConfWarps;

@@ -1,0 +1,156 @@
+"""Cross-stitch network, drop-in for ``vision_mtl/models/cross_stitch_model.py``.
+
+``CrossStitchLayer`` keeps the reference's parameter (``weights`` ``[T,T]`` / ``[T,T,C]``,
+``uniform_(0,1)`` init) and call signature, but the mixing runs in the hand-written NHWC
+kernels of ``csrc/xstitch.cu`` straight from the T task tensors -- the ``torch.stack`` copy
+and the einsum temporaries of the reference (cross_stitch_model.py:32-37,147-152) are gone.
+
+``mode``:
+  * ``"reference_diag"`` (default): bit-for-bit what the reference einsum computes.  Its
+    repeated index ``a`` takes the DIAGONAL of alpha (``y[a] = alpha[a,a(,c)] * x[a]``), so the
+    tasks never mix and off-diagonal alphas get exactly-zero gradients.
+  * ``"full_mix"``: the cross-stitch unit as published, ``y[a] = sum_b alpha[a,b(,c)] * x[b]``.
+
+``CSNet`` reproduces the reference's flat walk over leaf modules (cross_stitch_model.py:102-157)
+from a plan that is compiled once at construction instead of regex-matching every layer name
+for every task on every step.
+"""
+from __future__ import annotations
+
+import re
+import typing as t
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..utils.model_utils import (
+    concat_slightly_diff_sized_tensors,
+    get_joint_layer_names_before_stitch_for_unet,
+)
+from ..utils.utils import get_module_by_name
+
+ENCODER_BLOCK_RE = r"0.encoder.model.blocks.(\d+)$"
+DECODER_BLOCK_RE = r"0.decoder.blocks.(\d+)$"
+
+
+class CrossStitchLayer(nn.Module):
+    def __init__(self, num_tasks: int, num_channels: t.Optional[int] = None, mode: str = "reference_diag"):
+        super().__init__()
+        self.num_tasks = num_tasks
+        self.channel_wise_stitching = num_channels is not None
+        shape = (num_tasks, num_tasks, num_channels) if self.channel_wise_stitching else (num_tasks, num_tasks)
+        self.weights = nn.Parameter(torch.empty(*shape))
+        self.mode = mode
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.uniform_(self.weights)
+
+    def forward(self, mt_activations):
+        """``mt_activations``: a stacked ``[T,B,C,H,W]`` tensor (reference API; returns the same) or
+        a sequence of T ``[B,C,H,W]`` tensors (no stack copy; returns a list)."""
+        if isinstance(mt_activations, (list, tuple)):
+            return ops.cross_stitch(list(mt_activations), self.weights, self.mode)
+        ys = ops.cross_stitch(list(mt_activations.unbind(0)), self.weights, self.mode)
+        return torch.stack(ys, dim=0)
+
+
+class CSNet(nn.Module):
+    def __init__(self, models: dict, channel_wise_stitching: bool = False, stitch_mode: str = "reference_diag"):
+        """``models``: task name -> network (all with identical structure)."""
+        super().__init__()
+        self.encoder_block_regex = ENCODER_BLOCK_RE
+        self.decoder_block_regex = DECODER_BLOCK_RE
+        self.num_tasks = len(models)
+        self.model_names = list(models.keys())
+        self.models = nn.ModuleDict(models)
+        proto = self.models[self.model_names[0]]
+        self.joint_layer_names = [name for name, _ in list(proto.named_modules())[1:]]
+        self.joint_layer_names_before_stitch = get_joint_layer_names_before_stitch_for_unet(self.joint_layer_names)
+        self.num_encoder_layers = len(list(get_module_by_name(proto, "0.encoder.model.blocks").named_children()))
+        self.num_decoder_layers = len(list(get_module_by_name(proto, "0.decoder.blocks").named_children()))
+        self.valid_cross_stitch_layer_names = [n.replace(".", "_") for n in self.joint_layer_names_before_stitch]
+        self.true_cross_stitch_layer_names = list(self.joint_layer_names_before_stitch)
+        if channel_wise_stitching:
+            self.stitch_channels = self.get_stitch_channels(proto, self.joint_layer_names_before_stitch)
+            layers = {
+                name: CrossStitchLayer(self.num_tasks, self.stitch_channels[i], mode=stitch_mode)
+                for i, name in enumerate(self.valid_cross_stitch_layer_names)
+            }
+        else:
+            layers = {name: CrossStitchLayer(self.num_tasks, mode=stitch_mode)
+                      for name in self.valid_cross_stitch_layer_names}
+        self.cross_stitch_layers = nn.ModuleDict(layers)
+        self._plan = self._compile_plan(proto)
+
+    # -- which encoder / decoder blocks take part (cross_stitch_model.py:159-169) ------------------
+    def consider_encoder_layer_at_idx(self, layer_idx: int) -> bool:
+        return layer_idx not in (0, self.num_encoder_layers - 1, self.num_decoder_layers - 1)
+
+    def consider_decoder_layer_at_idx(self, layer_idx: int) -> bool:
+        return layer_idx != self.num_decoder_layers - 1
+
+    def _compile_plan(self, proto: nn.Module) -> list:
+        """Flatten the reference's per-step walk into a list of (op, arg) steps."""
+        stitch_after = set(self.joint_layer_names_before_stitch)
+        plan = []
+        for name in self.joint_layer_names:
+            m = re.match(self.encoder_block_regex, name)
+            if m and self.consider_encoder_layer_at_idx(int(m.group(1))):
+                plan.append(("save_skip", None))
+            m = re.match(self.decoder_block_regex, name)
+            if m:
+                idx = int(m.group(1))
+                plan.append(("cat_skip", idx) if self.consider_decoder_layer_at_idx(idx) else ("upsample2", None))
+            layer = get_module_by_name(proto, name)
+            if next(layer.children(), None) is None:
+                plan.append(("leaf", name))
+            if name in stitch_after:
+                plan.append(("stitch", name.replace(".", "_")))
+        return plan
+
+    def forward(self, x: torch.Tensor) -> dict:
+        """Returns task name -> output tensor."""
+        tasks = self.model_names
+        feats = [x for _ in tasks]
+        skips: t.List[list] = [[] for _ in tasks]
+        leaf_cache = self.__dict__.setdefault("_leaf_cache", {})
+        for op, arg in self._plan:
+            if op == "leaf":
+                mods = leaf_cache.get(arg)
+                if mods is None:
+                    mods = leaf_cache[arg] = [get_module_by_name(self.models[t_], arg) for t_ in tasks]
+                feats = [m(f) for m, f in zip(mods, feats)]
+            elif op == "stitch":
+                feats = self.cross_stitch_layers[arg](feats)
+            elif op == "save_skip":
+                for s, f in zip(skips, feats):
+                    s.append(f)
+            elif op == "cat_skip":
+                feats = [concat_slightly_diff_sized_tensors(f, s[-arg - 1]) for f, s in zip(feats, skips)]
+            else:  # upsample2
+                feats = [F.interpolate(f, scale_factor=2, mode="nearest") for f in feats]
+        return dict(zip(tasks, feats))
+
+    def get_stitch_channels(self, random_model: nn.Module, joint_layer_names_before_stitch: t.List[str]) -> t.List[int]:
+        """Channels entering each stitch site: out_channels of the closest preceding conv, plus the
+        skip channels for decoder blocks that concatenate one (cross_stitch_model.py:171-201)."""
+        named = list(random_model.named_modules())[1:]
+        index = {name: i for i, (name, _) in enumerate(named)}
+        channels, skip_channels = [], []
+        for site in joint_layer_names_before_stitch:
+            i = index[site] - 1
+            while not isinstance(named[i][1], nn.Conv2d):
+                i -= 1
+            c = named[i][1].out_channels
+            if "encoder" in site:
+                if self.consider_encoder_layer_at_idx(int(re.match(self.encoder_block_regex, site).group(1))):
+                    skip_channels.append(c)
+            if "decoder" in site:
+                idx = int(re.match(self.decoder_block_regex, site).group(1))
+                if self.consider_decoder_layer_at_idx(idx):
+                    c += skip_channels[-idx - 1]
+            channels.append(c)
+        return channels

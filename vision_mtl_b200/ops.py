@@ -206,7 +206,10 @@ class GateFunction(torch.autograd.Function):
         M = B * H * W
         w2 = weight.detach().reshape(N, K).contiguous()
         y = torch.empty_like(s)
-        z = torch.empty_like(s)
+        # z = conv output is kept for the backward; pure inference on the tensor-core path
+        # fuses everything into one pass and never stores it
+        need_z = training or precision == GATE_FP32_FFMA or any(ctx.needs_input_grad)
+        z = torch.empty_like(s) if need_z else None
         mean = torch.empty(N, dtype=torch.float32, device=h.device)
         invstd = torch.empty(N, dtype=torch.float32, device=h.device)
         lib = _lib.load()
