@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the multi-task training step (BASELINE.json metric: MTL train-step images/sec;
+fused-kernel HBM GB/s vs peak).
+
+    python bench.py --gpus N --steps K --warmup W [--workload csnet|mtan|mtan_nyu] [--impl reference]
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  Prints ONE JSON line.
+
+* ``value``  : images/s, whole job, batch resident in HBM, CUDA-event timed, max over ranks.
+* ``e2e``    : same step through the public API with the batch copied from pinned host memory and
+               the five step scalars read back every step.
+* ``roofline``: the dominant hand-written kernel of the step, algorithmic bytes / CUDA-event time
+               measured live in the timed region, against MEASURED_PEAKS.json.
+* ``cpu_baseline`` (rank 0, N = 1) and ``--impl reference``: the reference's own CPU path --
+               restated in ``oracle/`` and pinned to the reference by tests/golden -- timed on the
+               host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (model, dataset, classes, H, W, per-GPU batch)   -- BASELINE.json configs[1..3]
+    "csnet": ("csnet", "cityscapes", 19, 128, 256, 32),
+    "mtan": ("mtan", "cityscapes", 19, 128, 256, 32),
+    "mtan_nyu": ("mtan", "nyuv2", 14, 256, 256, 16),
+}
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", choices=list(WORKLOADS), default="csnet")
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--conv-tf32", action="store_true", help="allow TF32 in the cuDNN 3x3 convs (default: strict fp32)")
+    ap.add_argument("--gate-precision", default="tc_3xtf32", choices=["tc_3xtf32", "tc_tf32", "fp32_ffma"])
+    ap.add_argument("--stitch-mode", default="reference_diag", choices=["reference_diag", "full_mix"])
+    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lr", type=float, default=5e-4)
+    return ap.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+# reference CPU path (oracle port), used by cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(workload: str, batch_size: int, lr: float):
+    """Build the reference's CPU training step (fwd + CE/SILog + metrics + bwd + Adam) for a
+    ``batch_size`` sample of the workload; returns (step_fn, n_threads)."""
+    from oracle import torch_port as TP
+    from vision_mtl_b200.synthetic import make_batch
+    from vision_mtl_b200.utils.model_utils import get_model_with_dense_preds
+
+    model, dataset, C, H, W, _ = WORKLOADS[workload]
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(11)
+    batch = make_batch(batch_size, H, W, C, dataset, seed=11)
+    if model == "csnet":
+        nets = {"depth": get_model_with_dense_preds(1, None, dict(encoder_weights=None)),
+                "segm": get_model_with_dense_preds(C, None, dict(encoder_weights=None))}
+        net = TP.CSNetOracle(nets, channel_wise_stitching=True).train()
+        params = list(net.parameters())
+        fwd = lambda img: net(img)  # noqa: E731
+    else:
+        from vision_mtl_b200.models.mtan_model import MTANMiniUnet  # structure / init only
+
+        skel = MTANMiniUnet(3, {"depth": 1, "segm": C}, 128, 32, 4)
+        p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+             for k, v in skel.state_dict().items()}
+        params = [v for v in p.values() if v.requires_grad]
+        fwd = lambda img: TP.mtan_forward(p, img, training=True)  # noqa: E731
+    opt = torch.optim.Adam(params, lr=lr)
+
+    def step():
+        opt.zero_grad()
+        raw = fwd(batch["img"])
+        res = TP.step_losses_and_metrics(raw, batch["mask"], batch["depth"], C)
+        res["loss"].backward()
+        opt.step()
+        return float(res["loss"].detach())
+
+    return step, threads
+
+
+def time_cpu_reference(workload: str, batch_size: int, lr: float, steps: int, warmup: int):
+    step, threads = cpu_reference_step_fn(workload, batch_size, lr)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch_size * steps / dt, dt / steps, threads
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    model, dataset, C, H, W, B = WORKLOADS[args.workload]
+    bs = args.cpu_sample_batch
+    ips, sec, threads = time_cpu_reference(args.workload, bs, args.lr, max(args.steps, 1), min(args.warmup, 1))
+    sample = f"{model} train step (fwd+CE/SILog+metrics+bwd+Adam) on a batch-{bs} sample of the {H}x{W} workload, fp32, torch CPU"
+    line = {
+        "impl": "reference", "metric": "mtl_train_step_images_per_sec", "value": ips, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {model} training step, {dataset}-shaped {H}x{W}, {C} classes",
+                   "per_gpu_batch": B, "cpu_sample_batch": bs},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+
+    from vision_mtl_b200 import dist as vdist
+    from vision_mtl_b200 import ops
+    from vision_mtl_b200.synthetic import make_batch
+    from vision_mtl_b200.utils.pipeline_utils import DataShape, init_model
+
+    rank, local_rank, world = vdist.init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.backends.cudnn.allow_tf32 = bool(args.conv_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.conv_tf32)
+    torch.backends.cudnn.benchmark = True
+    ops.default_gate_precision = args.gate_precision
+
+    model, dataset, C, H, W, B = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    torch.manual_seed(11)  # identical weights on every rank
+    margs = argparse.Namespace(model_name=model, backbone_weights=None, channel_wise_stitching=True,
+                               stitch_mode=args.stitch_mode, lr=args.lr, device=dev, ckpt_dir=None)
+    module = init_model(margs, DataShape(num_classes=C, height=H, width=W, name=dataset))
+    module.to(dev)
+    module.model.to(memory_format=torch.channels_last)
+    module.model.train()
+    vdist.wrap_data_parallel(module, local_rank)
+    opt = torch.optim.Adam(module.parameters(), lr=args.lr, fused=True)
+
+    host = make_batch(B, H, W, C, dataset, seed=11 + rank, pin=True)          # pinned host copy
+    resident = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    resident["img"] = resident["img"].contiguous(memory_format=torch.channels_last)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def train_step(batch):
+        opt.zero_grad(set_to_none=True)
+        loss = module.training_step(batch, 0)
+        loss.backward()
+        opt.step()
+        if world > 1:  # the one metric exchange of the step (confusion matrix + loss)
+            module.last_global_stats = vdist.allreduce_step_stats(module.last_confusion, loss)
+        return loss
+
+    def e2e_step():
+        batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        train_step(batch)
+        return module.last_step_scalars.cpu()  # one D2H copy: loss + 4 metrics
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        train_step(resident)
+    barrier()
+
+    # ---- timed region: resident batch, per-launch kernel events recorded live ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ops.kernel_timing() as records:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            train_step(resident)
+        ev1.record()
+        barrier()
+    launches = ops.launch_count()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    kstats = ops.summarize_timing(records)
+
+    # ---- e2e: host batch in, step scalars out, every step ------------------------------------
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    for _ in range(args.steps):
+        scal = e2e_step()
+    ev3.record()
+    barrier()
+    ms_e2e = ev2.elapsed_time(ev3)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ips = B * world * args.steps / (ms * 1e-3)
+    ips_e2e = B * world * args.steps / (ms_e2e * 1e-3)
+    peak, peak_src = measured_peak()
+    top = max(kstats.items(), key=lambda kv: kv[1]["ms"]) if kstats else None
+    roofline = None
+    if top is not None:
+        name, d = top
+        achieved = d["gbps"]
+        traffic = None
+        tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(args.workload, {}).get(name)
+        roofline = {"bound": "hbm", "kernel": "vmtl_" + name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "launches_timed": d["calls"], "avg_launch_ms": d["ms"] / d["calls"],
+                    "algorithmic_bytes_per_launch": d["bytes"] / d["calls"]}
+    line = {
+        "metric": "mtl_train_step_images_per_sec", "value": ips, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload}: {model} training step (fwd + fused CE/SILog/metrics + bwd + Adam), "
+                        f"{dataset}-shaped {H}x{W}, {C} classes, per-GPU batch {B}",
+            "global_batch": B * world, "parallelism": f"dp{world}",
+            "conv_math": "tf32 (cuDNN)" if args.conv_tf32 else "fp32 (cuDNN, TF32 off)",
+            "gate_precision": args.gate_precision, "stitch_mode": args.stitch_mode,
+            "l2": "per-step working set (activations of a batch-%d step) >> 126 MB L2; no explicit flush" % B,
+            "backbone": "stand-in MobileNetV3-Large/Unet (smp/timm not installable offline)" if model != "mtan" else "reference MTAN mini-UNet",
+        },
+        "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes * world,
+                "d2h_bytes_per_step": int(scal.numel() * scal.element_size()) * world,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": {k: {"calls": v["calls"], "ms_per_step": v["ms"] / args.steps, "gbps": v["gbps"],
+                        "frac_of_peak": v["gbps"] / peak} for k, v in sorted(kstats.items())},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        bs = args.cpu_sample_batch
+        cips, csec, threads = time_cpu_reference(args.workload, bs, args.lr, 2, 1)
+        line["cpu_baseline"] = {
+            "value": cips, "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": f"1 warm-up + 2 timed {model} train steps on a batch-{bs} sample of the same {H}x{W} workload "
+                      f"({csec:.1f} s/step), oracle port of the reference's PyTorch CPU path"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

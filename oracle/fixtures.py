@@ -1,9 +1,9 @@
 """Deterministic, RNG-free test data shared by the golden generator, the oracle tests and the
 GPU parity tests.  TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).
 
-Values come from a 31-bit linear congruential sequence in integer arithmetic, so the same
-tensors are rebuilt bit-for-bit on any machine without storing them: golden files only have to
-hold the reference's OUTPUTS.
+Values come from NumPy's frozen legacy MT19937 stream seeded by a CRC of the tensor's NAME, so
+the same tensors are rebuilt bit-for-bit on any machine without storing them: golden files only
+have to hold the reference's OUTPUTS.
 """
 from __future__ import annotations
 
@@ -12,17 +12,13 @@ import zlib
 import numpy as np
 import torch
 
-_A, _C, _M = 1103515245, 12345, 2**31
+_M = 2**31
 
 
 def lcg_uniform(n: int, seed: int) -> np.ndarray:
-    """n values in [-0.5, 0.5), float64, from x_{k+1} = (A x_k + C) mod 2^31 (vectorised jump)."""
-    # closed form of k LCG steps is awkward to vectorise exactly; use a counter-based variant:
-    # x_k = (A * ((seed + k) mod M) * ((seed + k) mod M | 1) + C) mod M, still pure integer math.
-    k = (np.arange(n, dtype=np.uint64) + np.uint64(seed % _M)) % np.uint64(_M)
-    x = (np.uint64(_A) * ((k * (k | np.uint64(1))) % np.uint64(_M)) + np.uint64(_C)) % np.uint64(_M)
-    x = (x * np.uint64(2654435761)) % np.uint64(_M)  # decorrelate neighbouring counters
-    return x.astype(np.float64) / float(_M) - 0.5
+    """n values in [-0.5, 0.5), float64.  ``numpy.random.RandomState`` (MT19937) is NumPy's frozen
+    legacy generator: its stream is guaranteed bit-identical across NumPy versions and platforms."""
+    return np.random.RandomState(seed % (2**32)).random_sample(n) - 0.5
 
 
 def key_seed(key: str, salt: int = 0) -> int:
@@ -79,7 +75,7 @@ def image_batch(B: int, H: int, W: int, num_classes: int, key: str = "batch", de
 
 def summarize(t: torch.Tensor, k: int = 8) -> np.ndarray:
     """Compact, order-sensitive fingerprint of a tensor: [sum, l2, first k, strided k]."""
-    f = t.detach().double().reshape(-1)
+    f = t.detach().cpu().double().reshape(-1)
     n = f.numel()
     head = f[:k]
     stride = max(n // k, 1)

@@ -32,9 +32,14 @@ XSTITCH_CASES = [  # (name, T, B, C, H, W, channel_wise)
     ("t3_cw", 3, 1, 12, 3, 5, True),
 ]
 MTAN_CASES = {  # name -> (hidden, first_channel, levels, B, H, W, classes)
-    "mtan_h128": (128, 32, 2, 2, 32, 64, 19),
-    "mtan_h64": (64, 32, 2, 2, 16, 32, 14),
+    "mtan_h128": (128, 32, 2, 1, 16, 32, 19),
+    "mtan_h64": (64, 32, 2, 1, 16, 16, 14),
 }
+# A ReLU input (or a max-pool runner-up) closer to the decision boundary than this can flip
+# between two correct fp32 implementations; one flipped element perturbs every upstream weight
+# gradient by ~1e-2 relative.  Golden MTAN cases are searched (over the fixture salt) to have no
+# activation this close, so that a 1e-4 gradient bar is meaningful.
+FLIP_MARGIN = 4e-6
 
 
 def _np(t):
@@ -65,16 +70,59 @@ def gen_silog(ref, out):
     out["silog/dlogit"] = _np(logit.grad)
 
 
+def _flip_margin(net, img):
+    """Smallest distance of any ReLU input / 2x2 max-pool decision from its boundary."""
+    margins = []
+
+    def relu_hook(_m, inp, _out):
+        margins.append(float(inp[0].detach().abs().min()))
+
+    def pool_hook(_m, inp, _out):
+        x = inp[0].detach()
+        win = F.unfold(x.reshape(-1, 1, *x.shape[2:]), 2, stride=2)  # [N*C, 4, L]
+        top2 = win.topk(2, dim=1).values
+        live = top2[:, 0] > 0  # all-zero windows (post-ReLU) route no gradient either way
+        if live.any():
+            margins.append(float((top2[:, 0] - top2[:, 1])[live].min()))
+
+    hooks = []
+    for m in net.modules():
+        if isinstance(m, nn.ReLU):
+            hooks.append(m.register_forward_hook(relu_hook))
+        elif isinstance(m, nn.MaxPool2d):
+            hooks.append(m.register_forward_hook(pool_hook))
+    net(img)
+    for h in hooks:
+        h.remove()
+    return min(margins)
+
+
 def gen_mtan(ref, out):
     for name, (hid, first, levels, B, H, W, C) in MTAN_CASES.items():
         torch.manual_seed(0)
-        net = ref["MTANMiniUnet"](3, {"depth": 1, "segm": C}, task_subnets_hidden_channels=hid,
-                                  encoder_first_channel=first, encoder_num_channels=levels)
-        net.load_state_dict(FX.fill_state_dict(net.state_dict()))
-        batch = FX.image_batch(B, H, W, C, name)
+
+        def make(salt, dtype=torch.float32):
+            net = ref["MTANMiniUnet"](3, {"depth": 1, "segm": C}, task_subnets_hidden_channels=hid,
+                                      encoder_first_channel=first, encoder_num_channels=levels)
+            net.load_state_dict(FX.fill_state_dict(net.state_dict(), salt=salt))
+            for m in net.modules():  # the margin hooks need the pre-activation, not the clamped tensor
+                if isinstance(m, nn.ReLU):
+                    m.inplace = False
+            return net.to(dtype).train()
+
+        for salt in range(400):
+            batch = FX.image_batch(B, H, W, C, f"{name}/{salt}")
+            margin = _flip_margin(make(salt), batch["img"])
+            if margin > FLIP_MARGIN:
+                break
+        else:
+            raise RuntimeError("no well-conditioned fixture found")
+        print(f"{name}: salt {salt}, flip margin {margin:.2e}")
+        net = make(salt)
+        out[f"{name}/salt"] = np.array([salt], dtype=np.int64)
+        out[f"{name}/flip_margin"] = np.array([margin])
         # --- one training step of the reference path: lit_module.py:78-81,120-144 restated with the
         #     reference's own loss classes (lit_module itself needs pytorch_lightning/torchmetrics)
-        net.train()
         raw = net(batch["img"])
         depth_pred = torch.sigmoid(raw["depth"]).permute(0, 2, 3, 1)
         preds = torch.argmax(F.softmax(raw["segm"], dim=1), dim=1)

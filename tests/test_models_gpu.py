@@ -1,6 +1,21 @@
-"""GPU parity of the drop-in models / step module against (a) the committed reference outputs in
-tests/golden and (b) the CPU oracle run on the same inputs.  Tolerance: 1e-4 relative
-(tensor-wise) on losses, logits, gradients and depth metrics; confusion matrices bit-exact."""
+"""GPU parity of the drop-in models / step module.
+
+Chain of evidence:
+  reference (CPU, unmodified)  ==  tests/golden/*.npz        (oracle/make_golden.py)
+  tests/golden                 ==  CPU oracle                 (tests/test_oracle_golden.py)
+  tests/golden, CPU oracle     ==  product on the B200        (this file)
+
+Bars (BASELINE.json north_star): losses, logits, gradients and depth metrics within 1e-4
+relative (tensor-wise: max|got-ref| <= 1e-4 * max|ref|, or on the gradient-norm scale for
+fingerprints); confusion matrices bit-exact.
+
+Gradients of a deep ReLU network are only reproducible between two correct fp32 implementations
+when no ReLU input / max-pool runner-up sits within round-off of its decision boundary (one
+flipped element perturbs every upstream weight gradient by ~1e-2).  The golden MTAN fixtures are
+searched to be free of such near-flips (oracle/make_golden.py:FLIP_MARGIN); for CSNet the
+comparison runs the oracle's flat walk on the SAME device, where every activation in front of a
+stitch site is bit-identical and the reference-mode stitch itself is a single fp32 multiply.
+"""
 import os
 
 import numpy as np
@@ -8,6 +23,7 @@ import pytest
 import torch
 
 from oracle import fixtures as FX
+from oracle import kernels_ref as K
 from oracle import metrics_np as MN
 from oracle import torch_port as TP
 from oracle.make_golden import MTAN_CASES
@@ -31,15 +47,6 @@ def to_dev(batch):
     return {k: v.to(dev()) for k, v in batch.items()}
 
 
-def near_tie_ok(pred, pred_ref, logits):
-    """Mismatching argmax pixels must be fp32 near-ties of the two top logits."""
-    mism = pred != pred_ref
-    if not mism.any():
-        return True
-    top2 = logits.permute(0, 2, 3, 1)[mism].topk(2, dim=-1).values
-    return bool(((top2[:, 0] - top2[:, 1]).abs() < 1e-4).all())
-
-
 @pytest.mark.parametrize("name", list(MTAN_CASES))
 @pytest.mark.parametrize("precision", ["tc_3xtf32", "fp32_ffma"])
 def test_mtan_step_vs_reference_golden(name, precision):
@@ -49,44 +56,50 @@ def test_mtan_step_vs_reference_golden(name, precision):
 
     hid, first, levels, B, H, W, C = MTAN_CASES[name]
     g = np.load(os.path.join(GOLDEN, "mtan.npz"))
+    salt = int(g[f"{name}/salt"][0])
     old = ops.default_gate_precision
     ops.default_gate_precision = precision
     try:
         net = MTANMiniUnet(3, {"depth": 1, "segm": C}, hid, first, levels)
-        sd = FX.fill_state_dict(net.state_dict())
-        net.load_state_dict(sd)
+        net.load_state_dict(FX.fill_state_dict(net.state_dict(), salt=salt))
         net.to(dev()).to(memory_format=torch.channels_last)
         module = MTLModule(net, num_classes=C, device=dev())
-        batch = to_dev(FX.image_batch(B, H, W, C, name))
+        batch = to_dev(FX.image_batch(B, H, W, C, f"{name}/{salt}"))
         net.train()
         loss = module.training_step(batch, 0)
         loss.backward()
         scal = module.last_step_scalars.cpu().double().numpy()  # loss, acc, jaccard, fbeta, mae
         assert abs(scal[0] - g[f"{name}/losses"][0]) <= TOL * abs(g[f"{name}/losses"][0])
         assert abs(scal[4] - g[f"{name}/mae"][0]) <= TOL * abs(g[f"{name}/mae"][0])
-        # confusion matrix from the fused head+argmax vs the reference's predictions
-        pred_ref = torch.from_numpy(g[f"{name}/preds"].astype(np.int64))
-        cm_ref = MN.confusion_matrix(pred_ref.numpy(), batch["mask"].cpu().numpy(), C)
-        cm = module.last_confusion.cpu().numpy()
-        if not np.array_equal(cm, cm_ref):
-            logits_ref = torch.from_numpy(g[f"{name}/segm_logits"])
-            assert np.abs(cm - cm_ref).sum() <= 4, "confusion differs by more than near-tie pixels"
-            assert near_tie_ok(torch.from_numpy(g[f"{name}/preds"].astype(np.int64)), pred_ref, logits_ref)
-        ref_m = MN.all_seg_metrics(cm)
+        # confusion matrix of the fused head+argmax == the one built from the reference's predictions
+        pred_ref = g[f"{name}/preds"].astype(np.int64)
+        cm_ref = MN.confusion_matrix(pred_ref, batch["mask"].cpu().numpy(), C)
+        assert np.array_equal(module.last_confusion.cpu().numpy(), cm_ref), "confusion matrix not bit-exact"
+        ref_m = MN.all_seg_metrics(cm_ref)
         np.testing.assert_allclose(scal[1:4], [ref_m["accuracy"], ref_m["jaccard_index"], ref_m["fbeta_score"]], rtol=1e-6)
-        # gradients and BN buffers: fingerprints of every parameter vs the reference's
-        worst = 0.0
+        # every parameter gradient (fingerprint: sum, l2, 16 samples) on the scale of its l2 norm
+        worst, worst_k = 0.0, None
         for k, p in net.named_parameters():
             ref = g[f"{name}/grad/{k}"]
-            got = FX.summarize(p.grad)
-            worst = max(worst, float(np.abs(got - ref).max() / max(ref[1], 1e-12)))
-        assert worst <= 3e-4, f"worst gradient fingerprint deviation {worst:.3e} (relative to the grad norm)"
+            if ref[1] < 1e-6:  # conv biases feeding a training-mode BN: analytically zero gradient
+                assert float(p.grad.norm()) < 1e-4
+                continue
+            d = float(np.abs(FX.summarize(p.grad) - ref).max() / ref[1])
+            if d > worst:
+                worst, worst_k = d, k
+        assert worst <= TOL, f"worst gradient deviation {worst:.3e} (of the grad norm) at {worst_k}"
         for k, b in net.named_buffers():
             if "num_batches_tracked" in k:
                 assert int(b) == 1
             else:
                 np.testing.assert_allclose(FX.summarize(b.float()), g[f"{name}/buf/{k}"], rtol=1e-4, atol=1e-6, err_msg=k)
-        # full logits through the API-compatible forward (eval mode, running stats just updated)
+        # API-compatible forward returning full logits (training-mode BN, like the reference step)
+        net.load_state_dict({k: v.to(dev()) for k, v in FX.fill_state_dict(net.state_dict(), salt=salt).items()})
+        with torch.no_grad():
+            raw = net(batch["img"])
+        assert rel_err(raw["segm"], g[f"{name}/segm_logits"]) <= TOL
+        assert rel_err(raw["depth"], g[f"{name}/depth_logits"]) <= TOL
+        # eval mode (predict path) on the running statistics that step just produced
         net.eval()
         with torch.no_grad():
             raw_e = net(batch["img"])
@@ -96,42 +109,89 @@ def test_mtan_step_vs_reference_golden(name, precision):
         ops.default_gate_precision = old
 
 
-def test_mtan_full_gradients_vs_oracle():
-    """Every gradient tensor (not just fingerprints) against the CPU oracle, Cityscapes classes."""
+def test_mtan_cityscapes_shape_vs_oracle_forward():
+    """Full-width MTAN (4 levels, hidden 128, 13.3 M parameters) on a 128x256 image: forward
+    quantities against the CPU oracle (gradients at this size are flip-limited, see module doc)."""
     from vision_mtl_b200.lit_module import MTLModule
     from vision_mtl_b200.models.mtan_model import MTANMiniUnet
 
-    C, B, H, W = 19, 2, 32, 64
-    net = MTANMiniUnet(3, {"depth": 1, "segm": C}, 128, 32, 3)
-    sd = FX.fill_state_dict(net.state_dict(), salt=3)
+    C, B, H, W = 19, 1, 128, 256
+    net = MTANMiniUnet(3, {"depth": 1, "segm": C}, 128, 32, 4)
+    sd = FX.fill_state_dict(net.state_dict(), salt=1)
     net.load_state_dict(sd)
-    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
-         for k, v in sd.items()}
-    batch = FX.image_batch(B, H, W, C, "full-grad")
-    raw = TP.mtan_forward(p, batch["img"], training=True)
+    batch = FX.image_batch(B, H, W, C, "cityscapes-shape")
+    p = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        raw = TP.mtan_forward(p, batch["img"], training=True)
     res = TP.step_losses_and_metrics(raw, batch["mask"], batch["depth"], C)
-    res["loss"].backward()
-
     net.to(dev()).to(memory_format=torch.channels_last).train()
     module = MTLModule(net, num_classes=C, device=dev())
-    loss = module.training_step(to_dev(batch), 0)
+    with torch.no_grad():
+        out = module.fused_losses_and_metrics(*[to_dev(batch)[k] for k in ("img", "mask", "depth")], want_preds=True)
+    assert rel_err(out["loss_segm"], res["loss_segm"]) <= TOL
+    assert rel_err(out["loss_depth"], res["loss_depth"]) <= TOL
+    assert rel_err(out["mae"], torch.tensor(res["mae"])) <= TOL
+    assert rel_err(out["depth_predictions"], res["depth_predictions"]) <= TOL
+    cm = module.last_confusion.cpu().numpy()
+    mism = out["segm_predictions"].cpu().long() != res["segm_predictions"]
+    if mism.any():  # only fp32 near-ties of the two top logits may differ (SURVEY F5)
+        top2 = raw["segm"].permute(0, 2, 3, 1)[mism].topk(2, dim=-1).values
+        assert ((top2[:, 0] - top2[:, 1]).abs() < 1e-4).all() and int(mism.sum()) <= 8
+    assert np.abs(cm - res["confusion"]).sum() <= 2 * int(mism.sum())
+    assert cm.sum() == B * H * W
+    for k, b in net.named_buffers():
+        if "running" in k:
+            assert rel_err(b, p[k]) <= TOL, k
+
+
+@pytest.mark.parametrize("cw", [True, False])
+@pytest.mark.parametrize("mode", ["reference_diag", "full_mix"])
+def test_csnet_vs_oracle_same_device(cw, mode):
+    """Product CSNet (compiled plan + stitch kernels) vs the oracle's flat walk with torch ops, same
+    weights, both on the GPU: logits, loss and every gradient."""
+    from vision_mtl_b200.lit_module import MTLModule
+    from vision_mtl_b200.models import CSNet
+    from vision_mtl_b200.utils.model_utils import get_model_with_dense_preds
+
+    def build():
+        return {"depth": get_model_with_dense_preds(1, None, dict(encoder_weights=None)),
+                "segm": get_model_with_dense_preds(19, None, dict(encoder_weights=None))}
+
+    net = CSNet(build(), channel_wise_stitching=cw, stitch_mode=mode)
+    sd = FX.fill_state_dict(net.state_dict())
+    net.load_state_dict(sd)
+    orc = TP.CSNetOracle(build(), channel_wise_stitching=cw, mode=mode)
+    orc.load_state_dict(sd)
+    net.to(dev()).train()
+    orc.to(dev()).train()
+    batch = to_dev(FX.image_batch(2, 64, 64, 19, "csnet-same-device"))
+    raw_o = orc(batch["img"])
+    res_loss = K.cross_entropy(raw_o["segm"], batch["mask"]) + K.silog(K.depth_predictions(raw_o["depth"]), batch["depth"])
+    res_loss.backward()
+    module = MTLModule(net, num_classes=19, device=dev())
+    loss = module.training_step(batch, 0)
     loss.backward()
-    assert rel_err(loss, res["loss"]) <= TOL
-    assert np.abs(module.last_confusion.cpu().numpy() - res["confusion"]).sum() <= 4
+    assert rel_err(loss, res_loss) <= TOL
+    go = dict(orc.named_parameters())
     bad = {}
-    for k, q in net.named_parameters():
-        e = rel_err(q.grad, p[k].grad)
-        # conv biases in front of a training-mode BN have analytically zero gradient: compare on the
-        # scale of the matching weight gradient instead of their own (noise-level) magnitude
-        if k.endswith("bias") and p[k].grad.abs().max() < 1e-5:
+    for k, p in net.named_parameters():
+        ref = go[k].grad
+        if ref is None or float(ref.abs().max()) < 1e-7:
+            assert p.grad is None or float(p.grad.abs().max()) < 1e-5, k
             continue
-        if e > 2e-4:
+        e = rel_err(p.grad, ref) if p.grad is not None else float("inf")
+        if e > TOL:
             bad[k] = e
-    assert not bad, f"gradient mismatches: {bad}"
+    assert not bad, f"{len(bad)} gradient mismatches, worst {max(bad.values()):.3e}: {list(bad)[:5]}"
+    if mode == "reference_diag":  # SURVEY F1: off-diagonal alphas get exactly-zero gradients
+        for layer in net.cross_stitch_layers.values():
+            gr = layer.weights.grad
+            assert float(gr[0, 1].abs().max()) == 0.0 and float(gr[1, 0].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("name,cw", [("csnet_cw", True), ("csnet_lw", False)])
-def test_csnet_step_vs_reference_golden(name, cw):
+def test_csnet_forward_vs_reference_golden(name, cw):
+    """Logits and loss of the reference CSNet class (run over the stand-in backbone on CPU)."""
     from vision_mtl_b200.lit_module import MTLModule
     from vision_mtl_b200.models import CSNet
     from vision_mtl_b200.utils.model_utils import get_model_with_dense_preds
@@ -143,30 +203,14 @@ def test_csnet_step_vs_reference_golden(name, cw):
     net.load_state_dict(FX.fill_state_dict(net.state_dict()))
     net.to(dev()).to(memory_format=torch.channels_last).train()
     batch = to_dev(FX.image_batch(2, 64, 64, 19, name))
-    batch["img"] = batch["img"].contiguous(memory_format=torch.channels_last)
-    raw = net(batch["img"])
+    module = MTLModule(net, num_classes=19, device=dev())
+    loss = module.training_step(batch, 0)
+    assert abs(loss.item() - g[f"{name}/losses"][0]) <= TOL * abs(g[f"{name}/losses"][0])
+    net.load_state_dict({k: v.to(dev()) for k, v in FX.fill_state_dict(net.state_dict()).items()})
+    with torch.no_grad():
+        raw = net(batch["img"])
     assert rel_err(raw["segm"], g[f"{name}/segm_logits"]) <= TOL
     assert rel_err(raw["depth"], g[f"{name}/depth_logits"]) <= TOL
-    module = MTLModule(net, num_classes=19, device=dev())
-    net.load_state_dict({k: v.to(dev()) for k, v in FX.fill_state_dict(net.state_dict()).items()})  # reset BN buffers
-    loss = module.training_step(batch, 0)
-    loss.backward()
-    assert abs(loss.item() - g[f"{name}/losses"][0]) <= TOL * abs(g[f"{name}/losses"][0])
-    worst, worst_k = 0.0, None
-    for k, p in net.named_parameters():
-        key = f"{name}/grad/{k}"
-        if key not in g.files:
-            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
-            continue
-        ref = g[key]
-        dev_ = float(np.abs(FX.summarize(p.grad) - ref).max() / max(ref[1], 1e-12))
-        if dev_ > worst:
-            worst, worst_k = dev_, k
-    assert worst <= 1e-3, f"worst gradient fingerprint deviation {worst:.3e} at {worst_k}"
-    # off-diagonal alphas get exactly-zero gradients in reference mode
-    for layer in net.cross_stitch_layers.values():
-        gr = layer.weights.grad.cpu()
-        assert float(gr[0, 1].abs().max()) == 0.0 and float(gr[1, 0].abs().max()) == 0.0
 
 
 def test_module_api_compat_paths():

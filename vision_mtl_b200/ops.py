@@ -173,7 +173,7 @@ class CrossStitchFunction(torch.autograd.Function):
         xs = [_nhwc(x) for x in xs]
         ys = xstitch_forward(xs, alpha, mode)
         ctx.mode = mode
-        ctx.need_dx = any(x.requires_grad for x in xs)
+        ctx.need_dx = any(ctx.needs_input_grad[2:])
         ctx.save_for_backward(alpha, *xs)
         return tuple(ys)
 
