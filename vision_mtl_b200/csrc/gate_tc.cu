@@ -79,7 +79,7 @@ __device__ __forceinline__ void load_tile_regs(const float* __restrict__ src, in
   }
 }
 
-template <int KATOMS, int ROWS, bool SPLIT>
+template <int KATOMS, int ROWS, bool SPLIT, bool MN32 = false>
 __device__ __forceinline__ void store_tile_split(uint8_t* hi_base, uint8_t* lo_base, int atom_bytes,
                                                  const float4 (&regs)[ROWS * KATOMS * 8 / kTcThreads]) {
   constexpr int K4 = KATOMS * 8;
@@ -89,7 +89,7 @@ __device__ __forceinline__ void store_tile_split(uint8_t* hi_base, uint8_t* lo_b
     const int q = it * kTcThreads + threadIdx.x;
     const int row = q / K4, kc = q % K4;
     const int atom = kc >> 3, c = kc & 7;
-    const uint32_t off = (uint32_t)(atom * atom_bytes) + sw128_off(row, c);
+    const uint32_t off = (uint32_t)(atom * atom_bytes) + (MN32 ? sw128b32_off(row, c) : sw128_off(row, c));
     const float4 a = regs[it];
     float4 hi = make_float4(tf32_hi(a.x), tf32_hi(a.y), tf32_hi(a.z), tf32_hi(a.w));
     *reinterpret_cast<float4*>(hi_base + off) = hi;
@@ -368,10 +368,346 @@ int gate_tc_fwd_eval(const float* h, const float* s, const float* W, const float
   return dispatch_fwd<true>(h, W, bias, s, coefA, coefB, M, K, N, split3, y, nullptr, tc_grid(M), st);
 }
 
-int gate_tc_bwd_gemm(const float*, const float*, const float*, const float*, const float*, const GateWs&,
-                     const float*, int64_t, int, int, int, float*, float*, int, int*, float*,
-                     cudaStream_t) {
-  return VMTL_EUNSUPPORTED;  // falls back to the materialised-dz path in gate.cu for now
+// =============================================================================================
+// Backward, phase B on tensor cores (N in {32, 64}, K = 128).
+//
+//   B1  gate_tc_dh_kernel : per 128-row tile, dz = gamma*invstd*(du - c1 - zhat*c2) is rebuilt
+//       from (dy, s, z) in registers, written once to a [M,N] scratch, split into tf32 hi/lo in
+//       swizzled smem and contracted with W^T:  dh[128 x K] = dz[128 x N] @ W[N x K]  (K-major
+//       operands, N/8 K-steps x 3 passes, accumulator double-buffered in TMEM).  db = sum dz is
+//       accumulated per thread (fixed column group) and reduced once per CTA.
+//   B2  gate_tc_dw_kernel : dW^T[K x N] += h^T[K x rows] @ dz[rows x N].  Both operands are read
+//       "MN-major" straight from their natural row-major tiles (one 128-byte row of 32 channels
+//       per pixel = one K index) in the SWIZZLE_128B_BASE32B layout tf32 requires; the 8 pixel
+//       rows of one MMA K-step are two 4-row groups.  The accumulator stays in TMEM across ALL
+//       tiles of the CTA and is drained once -> one [N x K] partial per CTA, fixed-order second
+//       stage.
+// =============================================================================================
+template <int NATOMS>
+struct DhSmem {
+  static constexpr int kAtom = kTileM * 128;                    // [128 rows x 128 B]
+  static constexpr int kAhi = 0;                                // dz hi, NATOMS atoms
+  static constexpr int kAlo = kAhi + NATOMS * kAtom;
+  static constexpr int kBhi = kAlo + NATOMS * kAtom;            // W^T hi: rows = k (128), NATOMS atoms
+  static constexpr int kBlo = kBhi + NATOMS * kAtom;
+  static constexpr int kMisc = kBlo + NATOMS * kAtom;
+  static constexpr int kBytes = kMisc + 64 + 6 * 64 * 4 + 1024;
+};
+
+template <int NATOMS, bool SPLIT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    gate_tc_dh_kernel(const float* __restrict__ dy, const float* __restrict__ s, const float* __restrict__ z,
+                      const float* __restrict__ W /* [N,128] */, const float* __restrict__ coefA,
+                      const float* __restrict__ coefB, const float* __restrict__ mean,
+                      const float* __restrict__ invstd, const float* __restrict__ c1,
+                      const float* __restrict__ c2, int64_t M, float* __restrict__ dz_out,
+                      float* __restrict__ dh, float* __restrict__ db_partial /* [grid][N] */) {
+  using L = DhSmem<NATOMS>;
+  constexpr int N = NATOMS * 32;
+  constexpr int KH = 128;                 // hidden width = MMA N
+  constexpr int N4 = N / 4;
+  constexpr int PER = kTileM * N4 / kTcThreads;  // float4 of dz per thread per tile (4 or 8)
+  constexpr uint32_t kTmemCols = 2 * KH;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sAhi = smem + L::kAhi;
+  uint8_t* sAlo = smem + L::kAlo;
+  uint8_t* sBhi = smem + L::kBhi;
+  uint8_t* sBlo = smem + L::kBlo;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::kMisc);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::kMisc + 16);
+  float* s_coef = reinterpret_cast<float*>(smem + L::kMisc + 64);  // [6][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar = smem_u32(s_bar);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), kTmemCols);
+  for (int i = threadIdx.x; i < N; i += kTcThreads) {
+    s_coef[0 * 64 + i] = coefA[i];
+    s_coef[1 * 64 + i] = coefB[i];
+    s_coef[2 * 64 + i] = mean[i];
+    s_coef[3 * 64 + i] = invstd[i];
+    s_coef[4 * 64 + i] = c1[i];
+    s_coef[5 * 64 + i] = c2[i];
+  }
+  // W^T staging: element (k, n) of the B operand = W[n][k]; rows k, K-major along n
+  for (int e = threadIdx.x; e < N * KH; e += kTcThreads) {
+    const int n = e / KH, k = e - n * KH;  // coalesced read of W
+    const float w = W[e];
+    const float hi = tf32_hi(w);
+    const uint32_t off = (uint32_t)((n >> 5) * L::kAtom) + sw128_off(k, (n & 31) >> 2) + (uint32_t)((n & 3) << 2);
+    *reinterpret_cast<float*>(sBhi + off) = hi;
+    if (SPLIT) *reinterpret_cast<float*>(sBlo + off) = w - hi;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int64_t ntiles = (M + kTileM - 1) / kTileM;
+  const int64_t nitems = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  // per-thread column group is fixed: q = it*256 + tid, c4 = q % N4 = tid % N4
+  const int c4 = threadIdx.x % N4;
+  float4 cA, cB, cMu, cRs, cK1, cK2;
+  {
+    const float4* p = reinterpret_cast<const float4*>(s_coef);
+    cA = p[0 * 16 + c4]; cB = p[1 * 16 + c4]; cMu = p[2 * 16 + c4];
+    cRs = p[3 * 16 + c4]; cK1 = p[4 * 16 + c4]; cK2 = p[5 * 16 + c4];
+  }
+  float4 db_acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 rdy[PER], rs[PER], rz[PER];
+  auto load_inputs = [&](int64_t tile) {
+    load_tile_regs<NATOMS, kTileM>(dy, tile * kTileM, M, rdy);
+    load_tile_regs<NATOMS, kTileM>(s, tile * kTileM, M, rs);
+    load_tile_regs<NATOMS, kTileM>(z, tile * kTileM, M, rz);
+  };
+  auto dz1 = [](float g, float sv, float zv, float A, float B, float mu, float r, float k1, float k2) {
+    const float a = sigmoidf_acc(fmaf(A, zv, B));
+    return A * (g * sv * a * (1.f - a) - k1 - (zv - mu) * r * k2);
+  };
+  // dz of the tile held in registers -> global scratch + hi/lo smem operand
+  auto produce_dz = [&](int64_t tile) {
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+      const int q = it * kTcThreads + threadIdx.x;
+      const int row = q / N4, kc = q % N4;
+      const int64_t grow = tile * kTileM + row;
+      float4 d;
+      d.x = dz1(rdy[it].x, rs[it].x, rz[it].x, cA.x, cB.x, cMu.x, cRs.x, cK1.x, cK2.x);
+      d.y = dz1(rdy[it].y, rs[it].y, rz[it].y, cA.y, cB.y, cMu.y, cRs.y, cK1.y, cK2.y);
+      d.z = dz1(rdy[it].z, rs[it].z, rz[it].z, cA.z, cB.z, cMu.z, cRs.z, cK1.z, cK2.z);
+      d.w = dz1(rdy[it].w, rs[it].w, rz[it].w, cA.w, cB.w, cMu.w, cRs.w, cK1.w, cK2.w);
+      if (grow >= M) d = make_float4(0.f, 0.f, 0.f, 0.f);
+      else stg_stream(reinterpret_cast<float4*>(dz_out) + grow * N4 + kc, d);
+      db_acc.x += d.x; db_acc.y += d.y; db_acc.z += d.z; db_acc.w += d.w;
+      const uint32_t off = (uint32_t)((kc >> 3) * L::kAtom) + sw128_off(row, kc & 7);
+      const float4 hi = make_float4(tf32_hi(d.x), tf32_hi(d.y), tf32_hi(d.z), tf32_hi(d.w));
+      *reinterpret_cast<float4*>(sAhi + off) = hi;
+      if (SPLIT)
+        *reinterpret_cast<float4*>(sAlo + off) = make_float4(d.x - hi.x, d.y - hi.y, d.z - hi.z, d.w - hi.w);
+    }
+  };
+  auto issue = [&](int64_t it) {
+    constexpr uint32_t idesc = idesc_tf32(kTileM, KH, 0, 0);
+    const uint32_t d_tmem = tmem_base + (uint32_t)((it & 1) * KH);
+    const uint32_t aH = smem_u32(sAhi), aL = smem_u32(sAlo), bH = smem_u32(sBhi), bL = smem_u32(sBlo);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int atom = 0; atom < NATOMS; ++atom)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t o = atom * L::kAtom + ks * 32;
+        const uint64_t dAh = smem_desc_sw128(aH + o, 16, 1024), dBh = smem_desc_sw128(bH + o, 16, 1024);
+        if (SPLIT) {
+          mma_tf32(d_tmem, smem_desc_sw128(aL + o, 16, 1024), dBh, idesc, acc);
+          acc = 1;
+          mma_tf32(d_tmem, dAh, smem_desc_sw128(bL + o, 16, 1024), idesc, 1);
+        }
+        mma_tf32(d_tmem, dAh, dBh, idesc, acc);
+        acc = 1;
+      }
+    mma_commit(bar);
+  };
+  auto epilogue = [&](int64_t it) {
+    const int64_t tile = blockIdx.x + it * gridDim.x;
+    const int64_t row = tile * kTileM + (warp & 3) * 32 + lane;
+    const int col0 = (warp >> 2) * (KH / 2);
+    const uint32_t taddr = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + (uint32_t)((it & 1) * KH + col0);
+#pragma unroll
+    for (int j = 0; j < KH / 2; j += 16) {
+      float t16[16];
+      tmem_ld16(taddr + j, t16);
+      if (row < M) {
+        float4* o = reinterpret_cast<float4*>(dh + row * KH + col0 + j);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          stg_stream(o + e, make_float4(t16[4 * e], t16[4 * e + 1], t16[4 * e + 2], t16[4 * e + 3]));
+      }
+    }
+  };
+
+  if (nitems > 0) load_inputs(blockIdx.x);
+  for (int64_t it = 0; it < nitems; ++it) {
+    const int64_t tile = blockIdx.x + it * gridDim.x;
+    if (it > 0) {
+      mbar_wait(bar, (uint32_t)((it - 1) & 1));
+      tc_fence_after_sync();
+    }
+    produce_dz(tile);
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after_sync();
+      issue(it);
+    }
+    if (it + 1 < nitems) load_inputs(tile + gridDim.x);
+    if (it > 0 && dh) epilogue(it - 1);
+  }
+  if (nitems > 0) {
+    mbar_wait(bar, (uint32_t)((nitems - 1) & 1));
+    tc_fence_after_sync();
+    if (dh) epilogue(nitems - 1);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+  // db partial of this CTA: threads sharing a column group summed in fixed order
+  float4* s_red = reinterpret_cast<float4*>(sAhi);
+  s_red[threadIdx.x] = db_acc;
+  __syncthreads();
+  if (threadIdx.x < N4) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = threadIdx.x; t < kTcThreads; t += N4) {
+      const float4 v = s_red[t];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    reinterpret_cast<float4*>(db_partial + (int64_t)blockIdx.x * N)[threadIdx.x] = a;
+  }
+}
+
+template <int NATOMS>
+struct DwSmem {
+  static constexpr int kAtom = kTileM * 128;
+  static constexpr int kHhi = 0;                         // h tile, 4 atoms (k), MN-major A
+  static constexpr int kHlo = kHhi + 4 * kAtom;
+  static constexpr int kDhi = kHlo + 4 * kAtom;          // dz tile, NATOMS atoms (n), MN-major B
+  static constexpr int kDlo = kDhi + NATOMS * kAtom;
+  static constexpr int kMisc = kDlo + NATOMS * kAtom;
+  static constexpr int kBytes = kMisc + 64 + 1024;
+};
+
+template <int NATOMS, bool SPLIT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    gate_tc_dw_kernel(const float* __restrict__ h, const float* __restrict__ dz, int64_t M,
+                      float* __restrict__ dw_partial /* [grid][N][128] */) {
+  using L = DwSmem<NATOMS>;
+  constexpr int N = NATOMS * 32;
+  constexpr int KH = 128;
+  constexpr uint32_t kTmemCols = N < 32 ? 32 : N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sHhi = smem + L::kHhi;
+  uint8_t* sHlo = smem + L::kHlo;
+  uint8_t* sDhi = smem + L::kDhi;
+  uint8_t* sDlo = smem + L::kDlo;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::kMisc);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::kMisc + 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar = smem_u32(s_bar);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int64_t ntiles = (M + kTileM - 1) / kTileM;
+  const int64_t nitems = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  float4 rh[kTileM * 32 / kTcThreads];
+  float4 rd[kTileM * NATOMS * 8 / kTcThreads];
+  if (nitems > 0) {
+    load_tile_regs<4, kTileM>(h, (int64_t)blockIdx.x * kTileM, M, rh);
+    load_tile_regs<NATOMS, kTileM>(dz, (int64_t)blockIdx.x * kTileM, M, rd);
+  }
+  for (int64_t it = 0; it < nitems; ++it) {
+    const int64_t tile = blockIdx.x + it * gridDim.x;
+    if (it > 0) {
+      mbar_wait(bar, (uint32_t)((it - 1) & 1));
+      tc_fence_after_sync();
+    }
+    store_tile_split<4, kTileM, SPLIT, true>(sHhi, sHlo, L::kAtom, rh);
+    store_tile_split<NATOMS, kTileM, SPLIT, true>(sDhi, sDlo, L::kAtom, rd);
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after_sync();
+      // D[k (128) x n (N)] += sum over the tile's 128 pixel rows, 8 rows (= one 1024 B group) per MMA
+      constexpr uint32_t idesc = idesc_tf32(KH, N, 1, 1);
+      const uint32_t hH = smem_u32(sHhi), hL = smem_u32(sHlo), dH = smem_u32(sDhi), dL = smem_u32(sDlo);
+      uint32_t acc = it > 0 ? 1u : 0u;
+#pragma unroll 1
+      for (int ks = 0; ks < kTileM / 8; ++ks) {
+        const uint32_t o = ks * 1024;
+        // MN-major tf32: LBO = stride between 32-element atoms along M/N, SBO = 4-row group stride
+        const uint64_t aH = smem_desc_mn_tf32(hH + o, L::kAtom, 512), bH = smem_desc_mn_tf32(dH + o, L::kAtom, 512);
+        if (SPLIT) {
+          mma_tf32(tmem_base, smem_desc_mn_tf32(hL + o, L::kAtom, 512), bH, idesc, acc);
+          acc = 1;
+          mma_tf32(tmem_base, aH, smem_desc_mn_tf32(dL + o, L::kAtom, 512), idesc, 1);
+        }
+        mma_tf32(tmem_base, aH, bH, idesc, acc);
+        acc = 1;
+      }
+      mma_commit(bar);
+    }
+    if (it + 1 < nitems) {
+      load_tile_regs<4, kTileM>(h, (tile + gridDim.x) * kTileM, M, rh);
+      load_tile_regs<NATOMS, kTileM>(dz, (tile + gridDim.x) * kTileM, M, rd);
+    }
+  }
+  float* out = dw_partial + (int64_t)blockIdx.x * N * KH;
+  if (nitems > 0) {
+    mbar_wait(bar, (uint32_t)((nitems - 1) & 1));
+    tc_fence_after_sync();
+    // drain: thread (k = TMEM lane) holds dW^T[k][n0..]; partial layout is dW[n][k]
+    const int k = (warp & 3) * 32 + lane;
+    const int col0 = (warp >> 2) * (N / 2);
+    const uint32_t taddr = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + (uint32_t)col0;
+#pragma unroll
+    for (int j = 0; j < N / 2; j += 16) {
+      float t16[16];
+      tmem_ld16(taddr + j, t16);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) out[(int64_t)(col0 + j + e) * KH + k] = t16[e];
+    }
+  } else {
+    for (int e = threadIdx.x; e < N * KH; e += kTcThreads) out[e] = 0.f;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+template <int NATOMS, bool SPLIT>
+static int launch_bwd(const float* dy, const float* h, const float* s, const float* z, const float* W,
+                      const GateWs& ws, int64_t M, float* dh, float* dw_partial, float* db_partial,
+                      int grid, cudaStream_t st) {
+  auto k1 = gate_tc_dh_kernel<NATOMS, SPLIT>;
+  auto k2 = gate_tc_dw_kernel<NATOMS, SPLIT>;
+  if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, DhSmem<NATOMS>::kBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem<NATOMS>::kBytes) != cudaSuccess)
+    return VMTL_ECUDA;
+  k1<<<grid, kTcThreads, DhSmem<NATOMS>::kBytes, st>>>(dy, s, z, W, ws.coefA, ws.coefB, ws.mean, ws.invstd, ws.c1,
+                                                       ws.c2, M, ws.dz, dh, db_partial);
+  int rc = launch_status();
+  if (rc != VMTL_OK) return rc;
+  k2<<<grid, kTcThreads, DwSmem<NATOMS>::kBytes, st>>>(h, ws.dz, M, dw_partial);
+  return launch_status();
+}
+
+int gate_tc_bwd_gemm(const float* dy, const float* h, const float* s, const float* z, const float* W,
+                     const GateWs& ws, const float* gamma, int64_t M, int K, int N, int split3,
+                     float* dh, float* dw_partial, int slots, int* nslots, float* db_partial,
+                     cudaStream_t st) {
+  (void)gamma;
+  if (K != 128 || (N != 32 && N != 64) || !ws.dz) return VMTL_EUNSUPPORTED;
+  const int grid = tc_grid(M);
+  if (grid > slots || grid > ws.partial_rows) return VMTL_EWORKSPACE;
+  *nslots = grid;
+  if (N == 32)
+    return split3 ? launch_bwd<1, true>(dy, h, s, z, W, ws, M, dh, dw_partial, db_partial, grid, st)
+                  : launch_bwd<1, false>(dy, h, s, z, W, ws, M, dh, dw_partial, db_partial, grid, st);
+  return split3 ? launch_bwd<2, true>(dy, h, s, z, W, ws, M, dh, dw_partial, db_partial, grid, st)
+                : launch_bwd<2, false>(dy, h, s, z, W, ws, M, dh, dw_partial, db_partial, grid, st);
 }
 
 }  // namespace vmtl

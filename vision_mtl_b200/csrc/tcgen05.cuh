@@ -76,6 +76,25 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t lbo_
   return d;
 }
 
+// MN-major tf32 operands have ONE legal shared-memory layout: SWIZZLE_128B_BASE32B.  Rows (one per
+// K index) of 128 bytes = 32 consecutive M/N elements, 4-row groups of 512 bytes, the 32-byte
+// chunk index XORed with (row % 4).  LBO = byte stride between 32-element atoms along M/N,
+// SBO = byte stride between 4-row groups along K (512 when rows are dense).
+__device__ __forceinline__ uint64_t smem_desc_mn_tf32(uint32_t addr, uint32_t lbo_bytes,
+                                                      uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
+// byte offset of 16-byte chunk `c` (0..7) of K-row `row` inside a [rows x 128B] BASE32B tile
+__device__ __forceinline__ uint32_t sw128b32_off(int row, int c) {
+  return (uint32_t)(row * 128 + ((((c >> 1) ^ (row & 3)) << 5) | ((c & 1) << 4)));
+}
+
 // Instruction descriptor for kind::tf32, fp32 accumulate, M x N tile.
 // a_mn / b_mn: 0 = K-major operand, 1 = MN-major operand.
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
