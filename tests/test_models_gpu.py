@@ -263,3 +263,27 @@ def test_module_api_compat_paths():
     assert preds["segm"].shape == (2, 32, 32) and preds["depth"].shape == (2, 32, 32, 1)
     ep = module.on_predict_epoch_end()
     assert set(ep) == {"predict/loss", "predict/accuracy", "predict/jaccard_index", "predict/fbeta_score", "predict/mae"}
+
+
+@pytest.mark.parametrize("model_name", ["mtan", "csnet", "basic"])
+def test_run_pipe_drop_in_loop(model_name, tmp_path):
+    """The reference's training loop surface end to end: train + val epoch, checkpoint, predict."""
+    from vision_mtl_b200 import training_lit
+    from vision_mtl_b200.utils.pipeline_utils import CITYSCAPES, init_model, load_ckpt_model
+    from vision_mtl_b200.utils.utils import parse_args
+
+    args = parse_args(["--model_name", model_name, "--batch_size", "2", "--num_epochs", "1", "--lr", "5e-4",
+                       "--device", "cuda:0", "--save_epoch_freq", "1"])
+    args.backbone_weights = None
+    torch.manual_seed(11)
+    module = init_model(args, CITYSCAPES)
+    dm = training_lit.SyntheticDataModule(CITYSCAPES, 2, steps_per_epoch=2, val_steps=1)
+    logger = training_lit._DirLogger(str(tmp_path))
+    hist = training_lit.run_pipe(args, module, dm, 1, "cuda:0", exp=None, logger=logger)
+    assert set(hist["train"]) == {"train/loss", "train/accuracy", "train/jaccard_index", "train/fbeta_score", "train/mae"}
+    assert all(np.isfinite(v[0]) for v in hist["train"].values()) and all(np.isfinite(v[0]) for v in hist["val"].values())
+    ckpt = load_ckpt_model(str(tmp_path))["model"]
+    assert all(k.startswith("model.") for k in ckpt) and len(ckpt) == len(module.state_dict())
+    preds, pm = training_lit.predict(dm.predict_dataloader(), module, "cuda:0")
+    assert preds[0]["segm"].shape == (2, 128, 256) and preds[0]["depth"].shape == (2, 128, 256, 1)
+    assert np.isfinite(pm["predict/loss"])

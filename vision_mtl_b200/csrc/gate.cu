@@ -99,15 +99,15 @@ __global__ void gate_fwd_stats_finalize(const float* __restrict__ partial, int n
                                         float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                         float* __restrict__ coefA, float* __restrict__ coefB,
                                         float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  double s = 0.0, q = 0.0;
+  if (training) {  // block-uniform branch: the reduction synchronises
+    s = block_colsum(partial, nparts, 2 * (int64_t)N, c < N ? c : 0, c < N);
+    q = block_colsum(partial, nparts, 2 * (int64_t)N, N + (c < N ? c : 0), c < N);
+  }
+  if (threadIdx.x >= 32 || c >= N) return;
   double mean, var;
   if (training) {
-    double s = 0.0, q = 0.0;
-    for (int k = 0; k < nparts; ++k) {
-      s += (double)partial[(int64_t)k * 2 * N + c];
-      q += (double)partial[(int64_t)k * 2 * N + N + c];
-    }
     mean = s / (double)M;
     var = q / (double)M - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -192,13 +192,10 @@ __global__ void gate_bwd_stats_finalize(const float* __restrict__ partial, int n
                                         int training, float* __restrict__ dgamma,
                                         float* __restrict__ dbeta, float* __restrict__ c1,
                                         float* __restrict__ c2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
-  double sb = 0.0, sg = 0.0;
-  for (int k = 0; k < nparts; ++k) {
-    sb += (double)partial[(int64_t)k * 2 * N + c];
-    sg += (double)partial[(int64_t)k * 2 * N + N + c];
-  }
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const double sb = block_colsum(partial, nparts, 2 * (int64_t)N, c < N ? c : 0, c < N);
+  const double sg = block_colsum(partial, nparts, 2 * (int64_t)N, N + (c < N ? c : 0), c < N);
+  if (threadIdx.x >= 32 || c >= N) return;
   dbeta[c] = (float)sb;
   dgamma[c] = (float)sg;
   c1[c] = training ? (float)(sb / (double)M) : 0.f;
@@ -237,11 +234,9 @@ __global__ void __launch_bounds__(kEwThreads)
 // out[j] = fixed-order fp64 sum over nparts rows of length `len`
 __global__ void rows_sum_finalize(const float* __restrict__ partial, int nparts, int len,
                                   float* __restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= len) return;
-  double s = 0.0;
-  for (int k = 0; k < nparts; ++k) s += (double)partial[(int64_t)k * len + j];
-  out[j] = (float)s;
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const double s = block_colsum(partial, nparts, (int64_t)len, j < len ? j : 0, j < len);
+  if (threadIdx.x < 32 && j < len) out[j] = (float)s;
 }
 
 // ---- fp32 CUDA-core contraction (VMTL_GATE_FP32_FFMA) --------------------------------------
@@ -358,7 +353,7 @@ extern "C" int vmtl_gate_fwd(const float* h, const float* s, const float* W, con
   const int split3 = precision == VMTL_GATE_TC_3XTF32;
 
   if (!training) {
-    gate_fwd_stats_finalize<<<(N + 127) / 128, 128, 0, st>>>(nullptr, 0, M, N, eps, momentum, 0, gamma,
+    gate_fwd_stats_finalize<<<(N + 31) / 32, kFinThreads, 0, st>>>(nullptr, 0, M, N, eps, momentum, 0, gamma,
                                                              beta, running_mean, running_var, ws.mean,
                                                              ws.invstd, ws.coefA, ws.coefB, save_mean,
                                                              save_invstd);
@@ -389,7 +384,7 @@ extern "C" int vmtl_gate_fwd(const float* h, const float* s, const float* W, con
     gate_colstats_kernel<<<nparts, kEwThreads, 0, st>>>(save_z, M, C4, ws.partial);
     if ((rc = launch_status()) != VMTL_OK) return rc;
   }
-  gate_fwd_stats_finalize<<<(N + 127) / 128, 128, 0, st>>>(ws.partial, nparts, M, N, eps, momentum, 1,
+  gate_fwd_stats_finalize<<<(N + 31) / 32, kFinThreads, 0, st>>>(ws.partial, nparts, M, N, eps, momentum, 1,
                                                            gamma, beta, running_mean, running_var,
                                                            ws.mean, ws.invstd, ws.coefA, ws.coefB,
                                                            save_mean, save_invstd);
@@ -441,7 +436,7 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, co
   gate_bwd_stats_kernel<<<nparts, kEwThreads, 0, st>>>(dy, s, z, M, C4, ws.coefA, ws.coefB, ws.mean,
                                                        ws.invstd, ds, ws.partial);
   if ((rc = launch_status()) != VMTL_OK) return rc;
-  gate_bwd_stats_finalize<<<(N + 127) / 128, 128, 0, st>>>(ws.partial, nparts, M, N, training, dgamma,
+  gate_bwd_stats_finalize<<<(N + 31) / 32, kFinThreads, 0, st>>>(ws.partial, nparts, M, N, training, dgamma,
                                                            dbeta, ws.c1, ws.c2);
   if ((rc = launch_status()) != VMTL_OK) return rc;
 
@@ -452,9 +447,9 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, co
     rc = gate_tc_bwd_gemm(dy, h, s, z, W, ws, gamma, M, K, N, split3, dh, ws.gemm_partial, ws.gemm_slots,
                           &nslots, ws.partial, st);
     if (rc == VMTL_OK) {
-      rows_sum_finalize<<<(N * K + 127) / 128, 128, 0, st>>>(ws.gemm_partial, nslots, N * K, dW);
+      rows_sum_finalize<<<(N * K + 31) / 32, kFinThreads, 0, st>>>(ws.gemm_partial, nslots, N * K, dW);
       if ((rc = launch_status()) != VMTL_OK) return rc;
-      rows_sum_finalize<<<(N + 127) / 128, 128, 0, st>>>(ws.partial, nslots, N, dbias);
+      rows_sum_finalize<<<(N + 31) / 32, kFinThreads, 0, st>>>(ws.partial, nslots, N, dbias);
       return launch_status();
     }
     if (rc != VMTL_EUNSUPPORTED) return rc;
@@ -463,7 +458,7 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, co
   gate_bwd_dz_kernel<<<nparts, kEwThreads, 0, st>>>(dy, s, z, M, C4, ws.coefA, ws.coefB, ws.mean,
                                                     ws.invstd, ws.c1, ws.c2, ws.dz, ws.partial);
   if ((rc = launch_status()) != VMTL_OK) return rc;
-  rows_sum_finalize<<<(N + 127) / 128, 128, 0, st>>>(ws.partial, nparts, N, dbias);
+  rows_sum_finalize<<<(N + 31) / 32, kFinThreads, 0, st>>>(ws.partial, nparts, N, dbias);
   if ((rc = launch_status()) != VMTL_OK) return rc;
   if (dh) {
     // dh[M,K] = dz[M,N] @ W[N,K]
@@ -480,6 +475,6 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, co
   if (splits > per) splits = per;
   rc = sgemm64(ws.dz, h, ws.gemm_partial, nullptr, N, K, M, 1, N, K, 1, K, splits, (int64_t)N * K, st);
   if (rc != VMTL_OK) return rc;
-  rows_sum_finalize<<<(N * K + 127) / 128, 128, 0, st>>>(ws.gemm_partial, splits, N * K, dW);
+  rows_sum_finalize<<<(N * K + 31) / 32, kFinThreads, 0, st>>>(ws.gemm_partial, splits, N * K, dW);
   return launch_status();
 }

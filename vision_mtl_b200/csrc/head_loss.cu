@@ -90,12 +90,13 @@ __device__ __forceinline__ void block_partial2(double a, double b, double* parti
 
 __global__ void ce_finalize(const double* __restrict__ partial, int nblocks, double* __restrict__ out,
                             float* __restrict__ loss) {
+  __shared__ double s_v[2];
+  const int col = threadIdx.x & 31;
+  const double v = block_colsum(partial, nblocks, 2, col < 2 ? col : 0, col < 2);
+  if (threadIdx.x < 2) s_v[threadIdx.x] = v;
+  __syncthreads();
   if (threadIdx.x == 0) {
-    double s = 0.0, n = 0.0;
-    for (int b = 0; b < nblocks; ++b) {
-      s += partial[2 * b];
-      n += partial[2 * b + 1];
-    }
+    const double s = s_v[0], n = s_v[1];
     out[0] = s;
     out[1] = n;
     if (loss) loss[0] = (float)(s / n);
@@ -335,11 +336,11 @@ __global__ void __launch_bounds__(kLossThreads)
 // dW[c][k] / db[c] = fixed-order fp64 sum of the block partials ([grid][CPAD][33])
 __global__ void head_ce_bwd_finalize(const float* __restrict__ partial, int nblocks, int CPAD, int C,
                                      float* __restrict__ dW, float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ROW = CPAD * (kHeadCin + 1);
-  if (i >= C * (kHeadCin + 1)) return;
-  double s = 0.0;
-  for (int bk = 0; bk < nblocks; ++bk) s += (double)partial[(int64_t)bk * ROW + i];
+  const bool ok = i < C * (kHeadCin + 1);
+  const double s = block_colsum(partial, nblocks, (int64_t)ROW, ok ? i : 0, ok);
+  if (threadIdx.x >= 32 || !ok) return;
   const int c = i / (kHeadCin + 1), k = i % (kHeadCin + 1);
   if (k < kHeadCin)
     dW[c * kHeadCin + k] = (float)s;
@@ -588,11 +589,9 @@ __global__ void __launch_bounds__(kLossThreads)
 __global__ void silog_finalize(const double* __restrict__ partial, int nblocks, int64_t P,
                                double* __restrict__ out, float* __restrict__ scalars) {
   __shared__ double s[5];
-  if (threadIdx.x < 5) {
-    double acc = 0.0;
-    for (int b = 0; b < nblocks; ++b) acc += partial[(int64_t)b * 5 + threadIdx.x];
-    s[threadIdx.x] = acc;
-  }
+  const int col = threadIdx.x & 31;
+  const double acc = block_colsum(partial, nblocks, 5, col < 5 ? col : 0, col < 5);
+  if (threadIdx.x < 5) s[threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     const double n = s[0], sg = s[1], sgg = s[2];
@@ -705,10 +704,9 @@ __global__ void __launch_bounds__(kLossThreads)
 
 __global__ void silog_bwd_finalize(const float* __restrict__ partial, int nblocks, int cin,
                                    float* __restrict__ dw, float* __restrict__ db) {
-  const int i = threadIdx.x;
-  if (i > cin) return;
-  double s = 0.0;
-  for (int bk = 0; bk < nblocks; ++bk) s += (double)partial[(int64_t)bk * (cin + 1) + i];
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+  const double s = block_colsum(partial, nblocks, (int64_t)(cin + 1), i <= cin ? i : 0, i <= cin);
+  if (threadIdx.x >= 32 || i > cin) return;
   if (i < cin)
     dw[i] = (float)s;
   else
@@ -750,7 +748,7 @@ extern "C" int vmtl_head_ce_fwd(const float* feat, const float* W, const float* 
   }
   int rc = launch_status();
   if (rc != VMTL_OK) return rc;
-  ce_finalize<<<1, 32, 0, st>>>(partial, grid, out, loss);
+  ce_finalize<<<1, kFinThreads, 0, st>>>(partial, grid, out, loss);
   return launch_status();
 }
 
@@ -790,7 +788,7 @@ extern "C" int vmtl_head_ce_bwd(const float* feat, const float* W, const float* 
   int rc = launch_status();
   if (rc != VMTL_OK) return rc;
   const int n = C * (kHeadCin + 1);
-  head_ce_bwd_finalize<<<(n + 127) / 128, 128, 0, st>>>(partial, grid, cpad, C, dW, db);
+  head_ce_bwd_finalize<<<(n + 31) / 32, kFinThreads, 0, st>>>(partial, grid, cpad, C, dW, db);
   return launch_status();
 }
 
@@ -820,7 +818,7 @@ extern "C" int vmtl_ce_logits_fwd(const float* logits, const int64_t* target, in
 #undef VMTL_CEF
   int rc = launch_status();
   if (rc != VMTL_OK) return rc;
-  ce_finalize<<<1, 32, 0, st>>>(partial, grid, out, loss);
+  ce_finalize<<<1, kFinThreads, 0, st>>>(partial, grid, out, loss);
   return launch_status();
 }
 
@@ -877,7 +875,7 @@ extern "C" int vmtl_head_silog_fwd(const float* feat, const float* w, const floa
   }
   int rc = launch_status();
   if (rc != VMTL_OK) return rc;
-  silog_finalize<<<1, 32, 0, st>>>(partial, grid, P, out, scalars);
+  silog_finalize<<<1, kFinThreads, 0, st>>>(partial, grid, P, out, scalars);
   return launch_status();
 }
 
@@ -907,6 +905,6 @@ extern "C" int vmtl_head_silog_bwd(const float* feat, const float* w, const floa
   }
   int rc = launch_status();
   if (rc != VMTL_OK) return rc;
-  silog_bwd_finalize<<<1, 128, 0, st>>>(partial, grid, Cin, dw, db);
+  silog_bwd_finalize<<<(Cin + 1 + 31) / 32, kFinThreads, 0, st>>>(partial, grid, Cin, dw, db);
   return launch_status();
 }

@@ -168,10 +168,9 @@ __global__ void __launch_bounds__(256)
 
 __global__ void depth_err_finalize(const double* __restrict__ partial, int nblocks, int64_t P,
                                    double* __restrict__ out) {
-  // one warp; lane k<3 sums column k in fixed order
+  const int col = threadIdx.x & 31;
+  const double s = block_colsum(partial, nblocks, 3, col < 3 ? col : 0, col < 3);
   if (threadIdx.x < 3) {
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * 3 + threadIdx.x];
     if (threadIdx.x == 0) {
       out[0] = (double)P;
       out[1] = s;
@@ -256,7 +255,7 @@ extern "C" int vmtl_depth_err_sums(const float* pred, const float* target, int64
   depth_err_kernel<<<grid, 256, 0, st>>>(pred, target, P, min_depth, partial);
   int rc = launch_status();
   if (rc != VMTL_OK) return rc;
-  depth_err_finalize<<<1, 32, 0, st>>>(partial, grid, P, out);
+  depth_err_finalize<<<1, kFinThreads, 0, st>>>(partial, grid, P, out);
   return launch_status();
 }
 

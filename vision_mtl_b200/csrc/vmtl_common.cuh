@@ -67,6 +67,40 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ---- second stage of every two-stage reduction ---------------------------------------------
+// Block of kFinThreads = 32 columns x 32 row groups.  Thread (lx, ly) sums rows ly, ly+32, ... of
+// column `col` of partial[nparts][rowlen] in fp64; the 32 sub-sums are then combined in a FIXED
+// order, so the result is deterministic and independent of the launch geometry of stage one.
+// The result is valid in the threads with ly == 0 (threadIdx.x < 32).
+constexpr int kFinThreads = 1024;
+template <typename T>
+__device__ __forceinline__ double block_colsum(const T* __restrict__ partial, int nparts, int64_t rowlen,
+                                               int64_t col, bool valid) {
+  __shared__ double s_sub[32][33];
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  double s = 0.0;
+  if (valid) {
+    int k = ly;
+    for (; k + 96 < nparts; k += 128) {  // 4 independent loads in flight
+      const double a = (double)partial[(int64_t)k * rowlen + col];
+      const double b = (double)partial[(int64_t)(k + 32) * rowlen + col];
+      const double c = (double)partial[(int64_t)(k + 64) * rowlen + col];
+      const double d = (double)partial[(int64_t)(k + 96) * rowlen + col];
+      s += (a + b) + (c + d);
+    }
+    for (; k < nparts; k += 32) s += (double)partial[(int64_t)k * rowlen + col];
+  }
+  s_sub[ly][lx] = s;
+  __syncthreads();
+  double t = 0.0;
+  if (ly == 0) {
+#pragma unroll
+    for (int q = 0; q < 32; ++q) t += s_sub[q][lx];
+  }
+  __syncthreads();
+  return t;
+}
+
 __device__ __forceinline__ float sigmoidf_acc(float u) {
   // 1/(1+exp(-u)) with the accurate expf: the parity bar is 1e-4 relative on gradients.
   return 1.0f / (1.0f + expf(-u));

@@ -215,26 +215,21 @@ template <bool DIAG>
 __global__ void xstitch_dalpha_finalize(const float* __restrict__ partial, float* __restrict__ dalpha,
                                         int nblocks, int T, int Cdim /* C or 1 */) {
   const int n = T * T * Cdim;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const int c = j % Cdim;
-  const int ab = j / Cdim;
-  const int o = ab / T, b = ab % T;
+  const int lx = threadIdx.x & 31;
+  const int j = blockIdx.x * 32 + lx;
   const int nacc = DIAG ? T : T * T;
-  int src;
-  if (DIAG) {
-    if (o != b) {
-      dalpha[j] = 0.f;  // exact zeros, as autograd gives for the reference einsum
-      return;
-    }
-    src = o * Cdim + c;
-  } else {
-    src = ab * Cdim + c;
+  int src = -1;
+  if (j < n) {
+    const int c = j % Cdim;
+    const int ab = j / Cdim;
+    const int o = ab / T, b = ab % T;
+    if (DIAG)
+      src = (o == b) ? o * Cdim + c : -1;  // off-diagonal: exact zeros, as autograd gives for the reference einsum
+    else
+      src = ab * Cdim + c;
   }
-  double s = 0.0;
-  const int64_t rowlen = (int64_t)nacc * Cdim;
-  for (int k = 0; k < nblocks; ++k) s += (double)partial[k * rowlen + src];
-  dalpha[j] = (float)s;
+  const double t = block_colsum(partial, nblocks, (int64_t)nacc * Cdim, src < 0 ? 0 : src, src >= 0);
+  if (threadIdx.x < 32 && j < n) dalpha[j] = (float)t;
 }
 
 struct XsBwdPlan {
@@ -329,9 +324,9 @@ static int xs_bwd_launch(const XsBwdArgs& a, const float* alpha, float* dalpha, 
   const int cdim = cw ? C : 1;
   const int n = T * T * cdim;
   if (diag)
-    xstitch_dalpha_finalize<true><<<(n + 127) / 128, 128, 0, st>>>(partial, dalpha, p.gridx, T, cdim);
+    xstitch_dalpha_finalize<true><<<(n + 31) / 32, kFinThreads, 0, st>>>(partial, dalpha, p.gridx, T, cdim);
   else
-    xstitch_dalpha_finalize<false><<<(n + 127) / 128, 128, 0, st>>>(partial, dalpha, p.gridx, T, cdim);
+    xstitch_dalpha_finalize<false><<<(n + 31) / 32, kFinThreads, 0, st>>>(partial, dalpha, p.gridx, T, cdim);
   return launch_status();
 }
 
