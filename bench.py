@@ -300,12 +300,17 @@ def main():
     if top is not None:
         name, d = top
         achieved = d["gbps"]
-        traffic = None
+        traffic, traffic_note = None, None
         tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(args.workload, {}).get(name)
+        if os.path.exists(tpath):  # dram__bytes_read+write of ONE captured launch (ncu --set full)
+            rec = json.load(open(tpath)).get(args.workload, {}).get(name)
+            if rec:
+                traffic = rec["bytes"]
+                traffic_note = (f"captured launch: {rec['site']}; algorithmic bytes of that launch "
+                                f"{rec['algorithmic_bytes_same_launch']}")
         roofline = {"bound": "hbm", "kernel": "vmtl_" + name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
+                    "peak_source": peak_src,
                     "launches_timed": d["calls"], "avg_launch_ms": d["ms"] / d["calls"],
                     "algorithmic_bytes_per_launch": d["bytes"] / d["calls"]}
     line = {

@@ -302,6 +302,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   }
 }
 
+}  // namespace vmtl
+#include "gate_tc_ws.cuh"   // warp-specialised forward (uses the tile helpers above)
+#include "gate_tc_tma.cuh"  // TMA + TMEM-resident A operand forward
+namespace vmtl {
+
 template <int KATOMS, int NC, int NCH, bool SPLIT, bool EVAL>
 static int launch_fwd(const float* h, const float* W, const float* bias, const float* s,
                       const float* coefA, const float* coefB, int64_t M, float* out, float* partial,
@@ -359,6 +364,27 @@ int gate_tc_fwd_gemm(const float* h, const float* W, const float* bias, int64_t 
   const int grid = tc_grid(M);
   if (grid > partial_rows) return VMTL_EWORKSPACE;
   *nparts = grid;
+  // VMTL_GATE_FWD = tma (default) | ws | base : kernel generation, for A/B comparisons
+  static const int variant = [] {
+    const char* e = getenv("VMTL_GATE_FWD");
+    if (e && e[0] == 'b') return 0;
+    if (e && e[0] == 'w') return 1;
+    return 2;
+  }();
+  if (variant == 2 && K == 128 && (N == 32 || N == 64)) {
+    if (N == 32)
+      return split3 ? launch_fwd_tma<32, true>(h, W, bias, M, z_out, partial, grid, st)
+                    : launch_fwd_tma<32, false>(h, W, bias, M, z_out, partial, grid, st);
+    return split3 ? launch_fwd_tma<64, true>(h, W, bias, M, z_out, partial, grid, st)
+                  : launch_fwd_tma<64, false>(h, W, bias, M, z_out, partial, grid, st);
+  }
+  if (variant >= 1 && K == 128 && (N == 32 || N == 64)) {
+    if (N == 32)
+      return split3 ? launch_fwd_ws<32, true>(h, W, bias, M, z_out, partial, grid, st)
+                    : launch_fwd_ws<32, false>(h, W, bias, M, z_out, partial, grid, st);
+    return split3 ? launch_fwd_ws<64, true>(h, W, bias, M, z_out, partial, grid, st)
+                  : launch_fwd_ws<64, false>(h, W, bias, M, z_out, partial, grid, st);
+  }
   return dispatch_fwd<false>(h, W, bias, nullptr, nullptr, nullptr, M, K, N, split3, z_out, partial, grid, st);
 }
 
