@@ -41,7 +41,7 @@ inline size_t gate_ws_floats(int64_t M, int K, int N, int precision, int backwar
   w.gemm_slots = backward ? sm_count() * 2 : 0;
   w.gemm_partial = take((size_t)w.gemm_slots * N * K);
   (void)precision;
-  w.dz = backward ? take((size_t)M * N) : nullptr;
+  w.dz = backward ? take((size_t)M * N * 2) : nullptr;  // dz, or its tf32 hi and lo parts (TMA kernels)
   if (ws) *ws = w;
   return off;
 }

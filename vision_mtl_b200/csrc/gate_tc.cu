@@ -305,6 +305,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 }  // namespace vmtl
 #include "gate_tc_ws.cuh"   // warp-specialised forward (uses the tile helpers above)
 #include "gate_tc_tma.cuh"  // TMA + TMEM-resident A operand forward
+#include "gate_tc_bwd_tma.cuh"  // same machinery for dh / dW
 namespace vmtl {
 
 template <int KATOMS, int NC, int NCH, bool SPLIT, bool EVAL>
@@ -361,9 +362,7 @@ static int tc_grid(int64_t M) {
 int gate_tc_fwd_gemm(const float* h, const float* W, const float* bias, int64_t M, int K, int N,
                      int split3, float* z_out, float* partial, int partial_rows, int* nparts,
                      cudaStream_t st) {
-  const int grid = tc_grid(M);
-  if (grid > partial_rows) return VMTL_EWORKSPACE;
-  *nparts = grid;
+  int grid = tc_grid(M);
   // VMTL_GATE_FWD = tma (default) | ws | base : kernel generation, for A/B comparisons
   static const int variant = [] {
     const char* e = getenv("VMTL_GATE_FWD");
@@ -371,13 +370,29 @@ int gate_tc_fwd_gemm(const float* h, const float* W, const float* bias, int64_t 
     if (e && e[0] == 'w') return 1;
     return 2;
   }();
-  if (variant == 2 && K == 128 && (N == 32 || N == 64)) {
-    if (N == 32)
-      return split3 ? launch_fwd_tma<32, true>(h, W, bias, M, z_out, partial, grid, st)
-                    : launch_fwd_tma<32, false>(h, W, bias, M, z_out, partial, grid, st);
-    return split3 ? launch_fwd_tma<64, true>(h, W, bias, M, z_out, partial, grid, st)
-                  : launch_fwd_tma<64, false>(h, W, bias, M, z_out, partial, grid, st);
+  if (variant == 2 && K == 128 && (N == 32 || N == 64 || N == 128 || N == 192 || N == 256)) {
+    // N > 64: (row tile, 64-column chunk) items; a CTA keeps one chunk so its W operand is staged once
+    const int nch = N <= 64 ? 1 : N / 64;
+    const int64_t items = ((M + kTileM - 1) / kTileM) * nch;
+    grid = (int)(items < sm_count() ? items : sm_count());
+    grid = grid / nch * nch;
+    if (grid < nch) grid = nch;
+    if (grid > partial_rows) return VMTL_EWORKSPACE;
+    *nparts = grid;
+#define VMTL_TMA(NC_, NCH_)                                                                         \
+  (split3 ? launch_fwd_tma<NC_, NCH_, true>(h, W, bias, M, z_out, partial, grid, st)                \
+          : launch_fwd_tma<NC_, NCH_, false>(h, W, bias, M, z_out, partial, grid, st))
+    switch (N) {
+      case 32: return VMTL_TMA(32, 1);
+      case 64: return VMTL_TMA(64, 1);
+      case 128: return VMTL_TMA(64, 2);
+      case 192: return VMTL_TMA(64, 3);
+      default: return VMTL_TMA(64, 4);
+    }
+#undef VMTL_TMA
   }
+  if (grid > partial_rows) return VMTL_EWORKSPACE;
+  *nparts = grid;
   if (variant >= 1 && K == 128 && (N == 32 || N == 64)) {
     if (N == 32)
       return split3 ? launch_fwd_ws<32, true>(h, W, bias, M, z_out, partial, grid, st)
@@ -729,6 +744,17 @@ int gate_tc_bwd_gemm(const float* dy, const float* h, const float* s, const floa
   const int grid = tc_grid(M);
   if (grid > slots || grid > ws.partial_rows) return VMTL_EWORKSPACE;
   *nslots = grid;
+  static const bool use_tma = [] {  // VMTL_GATE_BWD=base selects the register-staged kernels
+    const char* e = getenv("VMTL_GATE_BWD");
+    return !(e && e[0] == 'b');
+  }();
+  if (use_tma) {
+    if (N == 32)
+      return split3 ? launch_bwd_tma<1, true>(dy, h, s, z, W, ws, M, dh, dw_partial, db_partial, grid, st)
+                    : launch_bwd_tma<1, false>(dy, h, s, z, W, ws, M, dh, dw_partial, db_partial, grid, st);
+    return split3 ? launch_bwd_tma<2, true>(dy, h, s, z, W, ws, M, dh, dw_partial, db_partial, grid, st)
+                  : launch_bwd_tma<2, false>(dy, h, s, z, W, ws, M, dh, dw_partial, db_partial, grid, st);
+  }
   if (N == 32)
     return split3 ? launch_bwd<1, true>(dy, h, s, z, W, ws, M, dh, dw_partial, db_partial, grid, st)
                   : launch_bwd<1, false>(dy, h, s, z, W, ws, M, dh, dw_partial, db_partial, grid, st);

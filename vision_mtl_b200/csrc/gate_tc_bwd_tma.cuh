@@ -1,0 +1,537 @@
+// MTAN gate backward, phase B on tensor cores, TMA generation (K = 128, N in {32, 64}).
+// Included by gate_tc.cu.  Same machinery as gate_tc_tma.cuh: raw fp32 tiles arrive in shared memory
+// by TMA (>= 128 KB per SM in flight), the tf32 hi/lo A operand lives in TENSOR MEMORY.
+//
+//   B1 gate_tc_dh_tma_kernel : unit = (128-row tile, 32-column atom a).  TMA brings dy_a, s_a, z_a
+//      ([128 x 32] each, 48 KB per unit, 3 stages).  Converter threads (one row each) rebuild
+//      dz = gamma*invstd*(du - c1 - zhat*c2), store its tf32 hi and lo parts once to global (they
+//      are B2's operands), put hi/lo into TMEM and accumulate db.  MMA: dh[128 x 128] +=
+//      dz_a[128 x 32] @ W[a*32.., :]  (A from TMEM, B = W^T atoms K-major in smem, 3xTF32).
+//   B2 gate_tc_dw_tma_kernel : unit = (tile, 64-row half).  TMA brings the h half ([64 x 128], raw)
+//      and the dz_hi / dz_lo halves straight into the MN-major tf32 operand layout
+//      (SWIZZLE_128B_ATOM_32B), so B needs no conversion.  Converter threads (one hidden channel k
+//      each) transpose h^T into TMEM (lane = k, column = pixel row) as hi/lo.  MMA per 8 pixel rows:
+//          D[:, 0:2N] += h_hi^T @ [dz_hi | dz_lo] ,  D[:, 0:N] += h_lo^T @ dz_hi
+//      accumulating dW^T over ALL tiles of the CTA in TMEM; drained once.
+#pragma once
+
+namespace vmtl {
+
+// ------------------------------------------------------------------------------------------- B1
+template <int NA>
+struct DhTmaSmem {
+  static constexpr int kSlot = kTileM * 128;                 // [128 rows x 32 floats]
+  static constexpr int kStage = 3 * kSlot;                   // dy_a, s_a, z_a
+  static constexpr int kStages = 2;
+  static constexpr int kBhi = kStages * kStage;              // W^T hi: NA atoms of [128 rows(k) x 128 B]
+  static constexpr int kBlo = kBhi + NA * kSlot;
+  static constexpr int kOut = kBlo + NA * kSlot;             // dh tile staging for the TMA store: 4 atoms
+  static constexpr int kMisc = kOut + 4 * kSlot;
+  static constexpr int kBytes = kMisc + 256 + 6 * 64 * 4 + 1024;
+};
+
+template <int NA, bool SPLIT>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+    gate_tc_dh_tma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_s,
+                          const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_dh,
+                          const float* __restrict__ W /* [N,128] */,
+                          const float* __restrict__ coefA, const float* __restrict__ coefB,
+                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                          const float* __restrict__ c1, const float* __restrict__ c2, int64_t M,
+                          const __grid_constant__ CUtensorMap tmap_dzh_st, const __grid_constant__ CUtensorMap tmap_dzl_st,
+                          float* __restrict__ dh, float* __restrict__ db_partial /* [grid][N] */) {
+  using namespace tc;
+  using L = DhTmaSmem<NA>;
+  constexpr int S = L::kStages;
+  constexpr int N = NA * 32;
+  constexpr int KH = 128;
+  constexpr uint32_t kACols = 256;  // two A buffers of 128 columns: atom a -> hi [a*64, +32), lo [a*64+32, +32)
+  constexpr uint32_t kTmemCols = 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sBhi = smem + L::kBhi;
+  uint8_t* sBlo = smem + L::kBlo;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::kMisc);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::kMisc + 192);
+  float* s_coef = reinterpret_cast<float*>(smem + L::kMisc + 256);  // [6][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto bar_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto bar_empty = [&](int s) { return bar0 + 32u + 8u * (uint32_t)s; };
+  // one aready barrier per (A buffer, atom): a consumer must observe every phase of a barrier
+  // before its producers can complete the next one
+  auto bar_aready = [&](int b, int a) { return bar0 + 64u + 8u * (uint32_t)(b * 2 + a); };
+  auto bar_amma = [&](int b) { return bar0 + 96u + 8u * (uint32_t)b; };
+  auto bar_dfull = [&](int b) { return bar0 + 112u + 8u * (uint32_t)b; };
+  auto bar_dfree = [&](int b) { return bar0 + 128u + 8u * (uint32_t)b; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 256);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_aready(i, 0), 256);
+      mbar_init(bar_aready(i, 1), 256);
+      mbar_init(bar_amma(i), 1);
+      mbar_init(bar_dfull(i), 1);
+      mbar_init(bar_dfree(i), 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 17) tmem_alloc(smem_u32(s_tmem), kTmemCols);
+  if (warp == 16 && lane == 0) {
+    tma_prefetch_desc(&tmap_dy);
+    tma_prefetch_desc(&tmap_s);
+    tma_prefetch_desc(&tmap_z);
+  }
+  for (int i = threadIdx.x; i < N; i += kTmaThreads) {
+    s_coef[0 * 64 + i] = coefA[i];
+    s_coef[1 * 64 + i] = coefB[i];
+    s_coef[2 * 64 + i] = mean[i];
+    s_coef[3 * 64 + i] = invstd[i];
+    s_coef[4 * 64 + i] = c1[i];
+    s_coef[5 * 64 + i] = c2[i];
+  }
+  if (warp < 8) {  // W^T operand: element (k, n) = W[n][k]; rows k, K-major along n, atom = n / 32
+    for (int e = threadIdx.x; e < N * KH; e += 256) {
+      const int n = e / KH, k = e - n * KH;
+      const float w = W[e];
+      const float hi = tf32_hi(w);
+      const uint32_t off = (uint32_t)((n >> 5) * L::kSlot) + sw128_off(k, (n & 31) >> 2) + (uint32_t)((n & 3) << 2);
+      *reinterpret_cast<float*>(sBhi + off) = hi;
+      if (SPLIT) *reinterpret_cast<float*>(sBlo + off) = w - hi;
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_d0 = tmem_base + kACols;
+
+  const int64_t ntiles = (M + kTileM - 1) / kTileM;
+  const int64_t nitems = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  float db_acc[NA];
+#pragma unroll
+  for (int a = 0; a < NA; ++a) db_acc[a] = 0.f;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ converters (thread = row)
+    const int quad = warp & 3, ch = warp >> 2;  // lane quadrant, 16-column half of the atom
+    const int row = quad * 32 + lane;
+    uint32_t ph_amma[2] = {0, 0};
+    int64_t u = 0;
+    for (int64_t it = 0; it < nitems; ++it) {
+      const int tb = (int)(it & 1);
+      const int64_t grow = (blockIdx.x + it * gridDim.x) * kTileM + row;
+      const bool row_ok = grow < M;
+#pragma unroll
+      for (int a = 0; a < NA; ++a, ++u) {
+        const int s = (int)(u % S);
+        mbar_wait(bar_full(s), (uint32_t)((u / S) & 1));
+        const uint8_t* st = smem + s * L::kStage;
+        float4 vdy[4], vs[4], vz[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t o = sw128_off(row, ch * 4 + j);
+          vdy[j] = *reinterpret_cast<const float4*>(st + o);
+          vs[j] = *reinterpret_cast<const float4*>(st + L::kSlot + o);
+          vz[j] = *reinterpret_cast<const float4*>(st + 2 * L::kSlot + o);
+        }
+        float d[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c4 = (a * 32 + ch * 16 + j * 4) >> 2;
+          const float4 A = reinterpret_cast<const float4*>(s_coef)[0 * 16 + c4];
+          const float4 B = reinterpret_cast<const float4*>(s_coef)[1 * 16 + c4];
+          const float4 mu = reinterpret_cast<const float4*>(s_coef)[2 * 16 + c4];
+          const float4 rs = reinterpret_cast<const float4*>(s_coef)[3 * 16 + c4];
+          const float4 k1 = reinterpret_cast<const float4*>(s_coef)[4 * 16 + c4];
+          const float4 k2 = reinterpret_cast<const float4*>(s_coef)[5 * 16 + c4];
+          auto dz1 = [](float g, float sv, float zv, float A_, float B_, float mu_, float r_, float k1_, float k2_) {
+            const float act = sigmoidf_acc(fmaf(A_, zv, B_));
+            return A_ * (g * sv * act * (1.f - act) - k1_ - (zv - mu_) * r_ * k2_);
+          };
+          d[4 * j] = dz1(vdy[j].x, vs[j].x, vz[j].x, A.x, B.x, mu.x, rs.x, k1.x, k2.x);
+          d[4 * j + 1] = dz1(vdy[j].y, vs[j].y, vz[j].y, A.y, B.y, mu.y, rs.y, k1.y, k2.y);
+          d[4 * j + 2] = dz1(vdy[j].z, vs[j].z, vz[j].z, A.z, B.z, mu.z, rs.z, k1.z, k2.z);
+          d[4 * j + 3] = dz1(vdy[j].w, vs[j].w, vz[j].w, A.w, B.w, mu.w, rs.w, k1.w, k2.w);
+        }
+        float hi[16], lo[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          if (!row_ok) d[e] = 0.f;
+          hi[e] = tf32_hi(d[e]);
+          lo[e] = d[e] - hi[e];
+        }
+        // dz_hi / dz_lo leave through the stage buffer itself: once every converter holds its inputs in
+        // registers, slots 0/1 of the stage are rewritten (swizzled) and the TMA warp bulk-stores them
+        // before it refills the stage -- no row-per-thread global stores.
+        named_barrier_sync(3, 256);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t o = sw128_off(row, ch * 4 + j);
+          *reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + o) = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          *reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + L::kSlot + o) = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_empty(s));  // = "dz staged": the TMA warp stores it, then reuses the stage
+        if (a == 0 && it >= 2) {  // the MMAs of tile it-2 have consumed this A buffer
+          mbar_wait(bar_amma(tb), ph_amma[tb]);
+          ph_amma[tb] ^= 1u;
+          tc_fence_after_sync();
+        }
+        const uint32_t ta = tmem_base + (((uint32_t)quad * 32) << 16) + (uint32_t)(tb * 128 + a * 64 + ch * 16);
+        tmem_st16(ta, hi);
+        if (SPLIT) tmem_st16(ta + 32, lo);
+        tmem_wait_st();
+        tc_fence_before_sync();
+        mbar_arrive(bar_aready(tb, a));
+        db_acc[a] += butterfly_colsum<16>(d, lane);  // lanes l and l+16 both hold column (l % 16)
+      }
+    }
+  } else if (warp < 16) {
+    // ------------------------------------------------------------------ epilogue: dh rows
+    const int ew = warp - 8;
+    for (int64_t it = 0; it < nitems; ++it) {
+      const int b = (int)(it & 1);
+      mbar_wait(bar_dfull(b), (uint32_t)((it >> 1) & 1));
+      tc_fence_after_sync();
+      const int64_t grow = (blockIdx.x + it * gridDim.x) * kTileM + (ew & 3) * 32 + lane;
+      const int col0 = (ew >> 2) * 64;
+      const uint32_t taddr = tmem_d0 + (((uint32_t)(ew & 3) * 32) << 16) + (uint32_t)(b * KH + col0);
+      // A row per thread is the wrong shape for global stores (32 x 16 B pieces per request).  The
+      // tile goes through a 128B-swizzled staging buffer and leaves as four TMA bulk stores.
+      if (threadIdx.x == 8 * 32) tma_store_wait_read();  // previous tile's stores have read the staging
+      named_barrier_sync(2, 256);
+      const int trow = (ew & 3) * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < 64; j += 16) {
+        float t16[16];
+        tmem_ld16(taddr + j, t16);
+        uint8_t* atom = smem + L::kOut + ((col0 + j) >> 5) * L::kSlot;
+        const int c0 = ((col0 + j) & 31) >> 2;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          *reinterpret_cast<float4*>(atom + sw128_off(trow, c0 + e)) =
+              make_float4(t16[4 * e], t16[4 * e + 1], t16[4 * e + 2], t16[4 * e + 3]);
+      }
+      tc_fence_before_sync();
+      mbar_arrive(bar_dfree(b));
+      fence_proxy_async_smem();
+      named_barrier_sync(2, 256);
+      if (threadIdx.x == 8 * 32 && dh) {
+        const int row0 = (int)((blockIdx.x + it * gridDim.x) * kTileM);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) tma_store_2d(&tmap_dh, a * 32, row0, smem_u32(smem + L::kOut + a * L::kSlot));
+        tma_store_commit();
+      }
+      (void)grow;
+    }
+    if (threadIdx.x == 8 * 32) tma_store_wait_all();
+  } else if (warp == 16) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int64_t u = 0;
+      for (int64_t it = 0; it < nitems; ++it) {
+        const int row0 = (int)((blockIdx.x + it * gridDim.x) * kTileM);
+        for (int a = 0; a < NA; ++a, ++u) {
+          const int s = (int)(u % S);
+          if (u >= S) {  // unit u-S: its dz is staged in this stage -> bulk-store it, then the stage is free
+            mbar_wait(bar_empty(s), (uint32_t)(((u / S) - 1) & 1));
+            const int64_t v = u - S;
+            const int vrow0 = (int)((blockIdx.x + (v / NA) * gridDim.x) * kTileM), va = (int)(v % NA);
+            tma_store_2d(&tmap_dzh_st, va * 32, vrow0, smem_u32(smem + s * L::kStage));
+            tma_store_2d(&tmap_dzl_st, va * 32, vrow0, smem_u32(smem + s * L::kStage + L::kSlot));
+            tma_store_commit();
+            tma_store_wait_read();
+          }
+          mbar_expect_tx(bar_full(s), (uint32_t)L::kStage);
+          const uint32_t dst = smem_u32(smem + s * L::kStage);
+          tma_load_2d(dst, &tmap_dy, a * 32, row0, bar_full(s));
+          tma_load_2d(dst + L::kSlot, &tmap_s, a * 32, row0, bar_full(s));
+          tma_load_2d(dst + 2 * L::kSlot, &tmap_z, a * 32, row0, bar_full(s));
+        }
+      }
+      const int64_t nunits = nitems * NA;  // drain: the last min(S, nunits) units are still staged
+      for (int64_t v = nunits > S ? nunits - S : 0; v < nunits; ++v) {
+        const int s = (int)(v % S);
+        mbar_wait(bar_empty(s), (uint32_t)((v / S) & 1));
+        const int vrow0 = (int)((blockIdx.x + (v / NA) * gridDim.x) * kTileM), va = (int)(v % NA);
+        tma_store_2d(&tmap_dzh_st, va * 32, vrow0, smem_u32(smem + s * L::kStage));
+        tma_store_2d(&tmap_dzl_st, va * 32, vrow0, smem_u32(smem + s * L::kStage + L::kSlot));
+        tma_store_commit();
+      }
+      tma_store_wait_all();
+    }
+  } else if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = idesc_tf32(kTileM, KH, 0, 0);
+    const uint32_t bH = smem_u32(sBhi), bL = smem_u32(sBlo);
+    for (int64_t it = 0; it < nitems; ++it) {
+      const int b = (int)(it & 1);
+      const uint32_t d_tmem = tmem_d0 + (uint32_t)(b * KH);
+      if (it >= 2) mbar_wait(bar_dfree(b), (uint32_t)(((it >> 1) - 1) & 1));
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        mbar_wait(bar_aready(b, a), (uint32_t)((it >> 1) & 1));
+        tc_fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t a_hi = tmem_base + (uint32_t)(b * 128 + a * 64 + ks * 8);
+          const uint64_t dBh = smem_desc_sw128(bH + a * L::kSlot + ks * 32, 16, 1024);
+          if (SPLIT) {
+            mma_tf32_ts(d_tmem, a_hi + 32, dBh, idesc, (a | ks) != 0);
+            mma_tf32_ts(d_tmem, a_hi, smem_desc_sw128(bL + a * L::kSlot + ks * 32, 16, 1024), idesc, 1);
+            mma_tf32_ts(d_tmem, a_hi, dBh, idesc, 1);
+          } else {
+            mma_tf32_ts(d_tmem, a_hi, dBh, idesc, (a | ks) != 0);
+          }
+        }
+      }
+      mma_commit(bar_amma(b));
+      mma_commit(bar_dfull(b));
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 17) tmem_dealloc(tmem_base, kTmemCols);
+  // db partial of this CTA: the four quadrant warps of each 16-column group, fixed order
+  float* s_red = reinterpret_cast<float*>(smem);  // [8 converter warps][NA][16]
+  if (warp < 8 && lane < 16) {
+#pragma unroll
+    for (int a = 0; a < NA; ++a) s_red[(warp * NA + a) * 16 + lane] = db_acc[a];
+  }
+  __syncthreads();
+  for (int col = threadIdx.x; col < N; col += kTmaThreads) {
+    const int a = col >> 5, ch = (col >> 4) & 1, l = col & 15;
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc += s_red[((ch * 4 + q) * NA + a) * 16 + l];
+    db_partial[(int64_t)blockIdx.x * N + col] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- B2
+template <int NA>
+struct DwTmaSmem {
+  static constexpr int kHalfRows = 64;
+  static constexpr int kSlotH = kHalfRows * 128;             // one K-atom of the h half [64 rows x 128 B]
+  static constexpr int kStageH = 4 * kSlotH;                 // 32 KB
+  static constexpr int kSlotD = kHalfRows * 128;             // one 32-column atom of a dz half, MN-major
+  static constexpr int kStageD = 2 * NA * kSlotD;            // atoms [hi_0.. hi_NA-1, lo_0.. lo_NA-1]
+  static constexpr int kStage = kStageH + kStageD;           // 48 KB (N=32) / 64 KB (N=64)
+  static constexpr int kStages = NA == 1 ? 4 : 3;
+  static constexpr int kMisc = kStages * kStage;
+  static constexpr int kBytes = kMisc + 256 + 1024;
+};
+
+template <int NA, bool SPLIT>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+    gate_tc_dw_tma_kernel(const __grid_constant__ CUtensorMap tmap_h /* box [32 x 64], SW128 */,
+                          const __grid_constant__ CUtensorMap tmap_dzh /* box [32 x 64], SW128_ATOM_32B */,
+                          const __grid_constant__ CUtensorMap tmap_dzl, int64_t M,
+                          float* __restrict__ dw_partial /* [grid][N][128] */) {
+  using namespace tc;
+  using L = DwTmaSmem<NA>;
+  constexpr int S = L::kStages;
+  constexpr int N = NA * 32;
+  constexpr int KH = 128;
+  constexpr int DC = SPLIT ? 2 * N : N;
+  constexpr uint32_t kACols = 256;  // A half buffer hb: hi [hb*128, +64), lo [hb*128+64, +64); column = pixel row
+  constexpr uint32_t kTmemCols = 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::kMisc);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::kMisc + 192);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto bar_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto bar_hfree = [&](int s) { return bar0 + 32u + 8u * (uint32_t)s; };   // converters done with the h part
+  auto bar_aready = [&](int b) { return bar0 + 64u + 8u * (uint32_t)b; };
+  auto bar_umma = [&](int s) { return bar0 + 80u + 8u * (uint32_t)s; };    // MMAs of the unit in stage s done
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_hfree(s), 256);
+      mbar_init(bar_umma(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) mbar_init(bar_aready(i), 256);
+    fence_mbar_init();
+  }
+  if (warp == 17) tmem_alloc(smem_u32(s_tmem), kTmemCols);
+  if (warp == 16 && lane == 0) {
+    tma_prefetch_desc(&tmap_h);
+    tma_prefetch_desc(&tmap_dzh);
+    tma_prefetch_desc(&tmap_dzl);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_d = tmem_base + kACols;
+
+  const int64_t nhalves = (M + L::kHalfRows - 1) / L::kHalfRows;  // units of 64 pixel rows
+  const int64_t nunits = blockIdx.x < nhalves ? (nhalves - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ converters (thread = channel k)
+    const int quad = warp & 3, rh = warp >> 2;  // lane quadrant (k / 32), 32-row half of the unit
+    const int k = quad * 32 + lane;
+    for (int64_t u = 0; u < nunits; ++u) {
+      const int s = (int)(u % S), hb = (int)(u & 1);
+      mbar_wait(bar_full(s), (uint32_t)((u / S) & 1));
+      const uint8_t* hs = smem + s * L::kStage + (k >> 5) * L::kSlotH;  // K-atom holding channel k
+      float hv[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const int row = rh * 32 + r;
+        hv[r] = *reinterpret_cast<const float*>(hs + sw128_off(row, (k & 31) >> 2) + ((k & 3) << 2));
+      }
+      mbar_arrive(bar_hfree(s));
+      if (u >= 2) {  // the MMAs of unit u-2 (same A half buffer) are done
+        const int64_t up = u - 2;
+        mbar_wait(bar_umma((int)(up % S)), (uint32_t)((up / S) & 1));
+        tc_fence_after_sync();
+      }
+      const uint32_t ta = tmem_base + (((uint32_t)quad * 32) << 16) + (uint32_t)(hb * 128 + rh * 32);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          hi[e] = tf32_hi(hv[g * 16 + e]);
+          lo[e] = hv[g * 16 + e] - hi[e];
+        }
+        tmem_st16(ta + g * 16, hi);
+        if (SPLIT) tmem_st16(ta + 64 + g * 16, lo);
+      }
+      tmem_wait_st();
+      tc_fence_before_sync();
+      mbar_arrive(bar_aready(hb));
+    }
+  } else if (warp == 16) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int64_t u = 0; u < nunits; ++u) {
+        const int s = (int)(u % S);
+        if (u >= S) {  // stage reusable: converters have read h (hfree) and the unit's MMAs have read dz (umma)
+          mbar_wait(bar_hfree(s), (uint32_t)(((u / S) - 1) & 1));
+          mbar_wait(bar_umma(s), (uint32_t)(((u / S) - 1) & 1));
+        }
+        const int row0 = (int)((blockIdx.x + u * gridDim.x) * L::kHalfRows);
+        mbar_expect_tx(bar_full(s), (uint32_t)(L::kStageH + (SPLIT ? L::kStageD : L::kStageD / 2)));
+        const uint32_t dst = smem_u32(smem + s * L::kStage);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) tma_load_2d(dst + a * L::kSlotH, &tmap_h, a * 32, row0, bar_full(s));
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          tma_load_2d(dst + L::kStageH + a * L::kSlotD, &tmap_dzh, a * 32, row0, bar_full(s));
+          if (SPLIT) tma_load_2d(dst + L::kStageH + (NA + a) * L::kSlotD, &tmap_dzl, a * 32, row0, bar_full(s));
+        }
+      }
+    }
+  } else if (warp == 17 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_wide = idesc_tf32(KH, DC, 0, 1);  // A from TMEM (K-major form), B MN-major
+    constexpr uint32_t idesc_n = idesc_tf32(KH, N, 0, 1);
+    for (int64_t u = 0; u < nunits; ++u) {
+      const int s = (int)(u % S), hb = (int)(u & 1);
+      mbar_wait(bar_aready(hb), (uint32_t)((u >> 1) & 1));
+      mbar_wait(bar_full(s), (uint32_t)((u / S) & 1));  // dz operands landed (usually long ago)
+      tc_fence_after_sync();
+      const uint32_t bD = smem_u32(smem + s * L::kStage + L::kStageH);
+#pragma unroll
+      for (int ks = 0; ks < L::kHalfRows / 8; ++ks) {  // 8 pixel rows per MMA = two 4-row groups
+        const uint32_t a_hi = tmem_base + (uint32_t)(hb * 128 + ks * 8);
+        const uint64_t dB = smem_desc_mn_tf32(bD + ks * 1024, L::kSlotD, 512);
+        mma_tf32_ts(tmem_d, a_hi, dB, idesc_wide, (u | ks) != 0);
+        if (SPLIT) mma_tf32_ts(tmem_d, a_hi + 64, dB, idesc_n, 1);
+      }
+      mma_commit(bar_umma(s));
+    }
+  }
+  // warps 8-15 have no per-unit work in this kernel: they only help drain the accumulator
+  tc_fence_before_sync();
+  __syncthreads();
+  float* out = dw_partial + (int64_t)blockIdx.x * N * KH;
+  if (nunits > 0) {
+    if (warp == 17 && lane == 0) {  // wait for the last unit's MMAs
+      const int64_t ul = nunits - 1;
+      mbar_wait(bar_umma((int)(ul % S)), (uint32_t)((ul / S) & 1));
+    }
+    __syncthreads();
+    tc_fence_after_sync();
+    if (warp < 8) {  // thread (k = lane quadrant row) drains dW^T[k][n]; partial layout is dW[n][k]
+      const int k = (warp & 3) * 32 + lane;
+      const int col0 = (warp >> 2) * (N / 2);
+      const uint32_t taddr = tmem_d + (((uint32_t)(warp & 3) * 32) << 16) + (uint32_t)col0;
+#pragma unroll
+      for (int j = 0; j < N / 2; j += 16) {
+        float t16[16], t2[16];
+        tmem_ld16(taddr + j, t16);
+        if (SPLIT) {
+          tmem_ld16(taddr + N + j, t2);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) t16[e] += t2[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) out[(int64_t)(col0 + j + e) * KH + k] = t16[e];
+      }
+    }
+  } else {
+    for (int e = threadIdx.x; e < N * KH; e += kTmaThreads) out[e] = 0.f;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 17) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+#ifndef CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+#define VMTL_NO_ATOM32B 1
+#endif
+
+// [rows, cols] fp32, box [box_rows x 32 floats]; mn32 selects the 128B swizzle with 32-byte atoms
+inline bool make_tmap_2d_sw(CUtensorMap* m, const float* base, int64_t rows, int cols, int box_rows, bool mn32) {
+  PFN_encodeTiled enc = tma_encode_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUtensorMapSwizzle sw = mn32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NA, bool SPLIT>
+static int launch_bwd_tma(const float* dy, const float* h, const float* s, const float* z, const float* W,
+                          const GateWs& ws, int64_t M, float* dh, float* dw_partial, float* db_partial, int grid,
+                          cudaStream_t st) {
+  constexpr int N = NA * 32;
+  float* dz_hi = ws.dz;
+  float* dz_lo = ws.dz + (size_t)M * N;
+  CUtensorMap t_dy, t_s, t_z, t_h, t_dzh, t_dzl, t_dh, t_dzh_st, t_dzl_st;
+  if (!make_tmap_2d_sw(&t_dy, dy, M, N, kTileM, false) || !make_tmap_2d_sw(&t_s, s, M, N, kTileM, false) ||
+      !make_tmap_2d_sw(&t_z, z, M, N, kTileM, false) || !make_tmap_2d_sw(&t_h, h, M, 128, 64, false) ||
+      !make_tmap_2d_sw(&t_dzh, dz_hi, M, N, 64, true) || !make_tmap_2d_sw(&t_dzl, dz_lo, M, N, 64, true) ||
+      !make_tmap_2d_sw(&t_dh, dh ? dh : h, M, 128, kTileM, false) ||
+      !make_tmap_2d_sw(&t_dzh_st, dz_hi, M, N, kTileM, false) || !make_tmap_2d_sw(&t_dzl_st, dz_lo, M, N, kTileM, false))
+    return VMTL_ECUDA;
+  auto k1 = gate_tc_dh_tma_kernel<NA, SPLIT>;
+  auto k2 = gate_tc_dw_tma_kernel<NA, SPLIT>;
+  if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, DhTmaSmem<NA>::kBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, DwTmaSmem<NA>::kBytes) != cudaSuccess)
+    return VMTL_ECUDA;
+  k1<<<grid, kTmaThreads, DhTmaSmem<NA>::kBytes, st>>>(t_dy, t_s, t_z, t_dh, W, ws.coefA, ws.coefB, ws.mean, ws.invstd,
+                                                        ws.c1, ws.c2, M, t_dzh_st, t_dzl_st, dh, db_partial);
+  int rc = launch_status();
+  if (rc != VMTL_OK) return rc;
+  k2<<<grid, kTmaThreads, DwTmaSmem<NA>::kBytes, st>>>(t_h, t_dzh, t_dzl, M, dw_partial);
+  return launch_status();
+}
+
+}  // namespace vmtl

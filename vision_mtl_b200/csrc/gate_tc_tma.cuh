@@ -65,7 +65,7 @@ inline bool make_tmap_2d(CUtensorMap* m, const float* base, int64_t rows, int co
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int NC, bool SPLIT>
+template <int NC, int NCH, bool SPLIT>
 __global__ void __launch_bounds__(kTmaThreads, 1)
     gate_tc_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_h, const float* __restrict__ W,
                            const float* __restrict__ bias, int64_t M, float* __restrict__ z_out,
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   using namespace tc;
   using L = TmaSmem<NC>;
   constexpr int S = L::kStages;
-  constexpr int N = NC;
+  constexpr int N = NC * NCH;  // N > 64: column chunks of NC are spread over CTAs (chunk = blockIdx.x % NCH)
   constexpr int V = NC / 2;                  // columns per epilogue thread
   constexpr int DC = SPLIT ? 2 * NC : NC;    // accumulator columns per buffer
   constexpr uint32_t kACols = 256;           // TMEM: A halves [h*128, +64) hi, [+64, +128) lo
@@ -86,6 +86,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   float* s_bias = reinterpret_cast<float*>(smem + L::kMisc + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x % NCH;          // this CTA's column chunk (fixed: W staged once)
+  const int cslot = blockIdx.x / NCH;          // position among the CTAs that share the chunk
+  const int cgrid = gridDim.x / NCH;
   const uint32_t bar0 = smem_u32(s_bar);
   auto bar_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };            // [0,4)
   auto bar_empty = [&](int s) { return bar0 + 32u + 8u * (uint32_t)s; };     // [4,8)
@@ -109,11 +112,11 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   }
   if (warp == 17) tmem_alloc(smem_u32(s_tmem), kTmemCols);
   if (warp == 16 && lane == 0) tma_prefetch_desc(&tmap_h);
-  for (int i = threadIdx.x; i < N; i += kTmaThreads) s_bias[i] = bias[i];
+  for (int i = threadIdx.x; i < NC; i += kTmaThreads) s_bias[i] = bias[chunk * NC + i];
   if (warp < 8) {  // stacked W operand: row n = W_hi[n], row NC + n = W_lo[n]; K-major, SW128
     for (int q = threadIdx.x; q < NC * 32; q += 256) {
       const int n = q >> 5, kc = q & 31;
-      const float4 w = __ldg(reinterpret_cast<const float4*>(W) + q);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(W) + (int64_t)chunk * NC * 32 + q);
       const float4 hi = make_float4(tf32_hi(w.x), tf32_hi(w.y), tf32_hi(w.z), tf32_hi(w.w));
       uint8_t* atom = sB + (kc >> 3) * L::kAtomB;
       *reinterpret_cast<float4*>(atom + sw128_off(n, kc & 7)) = hi;
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   const uint32_t tmem_d0 = tmem_base + kACols;
 
   const int64_t ntiles = (M + kTileM - 1) / kTileM;
-  const int64_t nitems = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t nitems = cslot < ntiles ? (ntiles - cslot + cgrid - 1) / cgrid : 0;
   double st_sum = 0.0, st_sq = 0.0;
 
   if (warp < 8) {
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       const int b = (int)(it & 1);
       mbar_wait(bar_dfull(b), (uint32_t)((it >> 1) & 1));
       tc_fence_after_sync();
-      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t tile = cslot + it * cgrid;
       const int col0 = (ew >> 2) * V;
       const int64_t grow = tile * kTileM + (ew & 3) * 32 + lane;
       const bool row_ok = grow < M;
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       tc_fence_before_sync();
       mbar_arrive(bar_dfree(b));
       if (row_ok) {
-        float4* zp = reinterpret_cast<float4*>(z_out + grow * N + col0);
+        float4* zp = reinterpret_cast<float4*>(z_out + grow * N + chunk * NC + col0);
 #pragma unroll
         for (int j = 0; j < V; j += 4) stg_stream(zp + j / 4, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
       }
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       for (int64_t it = 0; it < nitems; ++it) {
         const int s = (int)(it % S);
         if (it >= S) mbar_wait(bar_empty(s), (uint32_t)(((it / S) - 1) & 1));
-        const int row0 = (int)((blockIdx.x + it * gridDim.x) * kTileM);
+        const int row0 = (int)((cslot + it * cgrid) * kTileM);
         mbar_expect_tx(bar_full(s), (uint32_t)L::kStage);
         const uint32_t dst = smem_u32(smem + s * L::kStage);
 #pragma unroll
@@ -264,25 +267,27 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   }
   __syncthreads();
   for (int col = threadIdx.x; col < N; col += kTmaThreads) {
-    const int half = col / V, l = col % V;
     double a = 0.0, bq = 0.0;
+    if (col / NC == chunk) {  // columns of other chunks belong to other CTAs: contribute zeros
+      const int cc = col % NC, half = cc / V, l = cc % V;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      a += s_red[((half * 4 + q) * V + l) * 2];
-      bq += s_red[((half * 4 + q) * V + l) * 2 + 1];
+      for (int q = 0; q < 4; ++q) {
+        a += s_red[((half * 4 + q) * V + l) * 2];
+        bq += s_red[((half * 4 + q) * V + l) * 2 + 1];
+      }
     }
     partial[(int64_t)blockIdx.x * 2 * N + col] = (float)a;
     partial[(int64_t)blockIdx.x * 2 * N + N + col] = (float)bq;
   }
 }
 
-template <int NC, bool SPLIT>
+template <int NC, int NCH, bool SPLIT>
 static int launch_fwd_tma(const float* h, const float* W, const float* bias, int64_t M, float* z, float* partial,
                           int grid, cudaStream_t st) {
   using L = TmaSmem<NC>;
   CUtensorMap tmap;
   if (!make_tmap_2d(&tmap, h, M, 128, kTileM)) return VMTL_ECUDA;
-  auto kern = gate_tc_fwd_tma_kernel<NC, SPLIT>;
+  auto kern = gate_tc_fwd_tma_kernel<NC, NCH, SPLIT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes) != cudaSuccess)
     return VMTL_ECUDA;
   kern<<<grid, kTmaThreads, L::kBytes, st>>>(tmap, W, bias, M, z, partial);

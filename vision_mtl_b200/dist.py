@@ -36,9 +36,11 @@ def init_distributed(backend: t.Optional[str] = None) -> t.Tuple[int, int, int]:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
+        kwargs = {}
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+            kwargs["device_id"] = torch.device("cuda", local_rank)  # binds the communicator, no barrier() warning
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
     return rank, local_rank, world
 
 
