@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lr", type=float, default=5e-4)
+    ap.add_argument("--no-graph", action="store_true", help="eager step instead of the whole-step CUDA graph")
     return ap.parse_args()
 
 
@@ -222,27 +223,31 @@ def main():
     module.to(dev)
     module.model.to(memory_format=torch.channels_last)
     module.model.train()
-    vdist.wrap_data_parallel(module, local_rank)
-    opt = torch.optim.Adam(module.parameters(), lr=args.lr, fused=True)
+    use_graph = not args.no_graph
+    if world > 1:
+        side = torch.cuda.Stream()  # DDP built on a side stream so its buckets are capture-friendly
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            vdist.wrap_data_parallel(module, local_rank)
+        torch.cuda.current_stream().wait_stream(side)
+    opt = torch.optim.Adam(module.parameters(), lr=args.lr, fused=True, capturable=use_graph)
 
     host = make_batch(B, H, W, C, dataset, seed=11 + rank, pin=True)          # pinned host copy
     resident = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     resident["img"] = resident["img"].contiguous(memory_format=torch.channels_last)
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
-    def train_step(batch):
+    def metric_exchange():
+        if world > 1:  # the one metric exchange of the step (confusion matrix + loss)
+            module.last_global_stats = vdist.allreduce_step_stats(module.last_confusion, module.last_step_scalars[0])
+
+    def eager_step(batch):
         opt.zero_grad(set_to_none=True)
         loss = module.training_step(batch, 0)
         loss.backward()
+        metric_exchange()
         opt.step()
-        if world > 1:  # the one metric exchange of the step (confusion matrix + loss)
-            module.last_global_stats = vdist.allreduce_step_stats(module.last_confusion, loss)
         return loss
-
-    def e2e_step():
-        batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        train_step(batch)
-        return module.last_step_scalars.cpu()  # one D2H copy: loss + 4 metrics
 
     def barrier():
         if world > 1:
@@ -250,26 +255,68 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        train_step(resident)
+        eager_step(resident)
     barrier()
 
-    # ---- timed region: resident batch, per-launch kernel events recorded live ----------------
+    # ---- per-launch kernel events (roofline): recorded around every library call ---------------
+    # eager mode: inside the timed region; graph mode: in an eager pass of the identical step, because
+    # a graph replay exposes no per-launch host hooks
     sampler = ClockSampler(local_rank)
+    graphed = None
+    if use_graph:
+        ops.reset_launch_count()
+        with ops.kernel_timing() as records:
+            for _ in range(min(args.steps, 5)):
+                eager_step(resident)
+            barrier()
+        launches_per_step = ops.launch_count() // min(args.steps, 5)
+        kstats = ops.summarize_timing(records)
+        ksteps = min(args.steps, 5)
+        from vision_mtl_b200.graph_step import GraphedTrainStep
+
+        graphed = GraphedTrainStep(module, opt, resident, warmup=11 if world > 1 else 3, after_backward=metric_exchange)
+        for _ in range(3):
+            graphed()
+        barrier()
+
+    def train_step(batch):
+        if graphed is not None:
+            return graphed(None if batch is resident else batch)
+        return eager_step(batch)
+
+    def e2e_step():
+        if graphed is not None:
+            graphed(host)  # H2D copies into the static inputs, one graph launch
+        else:
+            eager_step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
+        return module.last_step_scalars.cpu()  # one D2H copy: loss + 4 metrics
+
+    # ---- timed region: batch resident in HBM ---------------------------------------------------
     if rank == 0:
         sampler.start()
-    ops.reset_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ops.kernel_timing() as records:
+    if graphed is None:
+        ops.reset_launch_count()
+        with ops.kernel_timing() as records:
+            barrier()
+            ev0.record()
+            for _ in range(args.steps):
+                train_step(resident)
+            ev1.record()
+            barrier()
+        launches_per_step = ops.launch_count() // args.steps
+        kstats = ops.summarize_timing(records)
+        ksteps = args.steps
+    else:
         barrier()
         ev0.record()
         for _ in range(args.steps):
             train_step(resident)
         ev1.record()
         barrier()
-    launches = ops.launch_count()
+    launches = launches_per_step * args.steps
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
-    kstats = ops.summarize_timing(records)
 
     # ---- e2e: host batch in, step scalars out, every step ------------------------------------
     for _ in range(2):
@@ -311,6 +358,8 @@ def main():
         roofline = {"bound": "hbm", "kernel": "vmtl_" + name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                     "peak_source": peak_src,
+                    "events_from": ("eager pass of the identical step right before the timed graph replays"
+                                    if graphed is not None else "the timed region"),
                     "launches_timed": d["calls"], "avg_launch_ms": d["ms"] / d["calls"],
                     "algorithmic_bytes_per_launch": d["bytes"] / d["calls"]}
     line = {
@@ -323,6 +372,7 @@ def main():
             "global_batch": B * world, "parallelism": f"dp{world}",
             "conv_math": "tf32 (cuDNN)" if args.conv_tf32 else "fp32 (cuDNN, TF32 off)",
             "gate_precision": args.gate_precision, "stitch_mode": args.stitch_mode,
+            "step_launch": "one CUDA graph per step (fwd + fused losses/metrics + bwd + Adam)" if graphed is not None else "eager",
             "l2": "per-step working set (activations of a batch-%d step) >> 126 MB L2; no explicit flush" % B,
             "backbone": "stand-in MobileNetV3-Large/Unet (smp/timm not installable offline)" if model != "mtan" else "reference MTAN mini-UNet",
         },
@@ -332,7 +382,7 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
-        "kernels": {k: {"calls": v["calls"], "ms_per_step": v["ms"] / args.steps, "gbps": v["gbps"],
+        "kernels": {k: {"calls": v["calls"], "ms_per_step": v["ms"] / ksteps, "gbps": v["gbps"],
                         "frac_of_peak": v["gbps"] / peak} for k, v in sorted(kstats.items())},
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -1,0 +1,63 @@
+"""The whole-step CUDA graph must do exactly what the eager step does."""
+import pytest
+import torch
+
+from oracle import fixtures as FX
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("model_name", ["mtan", "csnet"])
+def test_graphed_step_equals_eager(model_name):
+    from vision_mtl_b200.graph_step import GraphedTrainStep
+    from vision_mtl_b200.lit_module import MTLModule
+    from vision_mtl_b200.models import CSNet
+    from vision_mtl_b200.models.mtan_model import MTANMiniUnet
+    from vision_mtl_b200.utils.model_utils import get_model_with_dense_preds
+
+    dev = torch.device("cuda:0")
+    C = 19
+
+    def build():
+        torch.manual_seed(3)
+        if model_name == "mtan":
+            net = MTANMiniUnet(3, {"depth": 1, "segm": C}, 128, 32, 2)
+        else:
+            net = CSNet({"depth": get_model_with_dense_preds(1, None, dict(encoder_weights=None)),
+                         "segm": get_model_with_dense_preds(C, None, dict(encoder_weights=None))},
+                        channel_wise_stitching=True)
+        net.to(dev).to(memory_format=torch.channels_last).train()
+        module = MTLModule(net, num_classes=C, device=dev)
+        # plain SGD: Adam turns round-off-sized gradients into +-lr moves, which would hide real errors
+        opt = torch.optim.SGD(module.parameters(), lr=1e-2)
+        return net, module, opt
+
+    batches = [{k: v.to(dev) for k, v in FX.image_batch(2, 64, 64, C, f"graph/{i}").items()} for i in range(3)]
+    for b in batches:
+        b["img"] = b["img"].contiguous(memory_format=torch.channels_last)
+
+    # eager: warm-up steps on batch 0 (what GraphedTrainStep does before capturing), then batches 1, 2
+    net_e, mod_e, opt_e = build()
+    losses_e = []
+    for b in [batches[0]] * 4 + batches[1:]:
+        opt_e.zero_grad(set_to_none=True)
+        loss = mod_e.training_step(b, 0)
+        loss.backward()
+        opt_e.step()
+        losses_e.append(loss.item())
+    # graphed: 3 warm-up steps + 1 captured-run step on batch 0 happen inside the constructor/capture? no:
+    # capture does not execute; so: constructor = 3 eager warm-ups, then replays on batch 0, 1, 2
+    net_g, mod_g, opt_g = build()
+    g = GraphedTrainStep(mod_g, opt_g, batches[0], warmup=3)
+    losses_g = [g(b).item() for b in batches]
+    assert len(mod_g.step_outputs["train"]["loss"]) == 0  # capture leaves no stale records behind
+    # same weights, same batch -> the first replay reproduces the eager loss; afterwards the two runs
+    # drift apart slowly (cuDNN backward kernels use atomics, Adam amplifies the round-off)
+    # (two EAGER runs of this sequence already differ by ~5e-4 after four Adam steps)
+    for le, lg in zip(losses_e[3:], losses_g):
+        assert abs(le - lg) <= 5e-3 * abs(le), (losses_e, losses_g)
+    rel = []
+    for (k, p), q in zip(net_e.named_parameters(), net_g.parameters()):
+        rel.append(float((p - q).abs().max() / p.abs().max().clamp_min(1e-12)))
+    assert sorted(rel)[len(rel) // 2] <= 1e-4 and max(rel) <= 2e-2, (sorted(rel)[len(rel) // 2], max(rel))
+    assert torch.equal(mod_g.last_confusion.sum(), torch.tensor(2 * 64 * 64, device=dev))

@@ -88,18 +88,17 @@ def pack_step_stats(conf: torch.Tensor, loss: torch.Tensor, depth_sums: t.Option
     head = torch.zeros(2, dtype=torch.float64, device=dev)
     tail = torch.stack([loss.detach().to(torch.float64).reshape(()), torch.ones((), dtype=torch.float64, device=dev)])
     # layout of the extras: [0, 0, sum|p-t|, P, sum rel, n_valid, loss, 1]
-    return torch.cat([conf.reshape(-1).to(torch.float64), head, d[[1, 0, 3, 2]], tail])
+    # (no list-indexing here: it would build a host index tensor, i.e. a copy inside graph capture)
+    return torch.cat([conf.reshape(-1).to(torch.float64), head, torch.stack([d[1], d[0], d[3], d[2]]), tail])
 
 
 def unpack_step_stats(buf: torch.Tensor, num_classes: int) -> dict:
     CC = num_classes * num_classes
     conf = buf[:CC].round().to(torch.int64).reshape(num_classes, num_classes)
     e = buf[CC:]
-    out = {"confusion": conf, "loss": e[6] / e[7], "replicas": e[7]}
-    if float(e[3]) > 0:
-        out["mae"] = e[2] / e[3]
-        out["abs_rel"] = e[4] / torch.clamp(e[5], min=1.0)
-    return out
+    # no host reads here: this runs inside the captured step graph
+    return {"confusion": conf, "loss": e[6] / e[7], "replicas": e[7],
+            "mae": e[2] / torch.clamp(e[3], min=1.0), "abs_rel": e[4] / torch.clamp(e[5], min=1.0)}
 
 
 def allreduce_step_stats(conf: torch.Tensor, loss: torch.Tensor, depth_sums: t.Optional[torch.Tensor] = None) -> dict:
