@@ -29,7 +29,7 @@ def test_graphed_step_equals_eager(model_name):
         net.to(dev).to(memory_format=torch.channels_last).train()
         module = MTLModule(net, num_classes=C, device=dev)
         # plain SGD: Adam turns round-off-sized gradients into +-lr moves, which would hide real errors
-        opt = torch.optim.SGD(module.parameters(), lr=1e-2)
+        opt = torch.optim.SGD(module.parameters(), lr=1e-4)  # small: keeps the 6-step trajectories from amplifying round-off
         return net, module, opt
 
     batches = [{k: v.to(dev) for k, v in FX.image_batch(2, 64, 64, C, f"graph/{i}").items()} for i in range(3)]
@@ -59,5 +59,5 @@ def test_graphed_step_equals_eager(model_name):
     rel = []
     for (k, p), q in zip(net_e.named_parameters(), net_g.parameters()):
         rel.append(float((p - q).abs().max() / p.abs().max().clamp_min(1e-12)))
-    assert sorted(rel)[len(rel) // 2] <= 1e-4 and max(rel) <= 2e-2, (sorted(rel)[len(rel) // 2], max(rel))
+    assert sorted(rel)[len(rel) // 2] <= 1e-5 and max(rel) <= 1e-3, (sorted(rel)[len(rel) // 2], max(rel))
     assert torch.equal(mod_g.last_confusion.sum(), torch.tensor(2 * 64 * 64, device=dev))

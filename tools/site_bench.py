@@ -103,6 +103,9 @@ def main():
                 return ops.cross_stitch(xs, alpha, "reference_diag")
 
             def bwd(ys):
+                for t_ in xs:
+                    t_.grad = None  # otherwise AccumulateGrad adds into the old .grad (an extra 3x pass)
+                alpha.grad = None
                 torch.autograd.backward(ys, dys)
 
             timed("xstitch", f"C={Cc} {h}x{w}", 8 * E, 12 * E, fwd, bwd)
@@ -115,21 +118,29 @@ def main():
         tgt = torch.randint(0, C, (B, H, W), device=dev)
         dt = torch.rand(B, H, W, 1, device=dev) * 0.5
         conf = torch.zeros(C, C, dtype=torch.int64, device=dev)
+        def bw(leaves):
+            def f(l):
+                for t_ in leaves:
+                    t_.grad = None
+                l.backward()
+            return f
+
         timed("head_ce", f"P={P} C={C}", P * (4 * 32 + 8 + 1), P * (8 * 32 + 8),
               lambda: ops.head_cross_entropy(feat, head.weight, head.bias, tgt, -100, conf, True)[0],
-              lambda l: l.backward())
+              bw([feat, head.weight, head.bias]))
         timed("head_silog", f"P={P}", P * (4 * 32 + 4), P * (8 * 32 + 4),
-              lambda: ops.head_silog(feat, dhead.weight, dhead.bias, dt, 1e-3, False)[0], lambda l: l.backward())
+              lambda: ops.head_silog(feat, dhead.weight, dhead.bias, dt, 1e-3, False)[0],
+              bw([feat, dhead.weight, dhead.bias]))
         for layout in ("nhwc", "nchw"):
             lg = torch.randn(B, C, H, W, device=dev)
             if layout == "nhwc":
                 lg = lg.contiguous(memory_format=torch.channels_last)
             lg.requires_grad_(True)
             timed(f"ce_logits_{layout}", f"P={P} C={C}", P * (4 * C + 8 + 1), P * (8 * C + 8),
-                  lambda: ops.cross_entropy_logits(lg, tgt, -100, conf, True)[0], lambda l: l.backward())
+                  lambda: ops.cross_entropy_logits(lg, tgt, -100, conf, True)[0], bw([lg]))
         dl = torch.randn(B, 1, H, W, device=dev, requires_grad=True)
         timed("silog_logits", f"P={P}", P * 8, P * 12, lambda: ops.head_silog(dl, None, None, dt, 1e-3, False)[0],
-              lambda l: l.backward())
+              bw([dl]))
 
     if args.only in ("", "metrics"):
         P = B * H * W
