@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   constexpr int V = NC / 2;          // columns per thread in the epilogue
   constexpr uint32_t kTmemCols = 2 * NC;  // 64 or 128: power of two >= 32
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer (LDS/STS, not generic LD/ST)
   uint8_t* sAhi = smem + L::kAhi;
   uint8_t* sAlo = smem + L::kAlo;
   uint8_t* sBhi = smem + L::kBhi;
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   constexpr int PER = kTileM * N4 / kTcThreads;  // float4 of dz per thread per tile (4 or 8)
   constexpr uint32_t kTmemCols = 2 * KH;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer (LDS/STS, not generic LD/ST)
   uint8_t* sAhi = smem + L::kAhi;
   uint8_t* sAlo = smem + L::kAlo;
   uint8_t* sBhi = smem + L::kBhi;
@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   constexpr int KH = 128;
   constexpr uint32_t kTmemCols = N < 32 ? 32 : N;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer (LDS/STS, not generic LD/ST)
   uint8_t* sHhi = smem + L::kHhi;
   uint8_t* sHlo = smem + L::kHlo;
   uint8_t* sDhi = smem + L::kDhi;

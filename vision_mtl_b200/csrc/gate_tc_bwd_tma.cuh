@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   constexpr uint32_t kACols = 256;  // two A buffers of 128 columns: atom a -> hi [a*64, +32), lo [a*64+32, +32)
   constexpr uint32_t kTmemCols = 512;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer (LDS/STS, not generic LD/ST)
   uint8_t* sBhi = smem + L::kBhi;
   uint8_t* sBlo = smem + L::kBlo;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::kMisc);
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   constexpr uint32_t kACols = 256;  // A half buffer hb: hi [hb*128, +64), lo [hb*128+64, +64); column = pixel row
   constexpr uint32_t kTmemCols = 512;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer (LDS/STS, not generic LD/ST)
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::kMisc);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::kMisc + 192);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

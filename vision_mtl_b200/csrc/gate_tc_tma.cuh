@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   constexpr uint32_t kACols = 256;           // TMEM: A halves [h*128, +64) hi, [+64, +128) lo
   constexpr uint32_t kTmemCols = 512;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer (LDS/STS, not generic LD/ST)
   uint8_t* sB = smem + L::kB;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::kMisc);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::kMisc + 192);

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1)
   constexpr int DC = SPLIT ? 2 * NC : NC;   // accumulator columns per buffer
   constexpr uint32_t kTmemCols = 2 * DC;    // 64..256, power of two
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer (LDS/STS, not generic LD/ST)
   uint8_t* sAhi = smem + L::kAhi;
   uint8_t* sAlo = smem + L::kAlo;
   uint8_t* sB = smem + L::kB;

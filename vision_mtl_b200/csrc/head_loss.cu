@@ -17,6 +17,10 @@
 // the confusion matrix uses integer atomics only.
 #include <math.h>
 
+#include <stdlib.h>
+#include <string.h>
+
+#include "head_internal.cuh"
 #include "vmtl_common.cuh"
 
 namespace vmtl {
@@ -735,9 +739,24 @@ extern "C" int vmtl_head_ce_fwd(const float* feat, const float* W, const float* 
   if (!cpad) return VMTL_EUNSUPPORTED;
   if (!aligned16(feat)) return VMTL_EALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* partial = static_cast<double*>(workspace);
+  // tensor-core projection (head_tc.cu) unless VMTL_HEAD_FWD=ffma; tiny inputs keep the CUDA-core kernel
+  static const bool use_tc = [] {
+    const char* e = getenv("VMTL_HEAD_FWD");
+    return !(e && strcmp(e, "ffma") == 0);
+  }();
+  if (use_tc && P >= 128) {
+    int g = 0;
+    const int max_blocks = (int)(workspace_bytes / (2 * sizeof(double)));
+    const int rc = head_ce_tc_fwd(feat, W, b, target, P, C, ignore_index, partial, max_blocks, &g, pred, conf, st);
+    if (rc == VMTL_OK) {
+      ce_finalize<<<1, kFinThreads, 0, st>>>(partial, g, out, loss);
+      return launch_status();
+    }
+    if (rc != VMTL_EUNSUPPORTED) return rc;
+  }
   const int grid = loss_grid(P, kLossThreads, 4);
   if (workspace_bytes < (size_t)grid * 2 * sizeof(double)) return VMTL_EWORKSPACE;
-  double* partial = static_cast<double*>(workspace);
   const size_t smem = conf ? (size_t)C * C * sizeof(unsigned int) : 0;
   const float4* f4 = reinterpret_cast<const float4*>(feat);
   unsigned long long* cf = reinterpret_cast<unsigned long long*>(conf);

@@ -1,0 +1,312 @@
+// Segmentation head (1x1 conv, 32 -> C <= 32) fused with softmax / argmax / cross-entropy / confusion,
+// projection on tensor cores: TMA -> smem -> TMEM (tf32 hi/lo) -> tcgen05 -> per-pixel epilogue.
+//
+// Replaces nn.Conv2d(32,C,1) + softmax + argmax + CrossEntropyLoss + the torchmetrics statistics
+// (mtan_model.py:367-376,401-404; lit_module.py:31,123,137-138,109-111).
+//
+// Why tensor cores here: the CUDA-core version (head_loss.cu) spends ~1450 instructions per pixel
+// (608 FMA + 152 shared loads + accurate exp/log) and sits at 20 % of the HBM roofline.  A 128-pixel
+// tile is a [128 x 32] x [32 x 32] contraction = 8 tcgen05.mma (3xTF32 with the stacked W operand:
+// A_hi @ [W_hi;W_lo]^T and A_lo @ W_hi^T per K-step) -- ~360 tensor-pipe cycles against the ~400
+// cycles the tile's 17 KB take at the roofline -- and tcgen05.ld hands every epilogue thread exactly
+// one pixel's logits, which is the shape softmax / argmax / CE want.
+//
+// Roles (22 warps): 0-3 converters (one pixel row per thread: smem -> hi/lo -> TMEM), 4-19 four
+// epilogue groups (group g owns accumulator buffer g = tiles g, g+4, ...; a tile's epilogue is a
+// ~300-instruction dependent chain per warp, so throughput comes from groups in flight),
+// 20 TMA producer, 21 MMA issuer.
+// Feature tile = ONE 128B-swizzled atom of 16 KB; 8 stages -> 128 KB in flight per SM.
+#include <cuda.h>
+#include <math.h>
+
+#include "head_internal.cuh"
+#include "tcgen05.cuh"
+
+namespace vmtl {
+
+using namespace tc;
+
+constexpr int kHtThreads = 22 * 32;
+constexpr int kHtTile = 128;
+constexpr int kHtStages = 8;
+constexpr int kHtStageBytes = kHtTile * 128;  // 16 KB
+
+struct HtSmem {
+  static constexpr int kW = kHtStages * kHtStageBytes;  // stacked W operand: [64 rows x 128 B]
+  static constexpr int kMisc = kW + 64 * 128;
+  static constexpr int kConf = kMisc + 512;             // uint32 [32*32]
+  static constexpr int kBytes = kConf + 32 * 32 * 4 + 1024;
+};
+
+typedef CUresult (*PFN_encodeTiledH)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool ht_make_tmap(CUtensorMap* m, const float* base, int64_t rows) {
+  static PFN_encodeTiledH enc = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<PFN_encodeTiledH>(p);
+  }();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {32, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {32 * sizeof(float)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)kHtTile};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ float fast_exp(float x) {  // ex2.approx: ~2 ulp, inputs here are <= 0
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+  return r;
+}
+__device__ __forceinline__ float fast_log(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * 0.6931471805599453f;
+}
+
+template <int CPAD>
+__global__ void __launch_bounds__(kHtThreads, 1)
+    head_ce_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_f, const float* __restrict__ W,
+                          const float* __restrict__ bias, const int64_t* __restrict__ target, int64_t P, int C,
+                          int64_t ignore_index, double* __restrict__ partial, uint8_t* __restrict__ pred,
+                          unsigned long long* __restrict__ conf) {
+  using L = HtSmem;
+  constexpr int S = kHtStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer (LDS/STS, not generic LD/ST)
+  uint8_t* sW = smem + L::kW;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::kMisc);   // full[8] empty[8] aready[4] amma[4] dfull[4] dfree[4]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::kMisc + 288);
+  float* s_bias = reinterpret_cast<float*>(smem + L::kMisc + 320);  // [32]
+  unsigned int* s_conf = reinterpret_cast<unsigned int*>(smem + L::kConf);
+  __shared__ double s_part[16][2];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto bar_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto bar_empty = [&](int s) { return bar0 + 64u + 8u * (uint32_t)s; };
+  auto bar_aready = [&](int b) { return bar0 + 128u + 8u * (uint32_t)b; };
+  auto bar_amma = [&](int b) { return bar0 + 160u + 8u * (uint32_t)b; };
+  auto bar_dfull = [&](int b) { return bar0 + 192u + 8u * (uint32_t)b; };
+  auto bar_dfree = [&](int b) { return bar0 + 224u + 8u * (uint32_t)b; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 128);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar_aready(i), 128);
+      mbar_init(bar_amma(i), 1);
+      mbar_init(bar_dfull(i), 1);
+      mbar_init(bar_dfree(i), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 21) tmem_alloc(smem_u32(s_tmem), 512);
+  if (warp == 20 && lane == 0) tma_prefetch_desc(&tmap_f);
+  for (int i = threadIdx.x; i < 32; i += kHtThreads) s_bias[i] = i < C ? bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 32 * 32; i += kHtThreads) s_conf[i] = 0u;
+  // stacked W operand: row n (< 32) = W_hi[n], row 32 + n = W_lo[n]; classes >= C are zero rows
+  for (int e = threadIdx.x; e < 32 * 32; e += kHtThreads) {
+    const int n = e >> 5, k = e & 31;
+    const float w = n < C ? W[n * 32 + k] : 0.f;
+    const float hi = tf32_hi(w);
+    *reinterpret_cast<float*>(sW + n * 128 + (((k >> 2) ^ (n & 7)) << 4) + ((k & 3) << 2)) = hi;
+    *reinterpret_cast<float*>(sW + (32 + n) * 128 + (((k >> 2) ^ ((32 + n) & 7)) << 4) + ((k & 3) << 2)) = w - hi;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_d0 = tmem_base + 256;
+
+  const int64_t ntiles = (P + kHtTile - 1) / kHtTile;
+  const int64_t nitems = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  double loss_acc = 0.0, n_acc = 0.0;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ converters (thread = pixel row)
+    const int row = warp * 32 + lane;
+    for (int64_t it = 0; it < nitems; ++it) {
+      const int s = (int)(it % S), ab = (int)(it & 3);
+      mbar_wait(bar_full(s), (uint32_t)((it / S) & 1));
+      const uint8_t* st = smem + s * kHtStageBytes;
+      float4 c[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) c[j] = *reinterpret_cast<const float4*>(st + sw128_off(row, j));
+      mbar_arrive(bar_empty(s));
+      if (it >= 4) {
+        mbar_wait(bar_amma(ab), (uint32_t)(((it >> 2) - 1) & 1));
+        tc_fence_after_sync();
+      }
+      const uint32_t ta = tmem_base + (((uint32_t)warp * 32) << 16) + (uint32_t)(ab * 64);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 a = c[g * 4 + j];
+          hi[4 * j] = tf32_hi(a.x); hi[4 * j + 1] = tf32_hi(a.y); hi[4 * j + 2] = tf32_hi(a.z); hi[4 * j + 3] = tf32_hi(a.w);
+          lo[4 * j] = a.x - hi[4 * j]; lo[4 * j + 1] = a.y - hi[4 * j + 1];
+          lo[4 * j + 2] = a.z - hi[4 * j + 2]; lo[4 * j + 3] = a.w - hi[4 * j + 3];
+        }
+        tmem_st16(ta + g * 16, hi);
+        tmem_st16(ta + 32 + g * 16, lo);
+      }
+      tmem_wait_st();
+      tc_fence_before_sync();
+      mbar_arrive(bar_aready(ab));
+    }
+  } else if (warp < 20) {
+    // ------------------------------------------------------------------ epilogue groups (tile it -> group it % 4)
+    const int g = (warp - 4) >> 2, quad = warp & 3;
+    const uint32_t taddr = tmem_d0 + (((uint32_t)quad * 32) << 16) + (uint32_t)(g * 64);
+    for (int64_t it = g; it < nitems; it += 4) {
+      const int64_t p = (blockIdx.x + it * gridDim.x) * kHtTile + quad * 32 + lane;
+      const int64_t t = p < P ? __ldg(target + p) : ignore_index;  // in flight while the MMAs finish
+      mbar_wait(bar_dfull(g), (uint32_t)((it >> 2) & 1));
+      tc_fence_after_sync();
+      float l[CPAD], l2[CPAD];
+      tmem_ld16_nowait(taddr, l);            // A_hi W_hi + A_lo W_hi
+      tmem_ld16_nowait(taddr + 32, l2);      // A_hi W_lo
+      if (CPAD == 20) {
+        tmem_ld4_nowait(taddr + 16, l + 16);
+        tmem_ld4_nowait(taddr + 48, l2 + 16);
+      } else if (CPAD == 32) {
+        tmem_ld16_nowait(taddr + 16, l + 16);
+        tmem_ld16_nowait(taddr + 48, l2 + 16);
+      }
+      tmem_wait_ld();
+#pragma unroll
+      for (int c = 0; c < CPAD; c += 4) {
+        tmem_pin4(l + c);
+        tmem_pin4(l2 + c);
+      }
+      tc_fence_before_sync();
+      mbar_arrive(bar_dfree(g));
+#pragma unroll
+      for (int c = 0; c < CPAD; ++c) l[c] = l[c] + l2[c] + s_bias[c];
+      float m = l[0];
+      int arg = 0;
+#pragma unroll
+      for (int c = 1; c < CPAD; ++c)
+        if ((CPAD == C || c < C) && l[c] > m) {
+          m = l[c];
+          arg = c;
+        }
+      float sum = 0.f, lt = 0.f;
+      const int ti = (int)t;
+#pragma unroll
+      for (int c = 0; c < CPAD; ++c) {
+        const float e = fast_exp(l[c] - m);
+        sum += (CPAD == C || c < C) ? e : 0.f;
+        lt += (c == ti) ? l[c] : 0.f;
+      }
+      if (p < P) {
+        if (pred) pred[p] = (uint8_t)arg;
+        if (t != ignore_index && (uint64_t)t < (uint64_t)C) {
+          loss_acc += (double)(m + fast_log(sum) - lt);
+          n_acc += 1.0;
+          if (conf) red_shared_add(smem_u32(s_conf) + 4u * (uint32_t)(ti * C + arg), 1u);
+        }
+      }
+    }
+  } else if (warp == 20) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int64_t it = 0; it < nitems; ++it) {
+        const int s = (int)(it % S);
+        if (it >= S) mbar_wait(bar_empty(s), (uint32_t)(((it / S) - 1) & 1));
+        mbar_expect_tx(bar_full(s), (uint32_t)kHtStageBytes);
+        tma_load_2d(smem_u32(smem + s * kHtStageBytes), &tmap_f, 0, (int)((blockIdx.x + it * gridDim.x) * kHtTile),
+                    bar_full(s));
+      }
+    }
+  } else if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_wide = idesc_tf32(kHtTile, 64, 0, 0);
+    constexpr uint32_t idesc_n = idesc_tf32(kHtTile, 32, 0, 0);
+    const uint32_t bW = smem_u32(sW);
+    for (int64_t it = 0; it < nitems; ++it) {
+      const int ab = (int)(it & 3);
+      mbar_wait(bar_aready(ab), (uint32_t)((it >> 2) & 1));
+      if (it >= 4) mbar_wait(bar_dfree(ab), (uint32_t)(((it >> 2) - 1) & 1));
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_d0 + (uint32_t)(ab * 64);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t a_hi = tmem_base + (uint32_t)(ab * 64 + ks * 8);
+        const uint64_t dB = smem_desc_sw128(bW + ks * 32, 16, 1024);
+        mma_tf32_ts(d_tmem, a_hi, dB, idesc_wide, ks != 0);
+        mma_tf32_ts(d_tmem, a_hi + 32, dB, idesc_n, 1);
+      }
+      mma_commit(bar_amma(ab));
+      mma_commit(bar_dfull(ab));
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 21) tmem_dealloc(tmem_base, 512);
+  if (conf)
+    for (int i = threadIdx.x; i < C * C; i += kHtThreads) {
+      const unsigned int v = s_conf[i];
+      if (v) atomicAdd(conf + i, (unsigned long long)v);
+    }
+  // (loss sum, valid count) partial of this CTA: the 16 epilogue warps in fixed order
+  loss_acc = warp_sum(loss_acc);
+  n_acc = warp_sum(n_acc);
+  if (warp >= 4 && warp < 20 && lane == 0) {
+    s_part[warp - 4][0] = loss_acc;
+    s_part[warp - 4][1] = n_acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double s = 0.0;
+    for (int w = 0; w < 16; ++w) s += s_part[w][threadIdx.x];
+    partial[(int64_t)blockIdx.x * 2 + threadIdx.x] = s;
+  }
+}
+
+int head_ce_tc_fwd(const float* feat, const float* W, const float* b, const int64_t* target, int64_t P, int C,
+                   int64_t ignore_index, double* partial, int max_blocks, int* grid_out, uint8_t* pred,
+                   int64_t* conf, cudaStream_t st) {
+  if (C > 32 || P < 1) return VMTL_EUNSUPPORTED;
+  CUtensorMap tmap;
+  if (!ht_make_tmap(&tmap, feat, P)) return VMTL_ECUDA;
+  const int64_t ntiles = (P + kHtTile - 1) / kHtTile;
+  int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  if (grid > max_blocks) grid = max_blocks;
+  *grid_out = grid;
+  unsigned long long* cf = reinterpret_cast<unsigned long long*>(conf);
+#define VMTL_HT(CP)                                                                                          \
+  do {                                                                                                       \
+    if (cudaFuncSetAttribute(head_ce_tc_fwd_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                             HtSmem::kBytes) != cudaSuccess)                                                 \
+      return VMTL_ECUDA;                                                                                     \
+    head_ce_tc_fwd_kernel<CP><<<grid, kHtThreads, HtSmem::kBytes, st>>>(tmap, W, b, target, P, C,            \
+                                                                         ignore_index, partial, pred, cf);   \
+  } while (0)
+  if (C <= 16)
+    VMTL_HT(16);
+  else if (C <= 20)
+    VMTL_HT(20);
+  else
+    VMTL_HT(32);
+#undef VMTL_HT
+  return launch_status();
+}
+
+}  // namespace vmtl

@@ -21,19 +21,22 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// try_wait parks the thread until the phase completes or the hint expires; without a hint it returns
+// after a few tens of ns and the retry loops of idle warps eat the issue slots of the working ones.
+constexpr uint32_t kMbarSuspendNs = 2000;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   uint32_t spins = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(kMbarSuspendNs)
         : "memory");
     // a tile's MMAs take microseconds; a wait this long means a lost arrival -> fail loudly
-    if (!done && ++spins > (1u << 26)) __trap();
+    if (!done && ++spins > (1u << 22)) __trap();
   } while (!done);
 }
 
@@ -201,13 +204,43 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// un-waited forms: issue several loads, then ONE tmem_wait_ld() before the registers are used
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, float* v) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// ties 4 loaded registers to a point after the wait (volatile asms keep their order), so the compiler
+// cannot schedule a use of them above tmem_wait_ld()
+__device__ __forceinline__ void tmem_pin4(float* v) {
+  asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]));
+}
+
 // ---- tf32 hi/lo split -----------------------------------------------------------------------
 // hi = round-to-nearest tf32(a) (exactly representable, so the tensor core's own fp32->tf32
 // conversion cannot change it); lo = a - hi is exact in fp32 and has <= 13 significant bits.
 __device__ __forceinline__ float tf32_hi(float a) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
-  return __uint_as_float(r);
+  // == cvt.rna.tf32.f32 (nearest, ties away from zero) for finite inputs, as two integer ops: the cvt
+  // expands to ~5 SASS instructions (inf/nan handling) and the converter warps run it per element.
+  return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
 }
 
 // byte offset of 16-byte chunk `c` (0..7) of row `row` inside a [rows x 128B] SWIZZLE_128B tile
