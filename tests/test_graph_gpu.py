@@ -28,8 +28,9 @@ def test_graphed_step_equals_eager(model_name):
                         channel_wise_stitching=True)
         net.to(dev).to(memory_format=torch.channels_last).train()
         module = MTLModule(net, num_classes=C, device=dev)
-        # plain SGD: Adam turns round-off-sized gradients into +-lr moves, which would hide real errors
-        opt = torch.optim.SGD(module.parameters(), lr=1e-4)  # small: keeps the 6-step trajectories from amplifying round-off
+        # plain SGD with a small step: Adam turns round-off-sized gradients into +-lr moves, and a large
+        # step lets six-step trajectories amplify round-off
+        opt = torch.optim.SGD(module.parameters(), lr=1e-4)
         return net, module, opt
 
     batches = [{k: v.to(dev) for k, v in FX.image_batch(2, 64, 64, C, f"graph/{i}").items()} for i in range(3)]
@@ -37,31 +38,44 @@ def test_graphed_step_equals_eager(model_name):
         b["img"] = b["img"].contiguous(memory_format=torch.channels_last)
 
     # eager: warm-up steps on batch 0 (what GraphedTrainStep does before capturing), then batches 1, 2
-    net_e, mod_e, opt_e = build()
-    losses_e = []
-    for b in [batches[0]] * 4 + batches[1:]:
-        opt_e.zero_grad(set_to_none=True)
-        loss = mod_e.training_step(b, 0)
-        loss.backward()
-        opt_e.step()
-        losses_e.append(loss.item())
-    # graphed: 3 warm-up steps + 1 captured-run step on batch 0 happen inside the constructor/capture? no:
-    # capture does not execute; so: constructor = 3 eager warm-ups, then replays on batch 0, 1, 2
+    def run_eager():
+        net, mod, opt = build()
+        losses = []
+        for b in [batches[0]] * 4 + batches[1:]:
+            opt.zero_grad(set_to_none=True)
+            loss = mod.training_step(b, 0)
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        return net, losses
+
+    def param_diffs(net_a, net_b):
+        rel = []
+        for (k, p), q in zip(net_a.named_parameters(), net_b.parameters()):
+            p, q = p.detach(), q.detach()
+            # zero-initialised biases have moved by ~1e-6 after six lr=1e-4 steps and their gradients are
+            # round-off (they sit before a train-mode BN): measure against max(|p|, 1e-3), not |p|
+            rel.append((float((p - q).abs().max() / p.abs().max().clamp_min(1e-3)), k, float(p.abs().max())))
+        rel.sort()
+        return rel
+
+    net_e, losses_e = run_eager()
+    # the yardstick: a second, identical eager run.  cuDNN's backward kernels are not run-to-run
+    # deterministic, and ReLU / max-pool flips amplify that round-off in a few parameters.
+    net_e2, _ = run_eager()
+    noise = param_diffs(net_e, net_e2)
+
+    # graphed: the constructor runs 3 eager warm-up steps on batch 0 and captures (capture does not
+    # execute), then the replays consume batches 0, 1, 2
     net_g, mod_g, opt_g = build()
     g = GraphedTrainStep(mod_g, opt_g, batches[0], warmup=3)
     losses_g = [g(b).item() for b in batches]
     assert len(mod_g.step_outputs["train"]["loss"]) == 0  # capture leaves no stale records behind
-    # same weights, same batch -> the first replay reproduces the eager loss; afterwards the two runs
-    # drift apart slowly (cuDNN backward kernels use atomics, Adam amplifies the round-off)
-    # (two EAGER runs of this sequence already differ by ~5e-4 after four Adam steps)
+    # same weights, same batch -> the first replay reproduces the eager loss
     for le, lg in zip(losses_e[3:], losses_g):
         assert abs(le - lg) <= 5e-3 * abs(le), (losses_e, losses_g)
-    rel = []
-    for (k, p), q in zip(net_e.named_parameters(), net_g.parameters()):
-        p, q = p.detach(), q.detach()
-        # zero-initialised biases have moved by ~1e-6 after six lr=1e-4 steps and their gradients are
-        # round-off (they sit before a train-mode BN): measure against max(|p|, 1e-3), not |p|
-        rel.append((float((p - q).abs().max() / p.abs().max().clamp_min(1e-3)), k, float(p.abs().max())))
-    rel.sort()
-    assert rel[len(rel) // 2][0] <= 1e-4 and rel[-1][0] <= 1e-3, (rel[len(rel) // 2], rel[-6:])
+    rel = param_diffs(net_e, net_g)
+    med, worst = rel[len(rel) // 2][0], rel[-1][0]
+    assert med <= max(1e-5, 4 * noise[len(noise) // 2][0]), (rel[len(rel) // 2], noise[len(noise) // 2])
+    assert worst <= max(1e-3, 4 * noise[-1][0]), (rel[-4:], noise[-4:])
     assert torch.equal(mod_g.last_confusion.sum(), torch.tensor(2 * 64 * 64, device=dev))

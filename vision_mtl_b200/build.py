@@ -46,6 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    cmd += os.environ.get("VMTL_NVCC_EXTRA", "").split()  # e.g. -DVMTL_HT_PROF for the role-timing probes
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     tmp = LIB_PATH + ".tmp"
     cmd += ["-o", tmp, "-lcuda"]

@@ -11,10 +11,11 @@
 // cycles the tile's 17 KB take at the roofline -- and tcgen05.ld hands every epilogue thread exactly
 // one pixel's logits, which is the shape softmax / argmax / CE want.
 //
-// Roles (22 warps): 0-3 converters (one pixel row per thread: smem -> hi/lo -> TMEM), 4-19 four
-// epilogue groups (group g owns accumulator buffer g = tiles g, g+4, ...; a tile's epilogue is a
-// ~300-instruction dependent chain per warp, so throughput comes from groups in flight),
-// 20 TMA producer, 21 MMA issuer.
+// Roles (27 warps): 0-7 two converter groups (one pixel row per thread: smem -> hi/lo -> TMEM; alternate
+// tiles), 8-23 four epilogue groups (group g owns accumulator buffer g = tiles g, g+4, ...), 24 TMA
+// producer, 25-26 two MMA issuers (alternate tiles).  Every role is a serial chain of ~1-1.6k cycles per
+// tile (mbarrier round trips, 8 blocking MMA issues of ~60 cycles, a ~300-instruction epilogue), against
+// ~750 cycles a tile's bytes take at the HBM roofline -- hence several instances of each role in flight.
 // Feature tile = ONE 128B-swizzled atom of 16 KB; 8 stages -> 128 KB in flight per SM.
 #include <cuda.h>
 #include <math.h>
@@ -26,7 +27,7 @@ namespace vmtl {
 
 using namespace tc;
 
-constexpr int kHtThreads = 22 * 32;
+constexpr int kHtThreads = 27 * 32;
 constexpr int kHtTile = 128;
 constexpr int kHtStages = 8;
 constexpr int kHtStageBytes = kHtTile * 128;  // 16 KB
@@ -64,9 +65,9 @@ static bool ht_make_tmap(CUtensorMap* m, const float* base, int64_t rows) {
 __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
   asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ float fast_exp(float x) {  // ex2.approx: ~2 ulp, inputs here are <= 0
+__device__ __forceinline__ float fast_ex2(float x) {  // ex2.approx: ~2 ulp, inputs here are <= 0
   float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 __device__ __forceinline__ float fast_log(float x) {
@@ -74,6 +75,26 @@ __device__ __forceinline__ float fast_log(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r * 0.6931471805599453f;
 }
+
+#ifdef VMTL_HT_PROF
+__device__ long long g_ht_prof[148][16];
+#define PROF_T0(v) const long long v = clock64()
+#define PROF_ACC(acc, v) acc += clock64() - v
+#define PROF_DECL(...) long long __VA_ARGS__
+#define PROF_OUT(slot, val) if (lane == 0) g_ht_prof[blockIdx.x][slot] = (val)
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PROF_STAMP(slot) if (threadIdx.x == 0) g_ht_prof[blockIdx.x][slot] = gtimer()
+#else
+#define PROF_T0(v)
+#define PROF_ACC(acc, v)
+#define PROF_DECL(...)
+#define PROF_OUT(slot, val)
+#define PROF_STAMP(slot)
+#endif
 
 template <int CPAD>
 __global__ void __launch_bounds__(kHtThreads, 1)
@@ -84,6 +105,7 @@ __global__ void __launch_bounds__(kHtThreads, 1)
   using L = HtSmem;
   constexpr int S = kHtStages;
   extern __shared__ uint8_t smem_raw[];
+  PROF_STAMP(13);
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer (LDS/STS, not generic LD/ST)
   uint8_t* sW = smem + L::kW;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::kMisc);   // full[8] empty[8] aready[4] amma[4] dfull[4] dfree[4]
@@ -97,7 +119,6 @@ __global__ void __launch_bounds__(kHtThreads, 1)
   auto bar_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
   auto bar_empty = [&](int s) { return bar0 + 64u + 8u * (uint32_t)s; };
   auto bar_aready = [&](int b) { return bar0 + 128u + 8u * (uint32_t)b; };
-  auto bar_amma = [&](int b) { return bar0 + 160u + 8u * (uint32_t)b; };
   auto bar_dfull = [&](int b) { return bar0 + 192u + 8u * (uint32_t)b; };
   auto bar_dfree = [&](int b) { return bar0 + 224u + 8u * (uint32_t)b; };
 
@@ -108,14 +129,13 @@ __global__ void __launch_bounds__(kHtThreads, 1)
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(bar_aready(i), 128);
-      mbar_init(bar_amma(i), 1);
       mbar_init(bar_dfull(i), 1);
       mbar_init(bar_dfree(i), 128);
     }
     fence_mbar_init();
   }
-  if (warp == 21) tmem_alloc(smem_u32(s_tmem), 512);
-  if (warp == 20 && lane == 0) tma_prefetch_desc(&tmap_f);
+  if (warp == 25) tmem_alloc(smem_u32(s_tmem), 512);
+  if (warp == 24 && lane == 0) tma_prefetch_desc(&tmap_f);
   for (int i = threadIdx.x; i < 32; i += kHtThreads) s_bias[i] = i < C ? bias[i] : 0.f;
   for (int i = threadIdx.x; i < 32 * 32; i += kHtThreads) s_conf[i] = 0u;
   // stacked W operand: row n (< 32) = W_hi[n], row 32 + n = W_lo[n]; classes >= C are zero rows
@@ -132,27 +152,35 @@ __global__ void __launch_bounds__(kHtThreads, 1)
   tc_fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
   const uint32_t tmem_d0 = tmem_base + 256;
+  PROF_STAMP(14);
 
   const int64_t ntiles = (P + kHtTile - 1) / kHtTile;
   const int64_t nitems = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   double loss_acc = 0.0, n_acc = 0.0;
 
-  if (warp < 4) {
-    // ------------------------------------------------------------------ converters (thread = pixel row)
-    const int row = warp * 32 + lane;
-    for (int64_t it = 0; it < nitems; ++it) {
+  if (warp < 8) {
+    // ------------------------------------------------------------------ converters (thread = pixel row;
+    // two groups of 4 warps take alternate tiles)
+    const int row = (warp & 3) * 32 + lane;
+    PROF_DECL(w_full = 0, w_amma = 0, w_st = 0);
+    PROF_T0(t_begin);
+    for (int64_t it = warp >> 2; it < nitems; it += 2) {
       const int s = (int)(it % S), ab = (int)(it & 3);
+      PROF_T0(t0);
       mbar_wait(bar_full(s), (uint32_t)((it / S) & 1));
+      PROF_ACC(w_full, t0);
       const uint8_t* st = smem + s * kHtStageBytes;
       float4 c[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) c[j] = *reinterpret_cast<const float4*>(st + sw128_off(row, j));
       mbar_arrive(bar_empty(s));
       if (it >= 4) {
-        mbar_wait(bar_amma(ab), (uint32_t)(((it >> 2) - 1) & 1));
+        PROF_T0(t1);
+        mbar_wait(bar_dfull(ab), (uint32_t)(((it >> 2) - 1) & 1));  // tile it-4's MMAs have read this A buffer
+        PROF_ACC(w_amma, t1);
         tc_fence_after_sync();
       }
-      const uint32_t ta = tmem_base + (((uint32_t)warp * 32) << 16) + (uint32_t)(ab * 64);
+      const uint32_t ta = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + (uint32_t)(ab * 64);
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         float hi[16], lo[16];
@@ -166,18 +194,36 @@ __global__ void __launch_bounds__(kHtThreads, 1)
         tmem_st16(ta + g * 16, hi);
         tmem_st16(ta + 32 + g * 16, lo);
       }
+      PROF_T0(t2);
       tmem_wait_st();
+      PROF_ACC(w_st, t2);
       tc_fence_before_sync();
       mbar_arrive(bar_aready(ab));
     }
-  } else if (warp < 20) {
+#ifdef VMTL_HT_PROF
+    if (warp == 0) {
+      PROF_OUT(0, clock64() - t_begin);
+      PROF_OUT(1, w_full);
+      PROF_OUT(2, w_amma);
+      PROF_OUT(3, w_st);
+    }
+#endif
+  } else if (warp < 24) {
     // ------------------------------------------------------------------ epilogue groups (tile it -> group it % 4)
-    const int g = (warp - 4) >> 2, quad = warp & 3;
+    const int g = (warp - 8) >> 2, quad = warp & 3;
     const uint32_t taddr = tmem_d0 + (((uint32_t)quad * 32) << 16) + (uint32_t)(g * 64);
+    PROF_DECL(w_dfull = 0);
+    PROF_T0(t_begin);
+    auto pixel_of = [&](int64_t it) { return (blockIdx.x + it * gridDim.x) * kHtTile + quad * 32 + lane; };
+    // the label is fetched one tile ahead: its DRAM latency would otherwise sit in this group's serial chain
+    int64_t t_next = (g < nitems && pixel_of(g) < P) ? __ldg(target + pixel_of(g)) : ignore_index;
     for (int64_t it = g; it < nitems; it += 4) {
-      const int64_t p = (blockIdx.x + it * gridDim.x) * kHtTile + quad * 32 + lane;
-      const int64_t t = p < P ? __ldg(target + p) : ignore_index;  // in flight while the MMAs finish
+      const int64_t p = pixel_of(it);
+      const int64_t t = t_next;
+      t_next = (it + 4 < nitems && pixel_of(it + 4) < P) ? __ldg(target + pixel_of(it + 4)) : ignore_index;
+      PROF_T0(t0);
       mbar_wait(bar_dfull(g), (uint32_t)((it >> 2) & 1));
+      PROF_ACC(w_dfull, t0);
       tc_fence_after_sync();
       float l[CPAD], l2[CPAD];
       tmem_ld16_nowait(taddr, l);            // A_hi W_hi + A_lo W_hi
@@ -199,21 +245,34 @@ __global__ void __launch_bounds__(kHtThreads, 1)
       mbar_arrive(bar_dfree(g));
 #pragma unroll
       for (int c = 0; c < CPAD; ++c) l[c] = l[c] + l2[c] + s_bias[c];
+      // classes >= C exist only in the last few columns of a CPAD bucket (16: C<=16, 20: 17..20, 32: 21..32)
+      constexpr int CMIN = CPAD == 16 ? 1 : (CPAD == 20 ? 17 : 21);
+#pragma unroll
+      for (int c = CMIN; c < CPAD; ++c) l[c] = c < C ? l[c] : -INFINITY;
       float m = l[0];
       int arg = 0;
 #pragma unroll
       for (int c = 1; c < CPAD; ++c)
-        if ((CPAD == C || c < C) && l[c] > m) {
+        if (l[c] > m) {
           m = l[c];
           arg = c;
         }
-      float sum = 0.f, lt = 0.f;
-      const int ti = (int)t;
+      constexpr float kLog2e = 1.4426950408889634f;
+      const float mneg = -m * kLog2e;
+      float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < CPAD; ++c) {
-        const float e = fast_exp(l[c] - m);
-        sum += (CPAD == C || c < C) ? e : 0.f;
-        lt += (c == ti) ? l[c] : 0.f;
+      for (int c = 0; c < CPAD; ++c) sum += fast_ex2(fmaf(l[c], kLog2e, mneg));
+      // l[target]: two-level select (3 per group of 4 + 2 per group) instead of a compare per class
+      const int ti = (int)t;
+      const bool q1 = (ti & 3) == 1, q2 = (ti & 3) == 2, q3 = (ti & 3) == 3;
+      float lt = 0.f;
+#pragma unroll
+      for (int gq = 0; gq < CPAD / 4; ++gq) {
+        float v = l[4 * gq];
+        v = q1 ? l[4 * gq + 1] : v;
+        v = q2 ? l[4 * gq + 2] : v;
+        v = q3 ? l[4 * gq + 3] : v;
+        lt = (ti >> 2) == gq ? v : lt;
       }
       if (p < P) {
         if (pred) pred[p] = (uint8_t)arg;
@@ -224,28 +283,47 @@ __global__ void __launch_bounds__(kHtThreads, 1)
         }
       }
     }
-  } else if (warp == 20) {
+#ifdef VMTL_HT_PROF
+    if (warp == 8) {
+      PROF_OUT(4, clock64() - t_begin);
+      PROF_OUT(5, w_dfull);
+    }
+#endif
+  } else if (warp == 24) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      PROF_DECL(w_empty = 0);
+      PROF_T0(t_begin);
       for (int64_t it = 0; it < nitems; ++it) {
         const int s = (int)(it % S);
+        PROF_T0(t0);
         if (it >= S) mbar_wait(bar_empty(s), (uint32_t)(((it / S) - 1) & 1));
+        PROF_ACC(w_empty, t0);
         mbar_expect_tx(bar_full(s), (uint32_t)kHtStageBytes);
         tma_load_2d(smem_u32(smem + s * kHtStageBytes), &tmap_f, 0, (int)((blockIdx.x + it * gridDim.x) * kHtTile),
                     bar_full(s));
       }
+      PROF_OUT(6, clock64() - t_begin);
+      PROF_OUT(7, w_empty);
     }
   } else if (lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_wide = idesc_tf32(kHtTile, 64, 0, 0);
     constexpr uint32_t idesc_n = idesc_tf32(kHtTile, 32, 0, 0);
     const uint32_t bW = smem_u32(sW);
-    for (int64_t it = 0; it < nitems; ++it) {
+    PROF_DECL(w_aready = 0, w_dfree = 0, w_issue = 0, w_commit = 0);
+    PROF_T0(t_begin);
+    for (int64_t it = warp - 25; it < nitems; it += 2) {
       const int ab = (int)(it & 3);
+      PROF_T0(t0);
       mbar_wait(bar_aready(ab), (uint32_t)((it >> 2) & 1));
+      PROF_ACC(w_aready, t0);
+      PROF_T0(t1);
       if (it >= 4) mbar_wait(bar_dfree(ab), (uint32_t)(((it >> 2) - 1) & 1));
+      PROF_ACC(w_dfree, t1);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_d0 + (uint32_t)(ab * 64);
+      PROF_T0(t2);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const uint32_t a_hi = tmem_base + (uint32_t)(ab * 64 + ks * 8);
@@ -253,13 +331,21 @@ __global__ void __launch_bounds__(kHtThreads, 1)
         mma_tf32_ts(d_tmem, a_hi, dB, idesc_wide, ks != 0);
         mma_tf32_ts(d_tmem, a_hi + 32, dB, idesc_n, 1);
       }
-      mma_commit(bar_amma(ab));
+      PROF_ACC(w_issue, t2);
+      PROF_T0(t3);
       mma_commit(bar_dfull(ab));
+      PROF_ACC(w_commit, t3);
     }
+    PROF_OUT(11, w_issue);
+    PROF_OUT(12, w_commit);
+    PROF_OUT(8, clock64() - t_begin);
+    PROF_OUT(9, w_aready);
+    PROF_OUT(10, w_dfree);
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 21) tmem_dealloc(tmem_base, 512);
+  PROF_STAMP(15);
+  if (warp == 25) tmem_dealloc(tmem_base, 512);
   if (conf)
     for (int i = threadIdx.x; i < C * C; i += kHtThreads) {
       const unsigned int v = s_conf[i];
@@ -268,9 +354,9 @@ __global__ void __launch_bounds__(kHtThreads, 1)
   // (loss sum, valid count) partial of this CTA: the 16 epilogue warps in fixed order
   loss_acc = warp_sum(loss_acc);
   n_acc = warp_sum(n_acc);
-  if (warp >= 4 && warp < 20 && lane == 0) {
-    s_part[warp - 4][0] = loss_acc;
-    s_part[warp - 4][1] = n_acc;
+  if (warp >= 8 && warp < 24 && lane == 0) {
+    s_part[warp - 8][0] = loss_acc;
+    s_part[warp - 8][1] = n_acc;
   }
   __syncthreads();
   if (threadIdx.x < 2) {
@@ -278,6 +364,10 @@ __global__ void __launch_bounds__(kHtThreads, 1)
     for (int w = 0; w < 16; ++w) s += s_part[w][threadIdx.x];
     partial[(int64_t)blockIdx.x * 2 + threadIdx.x] = s;
   }
+#ifdef VMTL_HT_PROF
+  __syncthreads();
+  if (threadIdx.x == 0) g_ht_prof[blockIdx.x][3] = gtimer();
+#endif
 }
 
 int head_ce_tc_fwd(const float* feat, const float* W, const float* b, const int64_t* target, int64_t P, int C,
@@ -310,3 +400,9 @@ int head_ce_tc_fwd(const float* feat, const float* W, const float* b, const int6
 }
 
 }  // namespace vmtl
+
+#ifdef VMTL_HT_PROF
+extern "C" int vmtl_debug_head_prof(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, vmtl::g_ht_prof, sizeof(long long) * 148 * 16) == cudaSuccess ? 0 : 1;
+}
+#endif
