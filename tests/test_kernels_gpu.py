@@ -267,7 +267,8 @@ def test_head_silog(B, H, W, cin):
 
 
 # ----------------------------------------------------------------------------- MTAN gate
-GATE_SHAPES = [(2, 32, 16, 24), (1, 64, 9, 13), (2, 128, 8, 8), (1, 256, 4, 8), (4, 32, 64, 64)]
+GATE_SHAPES = [(2, 32, 16, 24), (1, 64, 9, 13), (2, 128, 8, 8), (1, 256, 4, 8), (4, 32, 64, 64),
+               (3, 128, 20, 24), (2, 256, 12, 10), (1, 192, 16, 20)]
 
 
 def _gate_case(B, N, H, W, seed=11):

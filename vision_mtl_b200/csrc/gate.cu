@@ -102,8 +102,7 @@ __global__ void gate_fwd_stats_finalize(const float* __restrict__ partial, int n
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double s = 0.0, q = 0.0;
   if (training) {  // block-uniform branch: the reduction synchronises
-    s = block_colsum(partial, nparts, 2 * (int64_t)N, c < N ? c : 0, c < N);
-    q = block_colsum(partial, nparts, 2 * (int64_t)N, N + (c < N ? c : 0), c < N);
+    block_colsum2(partial, nparts, 2 * (int64_t)N, c < N ? c : 0, N + (c < N ? c : 0), c < N, &s, &q);
   }
   if (threadIdx.x >= 32 || c >= N) return;
   double mean, var;
@@ -193,8 +192,8 @@ __global__ void gate_bwd_stats_finalize(const float* __restrict__ partial, int n
                                         float* __restrict__ dbeta, float* __restrict__ c1,
                                         float* __restrict__ c2) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const double sb = block_colsum(partial, nparts, 2 * (int64_t)N, c < N ? c : 0, c < N);
-  const double sg = block_colsum(partial, nparts, 2 * (int64_t)N, N + (c < N ? c : 0), c < N);
+  double sb, sg;
+  block_colsum2(partial, nparts, 2 * (int64_t)N, c < N ? c : 0, N + (c < N ? c : 0), c < N, &sb, &sg);
   if (threadIdx.x >= 32 || c >= N) return;
   dbeta[c] = (float)sb;
   dgamma[c] = (float)sg;

@@ -740,7 +740,7 @@ int gate_tc_bwd_gemm(const float* dy, const float* h, const float* s, const floa
                      float* dh, float* dw_partial, int slots, int* nslots, float* db_partial,
                      cudaStream_t st) {
   (void)gamma;
-  if (K != 128 || (N != 32 && N != 64) || !ws.dz) return VMTL_EUNSUPPORTED;
+  if (K != 128 || (N != 32 && N % 64 != 0) || N > 1024 || !ws.dz) return VMTL_EUNSUPPORTED;
   const int grid = tc_grid(M);
   if (grid > slots || grid > ws.partial_rows) return VMTL_EWORKSPACE;
   *nslots = grid;
@@ -748,12 +748,14 @@ int gate_tc_bwd_gemm(const float* dy, const float* h, const float* s, const floa
     const char* e = getenv("VMTL_GATE_BWD");
     return !(e && e[0] == 'b');
   }();
-  if (use_tma) {
-    if (N == 32)
-      return split3 ? launch_bwd_tma<1, true>(dy, h, s, z, W, ws, M, dh, dw_partial, db_partial, grid, st)
-                    : launch_bwd_tma<1, false>(dy, h, s, z, W, ws, M, dh, dw_partial, db_partial, grid, st);
-    return split3 ? launch_bwd_tma<2, true>(dy, h, s, z, W, ws, M, dh, dw_partial, db_partial, grid, st)
-                  : launch_bwd_tma<2, false>(dy, h, s, z, W, ws, M, dh, dw_partial, db_partial, grid, st);
+  if (use_tma || N > 64) {
+#define VMTL_BWD_TMA(NDH, NDW)                                                                                   \
+  (split3 ? launch_bwd_tma<NDH, NDW, true>(dy, h, s, z, W, ws, M, N, dh, dw_partial, db_partial, grid, st)       \
+          : launch_bwd_tma<NDH, NDW, false>(dy, h, s, z, W, ws, M, N, dh, dw_partial, db_partial, grid, st))
+    if (N == 32) return VMTL_BWD_TMA(1, 1);
+    if (N % 128 == 0) return VMTL_BWD_TMA(2, 4);
+    return VMTL_BWD_TMA(2, 2);
+#undef VMTL_BWD_TMA
   }
   if (N == 32)
     return split3 ? launch_bwd<1, true>(dy, h, s, z, W, ws, M, dh, dw_partial, db_partial, grid, st)

@@ -1,4 +1,4 @@
-// MTAN gate backward, phase B on tensor cores, TMA generation (K = 128, N in {32, 64}).
+// MTAN gate backward, phase B on tensor cores, TMA generation (K = 128, N = 32 or a multiple of 64).
 // Included by gate_tc.cu.  Same machinery as gate_tc_tma.cuh: raw fp32 tiles arrive in shared memory
 // by TMA (>= 128 KB per SM in flight), the tf32 hi/lo A operand lives in TENSOR MEMORY.
 //
@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
                           const float* __restrict__ mean, const float* __restrict__ invstd,
                           const float* __restrict__ c1, const float* __restrict__ c2, int64_t M,
                           const __grid_constant__ CUtensorMap tmap_dzh_st, const __grid_constant__ CUtensorMap tmap_dzl_st,
-                          float* __restrict__ dh, float* __restrict__ db_partial /* [grid][N] */) {
+                          float* __restrict__ dh, float* __restrict__ db_partial /* [grid][n_total] */,
+                          int n0 /* first gate column of this pass */, int n_total, int accumulate /* dh += */) {
   using namespace tc;
   using L = DhTmaSmem<NA>;
   constexpr int S = L::kStages;
@@ -87,17 +88,17 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     tma_prefetch_desc(&tmap_z);
   }
   for (int i = threadIdx.x; i < N; i += kTmaThreads) {
-    s_coef[0 * 64 + i] = coefA[i];
-    s_coef[1 * 64 + i] = coefB[i];
-    s_coef[2 * 64 + i] = mean[i];
-    s_coef[3 * 64 + i] = invstd[i];
-    s_coef[4 * 64 + i] = c1[i];
-    s_coef[5 * 64 + i] = c2[i];
+    s_coef[0 * 64 + i] = coefA[n0 + i];
+    s_coef[1 * 64 + i] = coefB[n0 + i];
+    s_coef[2 * 64 + i] = mean[n0 + i];
+    s_coef[3 * 64 + i] = invstd[n0 + i];
+    s_coef[4 * 64 + i] = c1[n0 + i];
+    s_coef[5 * 64 + i] = c2[n0 + i];
   }
   if (warp < 8) {  // W^T operand: element (k, n) = W[n][k]; rows k, K-major along n, atom = n / 32
     for (int e = threadIdx.x; e < N * KH; e += 256) {
       const int n = e / KH, k = e - n * KH;
-      const float w = W[e];
+      const float w = W[(int64_t)n0 * KH + e];
       const float hi = tf32_hi(w);
       const uint32_t off = (uint32_t)((n >> 5) * L::kSlot) + sw128_off(k, (n & 31) >> 2) + (uint32_t)((n & 3) << 2);
       *reinterpret_cast<float*>(sBhi + off) = hi;
@@ -225,7 +226,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       if (threadIdx.x == 8 * 32 && dh) {
         const int row0 = (int)((blockIdx.x + it * gridDim.x) * kTileM);
 #pragma unroll
-        for (int a = 0; a < 4; ++a) tma_store_2d(&tmap_dh, a * 32, row0, smem_u32(smem + L::kOut + a * L::kSlot));
+        for (int a = 0; a < 4; ++a) {
+          if (accumulate)  // later column passes add their share of dh in L2 (TMA reduce), no read-back
+            tma_reduce_add_2d(&tmap_dh, a * 32, row0, smem_u32(smem + L::kOut + a * L::kSlot));
+          else
+            tma_store_2d(&tmap_dh, a * 32, row0, smem_u32(smem + L::kOut + a * L::kSlot));
+        }
         tma_store_commit();
       }
       (void)grow;
@@ -243,16 +249,16 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
             mbar_wait(bar_empty(s), (uint32_t)(((u / S) - 1) & 1));
             const int64_t v = u - S;
             const int vrow0 = (int)((blockIdx.x + (v / NA) * gridDim.x) * kTileM), va = (int)(v % NA);
-            tma_store_2d(&tmap_dzh_st, va * 32, vrow0, smem_u32(smem + s * L::kStage));
-            tma_store_2d(&tmap_dzl_st, va * 32, vrow0, smem_u32(smem + s * L::kStage + L::kSlot));
+            tma_store_2d(&tmap_dzh_st, n0 + va * 32, vrow0, smem_u32(smem + s * L::kStage));
+            tma_store_2d(&tmap_dzl_st, n0 + va * 32, vrow0, smem_u32(smem + s * L::kStage + L::kSlot));
             tma_store_commit();
             tma_store_wait_read();
           }
           mbar_expect_tx(bar_full(s), (uint32_t)L::kStage);
           const uint32_t dst = smem_u32(smem + s * L::kStage);
-          tma_load_2d(dst, &tmap_dy, a * 32, row0, bar_full(s));
-          tma_load_2d(dst + L::kSlot, &tmap_s, a * 32, row0, bar_full(s));
-          tma_load_2d(dst + 2 * L::kSlot, &tmap_z, a * 32, row0, bar_full(s));
+          tma_load_2d(dst, &tmap_dy, n0 + a * 32, row0, bar_full(s));
+          tma_load_2d(dst + L::kSlot, &tmap_s, n0 + a * 32, row0, bar_full(s));
+          tma_load_2d(dst + 2 * L::kSlot, &tmap_z, n0 + a * 32, row0, bar_full(s));
         }
       }
       const int64_t nunits = nitems * NA;  // drain: the last min(S, nunits) units are still staged
@@ -260,8 +266,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         const int s = (int)(v % S);
         mbar_wait(bar_empty(s), (uint32_t)((v / S) & 1));
         const int vrow0 = (int)((blockIdx.x + (v / NA) * gridDim.x) * kTileM), va = (int)(v % NA);
-        tma_store_2d(&tmap_dzh_st, va * 32, vrow0, smem_u32(smem + s * L::kStage));
-        tma_store_2d(&tmap_dzl_st, va * 32, vrow0, smem_u32(smem + s * L::kStage + L::kSlot));
+        tma_store_2d(&tmap_dzh_st, n0 + va * 32, vrow0, smem_u32(smem + s * L::kStage));
+        tma_store_2d(&tmap_dzl_st, n0 + va * 32, vrow0, smem_u32(smem + s * L::kStage + L::kSlot));
         tma_store_commit();
       }
       tma_store_wait_all();
@@ -310,7 +316,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     float acc = 0.f;
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc += s_red[((ch * 4 + q) * NA + a) * 16 + l];
-    db_partial[(int64_t)blockIdx.x * N + col] = acc;
+    db_partial[(int64_t)blockIdx.x * n_total + n0 + col] = acc;
   }
 }
 
@@ -323,7 +329,7 @@ struct DwTmaSmem {
   static constexpr int kSlotD = kHalfRows * 128;             // one 32-column atom of a dz half, MN-major
   static constexpr int kStageD = 2 * NA * kSlotD;            // atoms [hi_0.. hi_NA-1, lo_0.. lo_NA-1]
   static constexpr int kStage = kStageH + kStageD;           // 48 KB (N=32) / 64 KB (N=64)
-  static constexpr int kStages = NA == 1 ? 4 : 3;
+  static constexpr int kStages = NA == 1 ? 4 : (NA == 2 ? 3 : 2);  // 48 / 64 / 96 KB per stage
   static constexpr int kMisc = kStages * kStage;
   static constexpr int kBytes = kMisc + 256 + 1024;
 };
@@ -333,7 +339,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     gate_tc_dw_tma_kernel(const __grid_constant__ CUtensorMap tmap_h /* box [32 x 64], SW128 */,
                           const __grid_constant__ CUtensorMap tmap_dzh /* box [32 x 64], SW128_ATOM_32B */,
                           const __grid_constant__ CUtensorMap tmap_dzl, int64_t M,
-                          float* __restrict__ dw_partial /* [grid][N][128] */) {
+                          float* __restrict__ dw_partial /* [grid][n_total][128] */, int n0, int n_total) {
   using namespace tc;
   using L = DwTmaSmem<NA>;
   constexpr int S = L::kStages;
@@ -428,8 +434,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         for (int a = 0; a < 4; ++a) tma_load_2d(dst + a * L::kSlotH, &tmap_h, a * 32, row0, bar_full(s));
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
-          tma_load_2d(dst + L::kStageH + a * L::kSlotD, &tmap_dzh, a * 32, row0, bar_full(s));
-          if (SPLIT) tma_load_2d(dst + L::kStageH + (NA + a) * L::kSlotD, &tmap_dzl, a * 32, row0, bar_full(s));
+          tma_load_2d(dst + L::kStageH + a * L::kSlotD, &tmap_dzh, n0 + a * 32, row0, bar_full(s));
+          if (SPLIT) tma_load_2d(dst + L::kStageH + (NA + a) * L::kSlotD, &tmap_dzl, n0 + a * 32, row0, bar_full(s));
         }
       }
     }
@@ -456,7 +462,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   // warps 8-15 have no per-unit work in this kernel: they only help drain the accumulator
   tc_fence_before_sync();
   __syncthreads();
-  float* out = dw_partial + (int64_t)blockIdx.x * N * KH;
+  float* out = dw_partial + ((int64_t)blockIdx.x * n_total + n0) * KH;
   if (nunits > 0) {
     if (warp == 17 && lane == 0) {  // wait for the last unit's MMAs
       const int64_t ul = nunits - 1;
@@ -507,11 +513,14 @@ inline bool make_tmap_2d_sw(CUtensorMap* m, const float* base, int64_t rows, int
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int NA, bool SPLIT>
+// N = any multiple of 64 (or 32): dh runs in column passes of NA_DH*32 gate columns (W^T hi/lo, the
+// stages and the dh staging fill the 227 KB of shared memory at 64 columns), passes after the first
+// accumulate into dh with TMA reduce-adds; dW runs in passes of NA_DW*32 columns (2*NA_DW*32 accumulator
+// columns in TMEM), each pass re-reading h.
+template <int NA_DH, int NA_DW, bool SPLIT>
 static int launch_bwd_tma(const float* dy, const float* h, const float* s, const float* z, const float* W,
-                          const GateWs& ws, int64_t M, float* dh, float* dw_partial, float* db_partial, int grid,
-                          cudaStream_t st) {
-  constexpr int N = NA * 32;
+                          const GateWs& ws, int64_t M, int N, float* dh, float* dw_partial, float* db_partial,
+                          int grid, cudaStream_t st) {
   float* dz_hi = ws.dz;
   float* dz_lo = ws.dz + (size_t)M * N;
   CUtensorMap t_dy, t_s, t_z, t_h, t_dzh, t_dzl, t_dh, t_dzh_st, t_dzl_st;
@@ -521,17 +530,24 @@ static int launch_bwd_tma(const float* dy, const float* h, const float* s, const
       !make_tmap_2d_sw(&t_dh, dh ? dh : h, M, 128, kTileM, false) ||
       !make_tmap_2d_sw(&t_dzh_st, dz_hi, M, N, kTileM, false) || !make_tmap_2d_sw(&t_dzl_st, dz_lo, M, N, kTileM, false))
     return VMTL_ECUDA;
-  auto k1 = gate_tc_dh_tma_kernel<NA, SPLIT>;
-  auto k2 = gate_tc_dw_tma_kernel<NA, SPLIT>;
-  if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, DhTmaSmem<NA>::kBytes) != cudaSuccess ||
-      cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, DwTmaSmem<NA>::kBytes) != cudaSuccess)
+  auto k1 = gate_tc_dh_tma_kernel<NA_DH, SPLIT>;
+  auto k2 = gate_tc_dw_tma_kernel<NA_DW, SPLIT>;
+  if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, DhTmaSmem<NA_DH>::kBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, DwTmaSmem<NA_DW>::kBytes) != cudaSuccess)
     return VMTL_ECUDA;
-  k1<<<grid, kTmaThreads, DhTmaSmem<NA>::kBytes, st>>>(t_dy, t_s, t_z, t_dh, W, ws.coefA, ws.coefB, ws.mean, ws.invstd,
-                                                        ws.c1, ws.c2, M, t_dzh_st, t_dzl_st, dh, db_partial);
-  int rc = launch_status();
-  if (rc != VMTL_OK) return rc;
-  k2<<<grid, kTmaThreads, DwTmaSmem<NA>::kBytes, st>>>(t_h, t_dzh, t_dzl, M, dw_partial);
-  return launch_status();
+  for (int n0 = 0; n0 < N; n0 += NA_DH * 32) {
+    k1<<<grid, kTmaThreads, DhTmaSmem<NA_DH>::kBytes, st>>>(t_dy, t_s, t_z, t_dh, W, ws.coefA, ws.coefB, ws.mean,
+                                                             ws.invstd, ws.c1, ws.c2, M, t_dzh_st, t_dzl_st, dh,
+                                                             db_partial, n0, N, n0 != 0);
+    const int rc = launch_status();
+    if (rc != VMTL_OK) return rc;
+  }
+  for (int n0 = 0; n0 < N; n0 += NA_DW * 32) {
+    k2<<<grid, kTmaThreads, DwTmaSmem<NA_DW>::kBytes, st>>>(t_h, t_dzh, t_dzl, M, dw_partial, n0, N);
+    const int rc = launch_status();
+    if (rc != VMTL_OK) return rc;
+  }
+  return VMTL_OK;
 }
 
 }  // namespace vmtl

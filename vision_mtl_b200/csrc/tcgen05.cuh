@@ -165,6 +165,12 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, int x, int y, uin
                "r"(smem_src), "r"(x), "r"(y)
                : "memory");
 }
+// same, but the tile is ADDED to global memory (fp32 reduction performed at L2)
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, int x, int y, uint32_t smem_src) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
+               "r"(smem_src), "r"(x), "r"(y)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed stores have finished READING shared memory (the staging buffer may be rewritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

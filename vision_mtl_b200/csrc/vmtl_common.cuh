@@ -81,12 +81,13 @@ __device__ __forceinline__ double block_colsum(const T* __restrict__ partial, in
   double s = 0.0;
   if (valid) {
     int k = ly;
-    for (; k + 96 < nparts; k += 128) {  // 4 independent loads in flight
-      const double a = (double)partial[(int64_t)k * rowlen + col];
-      const double b = (double)partial[(int64_t)(k + 32) * rowlen + col];
-      const double c = (double)partial[(int64_t)(k + 64) * rowlen + col];
-      const double d = (double)partial[(int64_t)(k + 96) * rowlen + col];
-      s += (a + b) + (c + d);
+    // the kernel is one dependent-latency chain per thread: keep 8 independent loads in flight
+    for (; k + 224 < nparts; k += 256) {
+      T v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = partial[(int64_t)(k + 32 * q) * rowlen + col];
+      s += (((double)v[0] + (double)v[1]) + ((double)v[2] + (double)v[3])) +
+           (((double)v[4] + (double)v[5]) + ((double)v[6] + (double)v[7]));
     }
     for (; k < nparts; k += 32) s += (double)partial[(int64_t)k * rowlen + col];
   }
@@ -99,6 +100,47 @@ __device__ __forceinline__ double block_colsum(const T* __restrict__ partial, in
   }
   __syncthreads();
   return t;
+}
+
+// Two columns of the same partial matrix at once (their loads overlap instead of running back to back).
+template <typename T>
+__device__ __forceinline__ void block_colsum2(const T* __restrict__ partial, int nparts, int64_t rowlen,
+                                              int64_t col_a, int64_t col_b, bool valid, double* out_a,
+                                              double* out_b) {
+  __shared__ double s_sub2[2][32][33];
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  double sa = 0.0, sb = 0.0;
+  if (valid) {
+    int k = ly;
+    for (; k + 96 < nparts; k += 128) {
+      T va[4], vb[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        va[q] = partial[(int64_t)(k + 32 * q) * rowlen + col_a];
+        vb[q] = partial[(int64_t)(k + 32 * q) * rowlen + col_b];
+      }
+      sa += ((double)va[0] + (double)va[1]) + ((double)va[2] + (double)va[3]);
+      sb += ((double)vb[0] + (double)vb[1]) + ((double)vb[2] + (double)vb[3]);
+    }
+    for (; k < nparts; k += 32) {
+      sa += (double)partial[(int64_t)k * rowlen + col_a];
+      sb += (double)partial[(int64_t)k * rowlen + col_b];
+    }
+  }
+  s_sub2[0][ly][lx] = sa;
+  s_sub2[1][ly][lx] = sb;
+  __syncthreads();
+  double ta = 0.0, tb = 0.0;
+  if (ly == 0) {
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      ta += s_sub2[0][q][lx];
+      tb += s_sub2[1][q][lx];
+    }
+  }
+  __syncthreads();
+  *out_a = ta;
+  *out_b = tb;
 }
 
 __device__ __forceinline__ float sigmoidf_acc(float u) {
