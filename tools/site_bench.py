@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--once", action="store_true", help="one un-timed pass (ncu target)")
     ap.add_argument("--precision", default="tc_3xtf32")
     ap.add_argument("--json", default="")
+    ap.add_argument("--profile-set", action="store_true",
+                    help="only the largest gate site, the largest cross-stitch site and the heads (ncu --set full target)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
@@ -74,7 +76,7 @@ def main():
                 print(f"{name + '_' + tag:18s} {site:22s} {ms * 1e3:9.1f} us {nb / 1e6:9.1f} MB {gbps:8.1f} GB/s  {gbps / pk:5.3f}")
 
     if args.only in ("", "gate"):
-        for site, N, down in GATE_SITES:
+        for site, N, down in (GATE_SITES[:1] if args.profile_set else GATE_SITES):
             h, w = H // down, W // down
             M = B * h * w
             hh = torch.relu(cl(B, 128, h, w)).requires_grad_(True)
@@ -93,7 +95,7 @@ def main():
             timed("gate", f"{site} N={N} M={M}", 4 * M * (128 + 4 * N), 4 * M * (2 * 128 + 7 * N), fwd, bwd)
 
     if args.only in ("", "xstitch"):
-        for Cc, h, w in XS_SITES:
+        for Cc, h, w in (XS_SITES[-1:] if args.profile_set else XS_SITES):
             xs = [cl(B, Cc, h, w).requires_grad_(True) for _ in range(2)]
             alpha = torch.rand(2, 2, Cc, device=dev, requires_grad=True)
             dys = [cl(B, Cc, h, w) for _ in range(2)]
