@@ -40,34 +40,55 @@ static int loss_max_blocks() { return sm_count() * 8; }
 // ---------------------------------------------------------------------------------------
 // per-pixel softmax cross-entropy on a register-resident logit vector
 // ---------------------------------------------------------------------------------------
+// cpad_for() buckets: CPAD 16 <- C in [1,16], 20 <- [17,20], 32 <- [21,32]: classes below kCmin<CPAD> exist
+// for every C of the bucket, so only the last few columns need a run-time `c < C` test.
+template <int CPAD>
+constexpr int kCmin = CPAD == 16 ? 1 : (CPAD == 20 ? 17 : 21);
+#define VMTL_HAS_CLASS(c, C) ((c) < kCmin<CPAD> || (c) < (C))
+
 template <int CPAD>
 struct PixelCE {
-  float lse;
+  float lse;    // log-sum-exp of the C logits
+  float mneg;   // -max * log2(e)
+  float inv_s;  // 1 / sum_c exp(l_c - max)
   int arg;
-  __device__ __forceinline__ void run(const float (&l)[CPAD], int C) {
+  // l[c] for c >= C is overwritten with -inf (its probability is then exactly 0)
+  __device__ __forceinline__ void run(float (&l)[CPAD], int C) {
+#pragma unroll
+    for (int c = kCmin<CPAD>; c < CPAD; ++c) l[c] = c < C ? l[c] : -INFINITY;
     float m = l[0];
     arg = 0;
 #pragma unroll
     for (int c = 1; c < CPAD; ++c)
-      if (c < C && l[c] > m) {
+      if (l[c] > m) {
         m = l[c];
         arg = c;
       }
+    mneg = -m * kLog2e;
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < CPAD; ++c)
-      if (c < C) s += expf(l[c] - m);
-    lse = m + logf(s);
+    for (int c = 0; c < CPAD; ++c) s += fast_ex2(fmaf(l[c], kLog2e, mneg));
+    lse = fmaf(fast_lg2(s), kLn2, m);
+    inv_s = __fdividef(1.f, s);
   }
+  // softmax probability of a class with logit lc
+  __device__ __forceinline__ float prob(float lc) const { return fast_ex2(fmaf(lc, kLog2e, mneg)) * inv_s; }
 };
 
+// l[t] without a compare per class: select inside groups of 4 by t % 4, then the group by t / 4
 template <int CPAD>
 __device__ __forceinline__ float pick(const float (&l)[CPAD], int t) {
-  float v = 0.f;
+  const bool q1 = (t & 3) == 1, q2 = (t & 3) == 2, q3 = (t & 3) == 3;
+  float r = 0.f;
 #pragma unroll
-  for (int c = 0; c < CPAD; ++c)
-    if (c == t) v = l[c];
-  return v;
+  for (int g = 0; g < CPAD / 4; ++g) {
+    float v = l[4 * g];
+    v = q1 ? l[4 * g + 1] : v;
+    v = q2 ? l[4 * g + 2] : v;
+    v = q3 ? l[4 * g + 3] : v;
+    r = (t >> 2) == g ? v : r;
+  }
+  return r;
 }
 
 __device__ __forceinline__ bool target_valid(int64_t t, int C, int64_t ignore_index) {
@@ -257,7 +278,7 @@ __global__ void __launch_bounds__(kLossThreads)
 #pragma unroll
       for (int c = 0; c < CPAD; ++c) {
         float d = 0.f;
-        if (valid && c < C) d = (expf(l[c] - ce.lse) - (c == (int)t ? 1.f : 0.f)) * scale;
+        if (valid) d = (ce.prob(l[c]) - (c == (int)t ? 1.f : 0.f)) * scale;
         l[c] = d;
       }
     } else {
@@ -357,6 +378,17 @@ __global__ void head_ce_bwd_finalize(const float* __restrict__ partial, int nblo
 // NHWC: the [256 x C] tile is contiguous; it is staged through shared memory (odd row
 // stride) so global accesses stay 128-bit and coalesced.
 // ---------------------------------------------------------------------------------------
+// element offset of (pixel p, class 0) in a [B, C, HW] tensor; 32-bit division whenever the pixel index fits
+__device__ __forceinline__ int64_t nchw_offset(int64_t p, int64_t HW, int C) {
+  if (p <= 0xffffffffll && HW <= 0xffffffffll) {
+    const uint32_t bi = (uint32_t)p / (uint32_t)HW;
+    const uint32_t hw = (uint32_t)p - bi * (uint32_t)HW;
+    return (int64_t)bi * C * HW + hw;
+  }
+  const int64_t bi = p / HW;
+  return bi * C * HW + (p - bi * HW);
+}
+
 template <int CPAD, bool NHWC>
 __device__ __forceinline__ void load_logits_tile(const float* __restrict__ logits, int64_t p0, int npx,
                                                  int64_t HW, int C, float* s_l, int CS,
@@ -365,10 +397,11 @@ __device__ __forceinline__ void load_logits_tile(const float* __restrict__ logit
     const int n = npx * C;
     const float* src = logits + p0 * C;  // 16B aligned: p0 is a multiple of 256
     const int n4 = n >> 2;
+    const uint32_t cmagic = 0xffffffffu / (uint32_t)C + 1u;  // idx / C == umulhi(idx, cmagic) for idx < 2^27
     for (int q = threadIdx.x; q < n4; q += kLossThreads) {
       const float4 v = ldg_stream(reinterpret_cast<const float4*>(src) + q);
       int idx = q * 4;
-      int r = idx / C, c = idx - r * C;
+      int r = (int)__umulhi((uint32_t)idx, cmagic), c = idx - r * C;
       const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -386,15 +419,13 @@ __device__ __forceinline__ void load_logits_tile(const float* __restrict__ logit
     __syncthreads();
     if ((int)threadIdx.x < npx) {
 #pragma unroll
-      for (int c = 0; c < CPAD; ++c) l[c] = c < C ? s_l[threadIdx.x * CS + c] : 0.f;
+      for (int c = 0; c < CPAD; ++c) l[c] = VMTL_HAS_CLASS(c, C) ? s_l[threadIdx.x * CS + c] : 0.f;
     }
   } else {
     if ((int)threadIdx.x < npx) {
-      const int64_t p = p0 + threadIdx.x;
-      const int64_t bi = p / HW, hw = p - bi * HW;
-      const float* base = logits + bi * C * HW + hw;
+      const float* ptr = logits + nchw_offset(p0 + threadIdx.x, HW, C);
 #pragma unroll
-      for (int c = 0; c < CPAD; ++c) l[c] = c < C ? __ldg(base + (int64_t)c * HW) : 0.f;
+      for (int c = 0; c < CPAD; ++c, ptr += HW) l[c] = VMTL_HAS_CLASS(c, C) ? __ldg(ptr) : 0.f;
     }
   }
 }
@@ -419,9 +450,9 @@ __global__ void __launch_bounds__(kLossThreads)
     float l[CPAD];
     load_logits_tile<CPAD, NHWC>(logits, p0, npx, HW, C, s_l, CS, l);
     if ((int)threadIdx.x < npx) {
+      const int64_t t = __ldg(target + p0 + threadIdx.x);  // issued before the softmax math
       PixelCE<CPAD> ce;
       ce.run(l, C);
-      const int64_t t = target[p0 + threadIdx.x];
       if (pred) pred[p0 + threadIdx.x] = (uint8_t)ce.arg;
       if (target_valid(t, C, ignore_index)) {
         loss_acc += (double)(ce.lse - pick<CPAD>(l, (int)t));
@@ -452,27 +483,25 @@ __global__ void __launch_bounds__(kLossThreads)
     float l[CPAD];
     load_logits_tile<CPAD, NHWC>(logits, p0, npx, HW, C, s_l, CS, l);
     if ((int)threadIdx.x < npx) {
+      const int64_t t = __ldg(target + p0 + threadIdx.x);
       PixelCE<CPAD> ce;
       ce.run(l, C);
-      const int64_t t = target[p0 + threadIdx.x];
       const bool valid = target_valid(t, C, ignore_index);
 #pragma unroll
       for (int c = 0; c < CPAD; ++c) {
         float d = 0.f;
-        if (valid && c < C) d = (expf(l[c] - ce.lse) - (c == (int)t ? 1.f : 0.f)) * scale;
+        if (valid) d = (ce.prob(l[c]) - (c == (int)t ? 1.f : 0.f)) * scale;
         l[c] = d;
       }
       if (NHWC) {
 #pragma unroll
         for (int c = 0; c < CPAD; ++c)
-          if (c < C) s_l[threadIdx.x * CS + c] = l[c];
+          if (VMTL_HAS_CLASS(c, C)) s_l[threadIdx.x * CS + c] = l[c];
       } else {
-        const int64_t p = p0 + threadIdx.x;
-        const int64_t bi = p / HW, hw = p - bi * HW;
-        float* base = dlogits + bi * C * HW + hw;
+        float* ptr = dlogits + nchw_offset(p0 + threadIdx.x, HW, C);
 #pragma unroll
-        for (int c = 0; c < CPAD; ++c)
-          if (c < C) base[(int64_t)c * HW] = l[c];
+        for (int c = 0; c < CPAD; ++c, ptr += HW)
+          if (VMTL_HAS_CLASS(c, C)) *ptr = l[c];
       }
     }
     if (NHWC) {
@@ -480,9 +509,10 @@ __global__ void __launch_bounds__(kLossThreads)
       const int n = npx * C;
       float* dst = dlogits + p0 * C;
       const int n4 = n >> 2;
+      const uint32_t cmagic = 0xffffffffu / (uint32_t)C + 1u;
       for (int q = threadIdx.x; q < n4; q += kLossThreads) {
         int idx = q * 4;
-        int r = idx / C, c = idx - r * C;
+        int r = (int)__umulhi((uint32_t)idx, cmagic), c = idx - r * C;
         float vv[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -511,17 +541,21 @@ struct SilogAcc {
   double n, sg, sgg, sabs, srel;
 };
 
+__device__ __forceinline__ float sigmoid_fast(float u) { return __fdividef(1.f, 1.f + fast_ex2(-u * kLog2e)); }
+// log(p) - log(t) through MUFU lg2
+__device__ __forceinline__ float log_ratio(float p, float t) { return (fast_lg2(p) - fast_lg2(t)) * kLn2; }
+
 __device__ __forceinline__ void silog_pixel(float zd, float t, float min_depth, SilogAcc& a, float& p_out) {
-  const float p = sigmoidf_acc(zd);
+  const float p = sigmoid_fast(zd);
   p_out = p;
   const float d = fabsf(p - t);
   a.sabs += (double)d;
   if (t > min_depth) {
-    const float g = logf(p) - logf(t);
+    const float g = log_ratio(p, t);
     a.n += 1.0;
     a.sg += (double)g;
     a.sgg += (double)g * (double)g;
-    a.srel += (double)(d / t);
+    a.srel += (double)__fdividef(d, t);
   }
 }
 
@@ -561,16 +595,25 @@ __global__ void __launch_bounds__(kLossThreads)
         v[u] = ok[u] ? ldg_stream(f4 + p * LPP + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
         tg[u] = ok[u] ? __ldg(target + p) : 0.f;
       }
+      // after the butterfly every lane of a pixel group holds all U dot products: lane `sub` (< U) takes
+      // pixel u = sub, so the sigmoid/log/fp64 part runs once per warp instead of once per unrolled pixel
+      float dsel = 0.f, tsel = 0.f;
+      bool oksel = false;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         float d = v[u].x * w4.x + v[u].y * w4.y + v[u].z * w4.z + v[u].w * w4.w;
 #pragma unroll
         for (int o = LPP / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        if (sub == 0 && ok[u]) {
-          float pr;
-          silog_pixel(d + bias, tg[u], min_depth, a, pr);
-          if (pred) pred[pbase + pl + u * ngrp] = pr;
+        if (sub == u) {
+          dsel = d;
+          tsel = tg[u];
+          oksel = ok[u];
         }
+      }
+      if (sub < U && oksel) {
+        float pr;
+        silog_pixel(dsel + bias, tsel, min_depth, a, pr);
+        if (pred) pred[pbase + pl + sub * ngrp] = pr;
       }
     }
   }
@@ -639,8 +682,8 @@ __global__ void __launch_bounds__(kLossThreads)
       const float t = __ldg(target + p);
       float dz = 0.f;
       if (t > min_depth) {
-        const float pr = sigmoidf_acc(__ldg(feat + p));
-        const float g = logf(pr) - logf(t);
+        const float pr = sigmoid_fast(__ldg(feat + p));
+        const float g = log_ratio(pr, t);
         dz = (cA * (g - fmean) + cB) * (1.f - pr);
       }
       dfeat[p] = dz;
@@ -657,26 +700,38 @@ __global__ void __launch_bounds__(kLossThreads)
     float dbacc = 0.f;
     const int lane_ = threadIdx.x & 31;
     const int pl = lane_ / LPP;
-    for (int64_t pbase = (gtid - lane_) / LPP; pbase < P; pbase += ngrp) {  // warp-uniform bound
-      const int64_t p = pbase + pl;
-      const bool ok = p < P;
-      const float4 v = ok ? ldg_stream(f4 + p * LPP + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float t = ok ? __ldg(target + p) : 0.f;
-      float d = v.x * w4.x + v.y * w4.y + v.z * w4.z + v.w * w4.w;
+    constexpr int U = 4;  // pixels in flight per thread
+    for (int64_t pbase = (gtid - lane_) / LPP; pbase < P; pbase += U * ngrp) {  // warp-uniform bound
+      float4 v[U];
+      float tg[U];
+      bool ok[U];
 #pragma unroll
-      for (int o = LPP / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-      float dz = 0.f;
-      if (ok && t > min_depth) {
-        const float pr = sigmoidf_acc(d + bias);
-        const float g = logf(pr) - logf(t);
-        dz = (cA * (g - fmean) + cB) * (1.f - pr);
+      for (int u = 0; u < U; ++u) {
+        const int64_t p = pbase + pl + u * ngrp;
+        ok[u] = p < P;
+        v[u] = ok[u] ? ldg_stream(f4 + p * LPP + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+        tg[u] = ok[u] ? __ldg(target + p) : 0.f;
       }
-      if (dfeat && ok) stg_stream(df4 + p * LPP + sub, make_float4(dz * w4.x, dz * w4.y, dz * w4.z, dz * w4.w));
-      dw.x = fmaf(dz, v.x, dw.x);
-      dw.y = fmaf(dz, v.y, dw.y);
-      dw.z = fmaf(dz, v.z, dw.z);
-      dw.w = fmaf(dz, v.w, dw.w);
-      if (sub == 0) dbacc += dz;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t p = pbase + pl + u * ngrp;
+        float d = v[u].x * w4.x + v[u].y * w4.y + v[u].z * w4.z + v[u].w * w4.w;
+#pragma unroll
+        for (int o = LPP / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        float dz = 0.f;
+        if (ok[u] && tg[u] > min_depth) {
+          const float pr = sigmoid_fast(d + bias);
+          const float g = log_ratio(pr, tg[u]);
+          dz = (cA * (g - fmean) + cB) * (1.f - pr);
+        }
+        if (dfeat && ok[u])
+          stg_stream(df4 + p * LPP + sub, make_float4(dz * w4.x, dz * w4.y, dz * w4.z, dz * w4.w));
+        dw.x = fmaf(dz, v[u].x, dw.x);
+        dw.y = fmaf(dz, v[u].y, dw.y);
+        dw.z = fmaf(dz, v[u].z, dw.z);
+        dw.w = fmaf(dz, v[u].w, dw.w);
+        if (sub == 0) dbacc += dz;
+      }
     }
     // reduce lanes that share `sub` inside the warp, then across warps
 #pragma unroll
@@ -821,7 +876,7 @@ extern "C" int vmtl_ce_logits_fwd(const float* logits, const int64_t* target, in
   if (!cpad) return VMTL_EUNSUPPORTED;
   if (layout == VMTL_LAYOUT_NHWC && !aligned16(logits)) return VMTL_EALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = loss_grid(P, kLossThreads, 4);
+  const int grid = loss_grid(P, kLossThreads, 8);
   if (workspace_bytes < (size_t)grid * 2 * sizeof(double)) return VMTL_EWORKSPACE;
   double* partial = static_cast<double*>(workspace);
   size_t smem = conf ? (size_t)C * C * sizeof(unsigned int) : 0;
@@ -851,7 +906,7 @@ extern "C" int vmtl_ce_logits_bwd(const float* logits, const int64_t* target, in
   if (layout == VMTL_LAYOUT_NHWC && (!aligned16(logits) || !aligned16(dlogits))) return VMTL_EALIGN;
   if (P == 0) return VMTL_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = loss_grid(P, kLossThreads, 4);
+  const int grid = loss_grid(P, kLossThreads, 8);
   const size_t smem = layout == VMTL_LAYOUT_NHWC ? (size_t)kLossThreads * (C | 1) * sizeof(float) : 0;
 #define VMTL_CEB(CP, NH)                                                                          \
   ce_logits_bwd_kernel<CP, NH><<<grid, kLossThreads, smem, st>>>(logits, target, P, HW, C,        \

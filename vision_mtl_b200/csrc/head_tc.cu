@@ -65,16 +65,6 @@ static bool ht_make_tmap(CUtensorMap* m, const float* base, int64_t rows) {
 __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
   asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ float fast_ex2(float x) {  // ex2.approx: ~2 ulp, inputs here are <= 0
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float fast_log(float x) {
-  float r;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r * 0.6931471805599453f;
-}
 
 #ifdef VMTL_HT_PROF
 __device__ long long g_ht_prof[148][16];
@@ -257,7 +247,6 @@ __global__ void __launch_bounds__(kHtThreads, 1)
           m = l[c];
           arg = c;
         }
-      constexpr float kLog2e = 1.4426950408889634f;
       const float mneg = -m * kLog2e;
       float sum = 0.f;
 #pragma unroll
@@ -277,7 +266,7 @@ __global__ void __launch_bounds__(kHtThreads, 1)
       if (p < P) {
         if (pred) pred[p] = (uint8_t)arg;
         if (t != ignore_index && (uint64_t)t < (uint64_t)C) {
-          loss_acc += (double)(m + fast_log(sum) - lt);
+          loss_acc += (double)(fmaf(fast_lg2(sum), kLn2, m) - lt);
           n_acc += 1.0;
           if (conf) red_shared_add(smem_u32(s_conf) + 4u * (uint32_t)(ti * C + arg), 1u);
         }
