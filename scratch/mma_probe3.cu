@@ -23,14 +23,14 @@ __device__ __forceinline__ void wait_k(uint32_t bar, uint32_t parity) {
   } while (!done);
 }
 
-template <int N, bool TS, int WAITK = 0>
+template <int N, bool TS, int WAITK = 0, int MODE = 0, int MM = 128>
 __global__ void __launch_bounds__(288, 1) probe(long long* times, int nmma, int n_st, int n_ld, int st_gap, int group) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   __shared__ volatile int stop;
-  for (int i = threadIdx.x; i < 65536 / 4; i += blockDim.x) ((float*)smem)[i] = 0.001f * (i & 63);
+  for (int i = threadIdx.x; i < 131072 / 4; i += blockDim.x) ((float*)smem)[i] = 0.001f * (i & 63);
   if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); stop = 0; }
   if (threadIdx.x < 32) tmem_alloc(smem_u32(&tmem_slot), 512);
   fence_proxy_async_smem();
@@ -66,9 +66,9 @@ __global__ void __launch_bounds__(288, 1) probe(long long* times, int nmma, int 
       if (l == 0) times[8 + blockIdx.x * 16 + w] = cnt + (acc == 123.f);
     }
   } else if (l == 0) {
-    constexpr uint32_t idesc = idesc_tf32(128, N, 0, 0);
+    constexpr uint32_t idesc = MODE == 2 ? idesc_tf32(MM, N, 1, 1) : (MODE == 3 ? idesc_tf32(MM, N, 0, 1) : idesc_tf32(MM, N, 0, 0));
     const uint32_t b = smem_u32(smem);          // B: [256 rows][128 B]
-    const uint32_t a_s = smem_u32(smem + 32768);  // A (SS): [128 rows][128 B]
+    const uint32_t a_s = smem_u32(smem + 65536);  // A (SS)
     tc_fence_after_sync();
     const long long t0 = clock64();
     int ph = 0;
@@ -76,7 +76,12 @@ __global__ void __launch_bounds__(288, 1) probe(long long* times, int nmma, int 
       for (int j = 0; j < group; ++j) {
         const uint32_t ks = (uint32_t)(j & 3);
         const uint64_t db = smem_desc_sw128(b + ks * 32, 16, 1024);
-        if (TS)
+        if (MODE == 2)
+          mma_tf32(tmem + (uint32_t)((i / group) & 1) * 128, smem_desc_mn_tf32(a_s + ks * 1024, 16384, 512),
+                   smem_desc_mn_tf32(b + ks * 1024, 16384, 512), idesc, j > 0);
+        else if (MODE == 3)
+          mma_tf32_ts(tmem + (uint32_t)((i / group) & 1) * 128, tmem + 256 + ks * 8, smem_desc_mn_tf32(b + ks * 1024, 16384, 512), idesc, j > 0);
+        else if (TS)
           mma_tf32_ts(tmem + (uint32_t)((i / group) & 1) * 128, tmem + 256 + ks * 8, db, idesc, j > 0);
         else
           mma_tf32(tmem + (uint32_t)((i / group) & 1) * 128, smem_desc_sw128(a_s + ks * 32, 16, 1024), db, idesc, j > 0);
@@ -95,15 +100,15 @@ __global__ void __launch_bounds__(288, 1) probe(long long* times, int nmma, int 
   if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
 }
 
-template <int N, bool TS, int WAITK = 0>
+template <int N, bool TS, int WAITK = 0, int MODE = 0, int MM = 128>
 void run(const char* name, int n_st, int n_ld, int gap, int group, int grid = 148) {
   long long* times;
   cudaMalloc(&times, 8192 * 8);
   cudaMemset(times, 0, 8192 * 8);
-  auto k = probe<N, TS, WAITK>;
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+  auto k = probe<N, TS, WAITK, MODE, MM>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
   const int nmma = 8192;
-  k<<<grid, 288, 72 * 1024>>>(times, nmma, n_st, n_ld, gap, group);
+  k<<<grid, 288, 140 * 1024>>>(times, nmma, n_st, n_ld, gap, group);
   cudaError_t e = cudaDeviceSynchronize();
   std::vector<long long> h(8192);
   cudaMemcpy(h.data(), times, 8192 * 8, cudaMemcpyDeviceToHost);
@@ -117,18 +122,17 @@ void run(const char* name, int n_st, int n_ld, int gap, int group, int grid = 14
 }
 
 int main() {
-  run<32, true, 0>("TS N32 hint", 0, 0, 0, 8);
-  run<32, true, 1>("TS N32 try_wait", 0, 0, 0, 8);
-  run<32, true, 2>("TS N32 test_wait", 0, 0, 0, 8);
-  run<32, true, 2>("TS N32 test_wait g4", 0, 0, 0, 4);
-  run<32, true, 2>("TS N32 test_wait g2", 0, 0, 0, 2);
-  run<32, true, 2>("TS N32 test_wait g32", 0, 0, 0, 32);
-  run<64, true, 2>("TS N64 test_wait", 0, 0, 0, 8);
-  run<128, true, 2>("TS N128 test_wait", 0, 0, 0, 8);
-  run<256, true, 2>("TS N256 test_wait", 0, 0, 0, 8);
-  run<64, true, 2>("TS N64 test_wait +st+ld", 4, 4, 0, 8);
-  run<64, true, 2>("TS N64 test_wait +st+ld gap", 4, 4, 500, 8);
-  run<64, false, 2>("SS N64 test_wait", 0, 0, 0, 8);
-  run<64, false, 2>("SS N64 test_wait +st+ld gap", 4, 4, 500, 8);
+  run<64, true, 2, 0>("TS Kmaj N64 g32", 0, 0, 0, 32);
+  run<64, false, 2, 1>("SS Kmaj N64 g32", 0, 0, 0, 32);
+  run<64, false, 2, 2>("SS MN/MN M128 N64 g32", 0, 0, 0, 32);
+  run<64, false, 2, 2, 64>("SS MN/MN M64 N64 g32", 0, 0, 0, 32);
+  run<32, false, 2, 2>("SS MN/MN M128 N32 g32", 0, 0, 0, 32);
+  run<128, false, 2, 2>("SS MN/MN M128 N128 g32", 0, 0, 0, 32);
+  run<64, true, 2, 3>("TS MN-B N64 g32", 0, 0, 0, 32);
+  run<128, true, 2, 3>("TS MN-B N128 g32", 0, 0, 0, 32);
+  run<32, true, 2, 3>("TS MN-B N32 g32", 0, 0, 0, 32);
+  run<64, true, 2, 3>("TS MN-B N64 g32 +st+ld gap", 4, 4, 500, 32);
+  run<64, false, 2, 2>("SS MN/MN M128 N64 g32 +st+ld gap", 4, 4, 500, 32);
+  run<64, true, 2, 0>("TS Kmaj N64 g32 +st+ld gap", 4, 4, 500, 32);
   return 0;
 }

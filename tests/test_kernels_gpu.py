@@ -174,7 +174,8 @@ def test_ce_logits(B, C, H, W, layout, ignore):
 
 
 # ----------------------------------------------------------------------------- fused heads
-@pytest.mark.parametrize("B,C,H,W", [(2, 19, 16, 32), (1, 13, 5, 9), (2, 14, 32, 32), (2, 19, 128, 256)])
+@pytest.mark.parametrize("B,C,H,W", [(2, 19, 16, 32), (1, 13, 5, 9), (2, 14, 32, 32), (2, 19, 128, 256),
+                                     (1, 27, 20, 20), (1, 13, 15, 9), (3, 16, 33, 47), (1, 32, 24, 24)])
 @pytest.mark.parametrize("ignore", [False, True])
 def test_head_ce(B, C, H, W, ignore):
     from vision_mtl_b200 import ops

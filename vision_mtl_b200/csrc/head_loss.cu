@@ -837,10 +837,26 @@ extern "C" int vmtl_head_ce_bwd(const float* feat, const float* W, const float* 
   if (!cpad) return VMTL_EUNSUPPORTED;
   if (!aligned16(feat) || (dfeat && !aligned16(dfeat))) return VMTL_EALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = loss_grid(P, kLossThreads, 2);
   const int ROW = cpad * (kHeadCin + 1);
-  if (workspace_bytes < (size_t)grid * ROW * sizeof(float)) return VMTL_EWORKSPACE;
   float* partial = static_cast<float*>(workspace);
+  static const bool use_tc = [] {  // VMTL_HEAD_BWD=ffma selects the CUDA-core kernel
+    const char* e = getenv("VMTL_HEAD_BWD");
+    return !(e && strcmp(e, "ffma") == 0);
+  }();
+  if (use_tc && P >= 128) {
+    int g = 0;
+    const int max_blocks = (int)(workspace_bytes / ((size_t)ROW * sizeof(float)));
+    const int rc = head_ce_tc_bwd(feat, W, b, target, P, C, ignore_index, fwd_out, gscale, dfeat, partial,
+                                  max_blocks, &g, st);
+    if (rc == VMTL_OK) {
+      const int n = C * (kHeadCin + 1);
+      head_ce_bwd_finalize<<<(n + 31) / 32, kFinThreads, 0, st>>>(partial, g, cpad, C, dW, db);
+      return launch_status();
+    }
+    if (rc != VMTL_EUNSUPPORTED) return rc;
+  }
+  const int grid = loss_grid(P, kLossThreads, 2);
+  if (workspace_bytes < (size_t)grid * ROW * sizeof(float)) return VMTL_EWORKSPACE;
   // dynamic smem: max(dl tile [256][cpad+1], reduction [8][ROW]) floats
   size_t a = (size_t)kLossThreads * (cpad + 1), r = (size_t)(kLossThreads / 32) * ROW;
   const size_t smem = (a > r ? a : r) * sizeof(float);
