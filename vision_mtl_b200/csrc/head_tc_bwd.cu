@@ -5,9 +5,11 @@
 //   (1) logits = f . W^T + b             [128 x 32] x [32 x C]      tcgen05, A = f hi/lo in TMEM
 //   (2) dl = (softmax - onehot) * g/n    one pixel per thread       epilogue-1 warps
 //   (3) dfeat = dl . W                   [128 x C] x [C x 32]       tcgen05, A = dl hi/lo in TMEM
-//   (4) dW^T-ish: D3 += [dl_hi;dl_lo]^T . [f_hi | f_lo]   contraction over the tile's pixels, both operands
-//       MN-major in shared memory (rows = pixels, exactly what a pixel-per-thread writer produces);
-//       the accumulator stays in TMEM for all tiles of the CTA.
+//   (4) D3 += [dl_hi;dl_mid]^T . [f_hi | f_mid]   contraction over the tile's pixels in bf16x2 (each operand
+//       split into two bf16 = 16 mantissa bits; the sum over >= 1e5 pixels of signed terms keeps the result
+//       at ~1e-5 relative), kind::f16 has K = 16, so 8 MMAs per tile; both operands MN-major in shared
+//       memory (one 128-byte row per pixel, exactly what a pixel-per-thread writer produces); the
+//       accumulator stays in TMEM for all tiles of the CTA.
 //   db accumulates in registers of the epilogue-1 threads.
 // The CUDA-core version (head_loss.cu) spends ~3500 instructions per pixel on the three contractions
 // (1824 FMA) and runs at 20 % of the HBM roofline.
@@ -33,12 +35,12 @@ constexpr int kHbTile = 128;
 
 struct HbSmem {
   static constexpr int kSlot = kHbTile * 128;          // 16 KB: [128 rows x 32 floats]
-  static constexpr int kStages = 2;
-  // MN-major operand slots of the pixel contraction: dl sets 0,1 = [hi][lo] each, then f sets 0,1,2 = [hi][lo].
-  // (the M = 128 A operand spans 4 slots from a dl set: the two extra slots are whatever follows -- finite
-  // data feeding accumulator rows 64..127, which nobody reads)
+  static constexpr int kStages = 4;
+  // MN-major bf16 operand slots of the pixel contraction, one 128-byte row per pixel = 64 bf16 =
+  // [hi(32) | mid(32)]: dl sets 0,1 then f sets 0,1,2.  (The M = 128 A operand spans 2 slots from a dl
+  // set: the second is whatever follows and feeds accumulator rows 64..127, which nobody reads.)
   static constexpr int kOps = kStages * kSlot;
-  static constexpr int kOut = kOps + 10 * kSlot;       // dfeat staging for the TMA store
+  static constexpr int kOut = kOps + 5 * kSlot;        // dfeat staging for the TMA store
   static constexpr int kW1 = kOut + kSlot;             // [W_hi ; W_lo]     rows = class,   K = feature
   static constexpr int kW2 = kW1 + 64 * 128;           // [W^T_hi ; W^T_lo] rows = feature, K = class
   static constexpr int kMisc = kW2 + 64 * 128;
@@ -93,20 +95,20 @@ __global__ void __launch_bounds__(kHbThreads, 1)
   uint8_t* sW1 = smem + L::kW1;
   uint8_t* sW2 = smem + L::kW2;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::kMisc);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::kMisc + 192);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::kMisc + 224);
   float* s_bias = reinterpret_cast<float*>(smem + L::kMisc + 256);  // [32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(s_bar);
   auto bar_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
-  auto bar_empty = [&](int s) { return bar0 + 16u + 8u * (uint32_t)s; };
-  auto bar_conv = [&](int r) { return bar0 + 32u + 8u * (uint32_t)r; };      // [3] f hi/lo in TMEM + smem
-  auto bar_d1full = [&](int b) { return bar0 + 56u + 8u * (uint32_t)b; };    // [2] logits accumulator complete
-  auto bar_dl = [&](int b) { return bar0 + 72u + 8u * (uint32_t)b; };        // [2] dl hi/lo in TMEM + smem
-  auto bar_d2full = [&](int r) { return bar0 + 88u + 8u * (uint32_t)r; };    // [3] dfeat accumulator complete
-  auto bar_d2free = [&](int r) { return bar0 + 112u + 8u * (uint32_t)r; };   // [3] ... and read out
+  auto bar_empty = [&](int s) { return bar0 + 32u + 8u * (uint32_t)s; };
+  auto bar_conv = [&](int r) { return bar0 + 64u + 8u * (uint32_t)r; };      // [3] f hi/lo in TMEM + smem
+  auto bar_d1full = [&](int b) { return bar0 + 88u + 8u * (uint32_t)b; };    // [2] logits accumulator complete
+  auto bar_dl = [&](int b) { return bar0 + 104u + 8u * (uint32_t)b; };        // [2] dl hi/lo in TMEM + smem
+  auto bar_d2full = [&](int r) { return bar0 + 120u + 8u * (uint32_t)r; };    // [3] dfeat accumulator complete
+  auto bar_d2free = [&](int r) { return bar0 + 144u + 8u * (uint32_t)r; };   // [3] ... and read out
   // pixel contraction of tile t retired: barrier t % 6 (its f set t % 3 and dl set t % 2 are free again)
-  auto bar_mma3 = [&](int64_t t) { return bar0 + 136u + 8u * (uint32_t)(t % 6); };
+  auto bar_mma3 = [&](int64_t t) { return bar0 + 168u + 8u * (uint32_t)(t % 6); };
   auto par_mma3 = [&](int64_t t) { return (uint32_t)((t / 6) & 1); };
 
   if (threadIdx.x == 0) {
@@ -151,8 +153,8 @@ __global__ void __launch_bounds__(kHbThreads, 1)
   auto R1 = [&](int r) { return tmem_base + (uint32_t)(r * 64); };        // r = tile % 3
   auto R2 = [&](int b) { return tmem_base + (uint32_t)(192 + b * 64); };  // b = tile % 2
   const uint32_t tmem_d3 = tmem_base + 320;
-  auto dl_set = [&](int b) { return smem + L::kOps + b * 2 * L::kSlot; };        // [hi][lo]
-  auto f_set = [&](int r) { return smem + L::kOps + (4 + r * 2) * L::kSlot; };   // [hi][lo]
+  auto dl_set = [&](int b) { return smem + L::kOps + b * L::kSlot; };
+  auto f_set = [&](int r) { return smem + L::kOps + (2 + r) * L::kSlot; };
 
   const int64_t ntiles = (P + kHbTile - 1) / kHbTile;
   const int64_t nitems = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -177,8 +179,7 @@ __global__ void __launch_bounds__(kHbThreads, 1)
         tc_fence_after_sync();
       }
       const uint32_t ta = R1(r) + (((uint32_t)quad * 32) << 16);
-      uint8_t* fh = f_set(r);
-      uint8_t* fl = f_set(r) + L::kSlot;
+      uint8_t* fs = f_set(r);
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         float hi[16], lo[16];
@@ -188,9 +189,16 @@ __global__ void __launch_bounds__(kHbThreads, 1)
           hi[4 * j] = tf32_hi(a.x); hi[4 * j + 1] = tf32_hi(a.y); hi[4 * j + 2] = tf32_hi(a.z); hi[4 * j + 3] = tf32_hi(a.w);
           lo[4 * j] = a.x - hi[4 * j]; lo[4 * j + 1] = a.y - hi[4 * j + 1];
           lo[4 * j + 2] = a.z - hi[4 * j + 2]; lo[4 * j + 3] = a.w - hi[4 * j + 3];
-          const uint32_t o = sw128b32_off(row, g * 4 + j);
-          *reinterpret_cast<float4*>(fh + o) = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-          *reinterpret_cast<float4*>(fl + o) = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {  // features 16g + 8j .. +7 -> bf16 hi (chunk 2g + j) and mid (chunk 4 + 2g + j)
+          const float x8[8] = {v[g * 4 + 2 * j].x, v[g * 4 + 2 * j].y, v[g * 4 + 2 * j].z, v[g * 4 + 2 * j].w,
+                               v[g * 4 + 2 * j + 1].x, v[g * 4 + 2 * j + 1].y, v[g * 4 + 2 * j + 1].z,
+                               v[g * 4 + 2 * j + 1].w};
+          uint4 bh, bm;
+          bf16_split8(x8, bh, bm);
+          *reinterpret_cast<uint4*>(fs + sw128_off(row, 2 * g + j)) = bh;
+          *reinterpret_cast<uint4*>(fs + sw128_off(row, 4 + 2 * g + j)) = bm;
         }
         tmem_st16(ta + g * 16, hi);
         tmem_st16(ta + 32 + g * 16, lo);
@@ -207,8 +215,7 @@ __global__ void __launch_bounds__(kHbThreads, 1)
     auto pixel_of = [&](int64_t it) { return (blockIdx.x + it * gridDim.x) * kHbTile + row; };
     int64_t t_next = (g < nitems && pixel_of(g) < P) ? __ldg(target + pixel_of(g)) : ignore_index;
     const uint32_t taddr = R2(g) + (((uint32_t)quad * 32) << 16);
-    uint8_t* dh = dl_set(g);
-    uint8_t* dlo = dl_set(g) + L::kSlot;
+    uint8_t* ds = dl_set(g);
     for (int64_t it = g; it < nitems; it += 2) {
       const uint32_t k2 = (uint32_t)(it >> 1);
       const int64_t p = pixel_of(it);
@@ -258,24 +265,26 @@ __global__ void __launch_bounds__(kHbThreads, 1)
         mbar_wait(bar_mma3(it - 2), par_mma3(it - 2));
         tc_fence_after_sync();
       }
-      // dl hi/lo: TMEM (A operand of dfeat = dl . W, columns = classes) and smem (MN-major rows = pixels)
+      // dl: tf32 hi/lo to TMEM (A operand of dfeat = dl . W, columns = classes) and bf16 hi/mid to smem
+      // (MN-major row of this pixel for the contraction over pixels)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        float hi[16], lo[16];
+        float d16[16], hi[16], lo[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const int c = h * 16 + e;
-          const float d = c < CPAD ? l[c < CPAD ? c : 0] : 0.f;
-          hi[e] = tf32_hi(d);
-          lo[e] = d - hi[e];
+          d16[e] = c < CPAD ? l[c < CPAD ? c : 0] : 0.f;
+          hi[e] = tf32_hi(d16[e]);
+          lo[e] = d16[e] - hi[e];
         }
         tmem_st16(taddr + h * 16, hi);
         tmem_st16(taddr + 32 + h * 16, lo);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t o = sw128b32_off(row, h * 4 + j);
-          *reinterpret_cast<float4*>(dh + o) = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-          *reinterpret_cast<float4*>(dlo + o) = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        for (int j = 0; j < 2; ++j) {
+          uint4 bh, bm;
+          bf16_split8(d16 + 8 * j, bh, bm);
+          *reinterpret_cast<uint4*>(ds + sw128_off(row, 2 * h + j)) = bh;
+          *reinterpret_cast<uint4*>(ds + sw128_off(row, 4 + 2 * h + j)) = bm;
         }
       }
       tmem_wait_st();
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__(kHbThreads, 1)
     // ------------------------------------------------------------------ MMA issuer (logits run one tile ahead)
     constexpr uint32_t idesc_wide = idesc_tf32(kHbTile, 64, 0, 0);
     constexpr uint32_t idesc_n = idesc_tf32(kHbTile, 32, 0, 0);
-    constexpr uint32_t idesc_px = idesc_tf32(128, 64, 1, 1);  // both operands MN-major (rows = pixels)
+    constexpr uint32_t idesc_px = idesc_bf16(128, 64, 1, 1);  // bf16, both operands MN-major (rows = pixels)
     const uint32_t bW1 = smem_u32(sW1), bW2 = smem_u32(sW2);
 #ifdef VMTL_HT_PROF
     long long hb_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -378,10 +387,10 @@ __global__ void __launch_bounds__(kHbThreads, 1)
         HB_ACC(3, t3);
         HB_T0(t4);
         const uint32_t oA = smem_u32(dl_set(b)), oB = smem_u32(f_set(r));
-#pragma unroll 1
-        for (int ks = 0; ks < kHbTile / 8; ++ks)
-          mma_tf32(tmem_d3, smem_desc_mn_tf32(oA + ks * 1024, L::kSlot, 512),
-                   smem_desc_mn_tf32(oB + ks * 1024, L::kSlot, 512), idesc_px, (j | ks) != 0);
+#pragma unroll
+        for (int ks = 0; ks < kHbTile / 16; ++ks)  // 16 pixel rows (two 8-row swizzle groups) per MMA
+          mma_bf16(tmem_d3, smem_desc_sw128(oA + ks * 2048, L::kSlot, 1024),
+                   smem_desc_sw128(oB + ks * 2048, L::kSlot, 1024), idesc_px, (j | ks) != 0);
         mma_commit(bar_mma3(j));
         HB_ACC(4, t4);
       }
