@@ -191,6 +191,16 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+_T0 = time.perf_counter()
+
+
+def _phase(msg: str) -> None:
+    """Progress line on stderr (rank 0): where the wall time of a bench run goes."""
+    if int(os.environ.get("RANK", 0)) == 0:
+        sys.stderr.write(f"[bench +{time.perf_counter() - _T0:7.1f}s] {msg}\n")
+        sys.stderr.flush()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -204,6 +214,7 @@ def main():
     from vision_mtl_b200.utils.pipeline_utils import DataShape, init_model
 
     rank, local_rank, world = vdist.init_distributed()
+    _phase(f"process group ready (world {world})")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -231,6 +242,7 @@ def main():
             vdist.wrap_data_parallel(module, local_rank)
         torch.cuda.current_stream().wait_stream(side)
     opt = torch.optim.Adam(module.parameters(), lr=args.lr, fused=True, capturable=use_graph)
+    _phase("model + optimizer built")
 
     host = make_batch(B, H, W, C, dataset, seed=11 + rank, pin=True)          # pinned host copy
     resident = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
@@ -257,6 +269,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         eager_step(resident)
     barrier()
+    _phase("eager warm-up done")
 
     # ---- per-launch kernel events (roofline): recorded around every library call ---------------
     # eager mode: inside the timed region; graph mode: in an eager pass of the identical step, because
@@ -274,10 +287,12 @@ def main():
         ksteps = min(args.steps, 5)
         from vision_mtl_b200.graph_step import GraphedTrainStep
 
+        _phase("per-kernel event pass done")
         graphed = GraphedTrainStep(module, opt, resident, warmup=11 if world > 1 else 3, after_backward=metric_exchange)
         for _ in range(3):
             graphed()
         barrier()
+        _phase("step graph captured and replayed")
 
     def train_step(batch):
         if graphed is not None:
@@ -316,6 +331,7 @@ def main():
         barrier()
     launches = launches_per_step * args.steps
     ms = ev0.elapsed_time(ev1)
+    _phase("timed region done")
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host batch in, step scalars out, every step ------------------------------------
@@ -329,15 +345,18 @@ def main():
     ev3.record()
     barrier()
     ms_e2e = ev2.elapsed_time(ev3)
+    _phase("e2e region done")
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    if rank != 0:  # see the exit note at the end of main(): no NCCL teardown under live graphs
+        sys.stdout.flush()
+        sys.stderr.flush()
+        graphed = None
+        barrier()
+        os._exit(0)
 
     ips = B * world * args.steps / (ms * 1e-3)
     ips_e2e = B * world * args.steps / (ms_e2e * 1e-3)
@@ -394,7 +413,14 @@ def main():
                       f"({csec:.1f} s/step), oracle port of the reference's PyTorch CPU path"}
     print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing NCCL down while captured graphs still reference the communicator blocks for minutes
+        # (destroy_process_group waits on work the graphs own).  Everything is measured and printed:
+        # release the graph, line the ranks up and leave without the teardown.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        graphed = None
+        barrier()
+        os._exit(0)
 
 
 if __name__ == "__main__":
