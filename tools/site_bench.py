@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Per-site micro-benchmark of the hand-written kernels at the BASELINE.json shapes (SURVEY A.1-A.3:
-Cityscapes-shaped batch 32, 128x256).  Each op is timed alone with CUDA events, an L2 flush
-(write of a 256 MiB buffer) between iterations, and reported as algorithmic GB/s against
-MEASURED_PEAKS.json.  Also the target command for the ncu captures kept under profiles/.
+Cityscapes-shaped batch 32, 128x256).  Each op is captured into a CUDA graph and timed alone with
+CUDA events around the replay (device time of all launches of the call, no host launch gaps), an L2
+flush (write of a 256 MiB buffer) before every replay and between forward and backward, and reported
+as algorithmic GB/s against MEASURED_PEAKS.json.  Also the target command for the ncu captures kept under profiles/.
 
     python tools/site_bench.py [--iters 5] [--only gate|xstitch|heads|metrics] [--once] [--json out.json]
 """
@@ -50,25 +51,47 @@ def main():
     def cl(*shape):
         return torch.randn(*shape, device=dev).contiguous(memory_format=torch.channels_last)
 
-    def timed(name, site, nbytes_fwd, nbytes_bwd, fwd, bwd=None):
-        iters = 1 if args.once else args.iters
-        best = [1e9, 1e9]
-        for it in range(iters + (0 if args.once else 2)):
+    def replay_ms(graph, iters):
+        best = 1e9
+        for _ in range(iters):
             flush.zero_()
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            e[0].record()
-            out = fwd()
-            e[1].record()
-            if bwd is not None:
-                flush.zero_()
-                e[2].record()
-                bwd(out)
-                e[3].record()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            graph.replay()
+            e1.record()
             torch.cuda.synchronize()
-            if it >= (0 if args.once else 2):
-                best[0] = min(best[0], e[0].elapsed_time(e[1]))
-                if bwd is not None:
-                    best[1] = min(best[1], e[2].elapsed_time(e[3]))
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    # the L2 flush that separates forward and backward inside the fwd+bwd graph, timed alone
+    g_flush = torch.cuda.CUDAGraph()
+    flush.zero_()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g_flush, stream=torch.cuda.current_stream()):
+        flush.zero_()
+    t_flush = replay_ms(g_flush, 5)
+
+    def timed(name, site, nbytes_fwd, nbytes_bwd, fwd, bwd=None):
+        """Each call is captured into a CUDA graph and replayed: the number is device time of ALL launches
+        of the call with no host launch gaps (eager timing of 20-50 us calls mostly measures the host)."""
+        for _ in range(1 if args.once else 2):  # eager warm-up (also the ncu target with --once)
+            out = fwd()
+            if bwd is not None:
+                bwd(out)
+        torch.cuda.synchronize()
+        if args.once:
+            return
+        g_f = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_f, stream=torch.cuda.current_stream()):
+            out = fwd()
+        best = [replay_ms(g_f, args.iters), 0.0]
+        if bwd is not None:
+            g_fb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_fb, stream=torch.cuda.current_stream()):
+                out = fwd()
+                flush.zero_()
+                bwd(out)
+            best[1] = replay_ms(g_fb, args.iters) - best[0] - t_flush
         for tag, ms, nb in (("fwd", best[0], nbytes_fwd), ("bwd", best[1], nbytes_bwd)):
             if nb:
                 gbps = nb / (ms * 1e-3) / 1e9
@@ -159,4 +182,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # everything (leaf creation, warm-up, capture, replay) on ONE non-default stream: autograd binds a
+    # leaf's gradient accumulator to the stream it first ran on, and capture cannot touch the legacy stream
+    _side = torch.cuda.Stream()
+    with torch.cuda.stream(_side):
+        main()
