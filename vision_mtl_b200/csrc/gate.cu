@@ -34,10 +34,10 @@ __device__ __forceinline__ EwMap ew_map(int C4) {
   m.active = m.r < m.rows;
   return m;
 }
-static int ew_grid(int64_t M, int N) {
+static int ew_grid(int64_t M, int N, int per_sm = 8) {
   const int rows = kEwThreads / (N / 4);
   int64_t want = (M + rows - 1) / rows;
-  int64_t cap = (int64_t)sm_count() * 8;
+  int64_t cap = (int64_t)sm_count() * per_sm;
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 
@@ -368,7 +368,7 @@ extern "C" int vmtl_gate_fwd(const float* h, const float* s, const float* W, con
       rc = sgemm64(h, W, zbuf, bias, M, N, K, K, 1, 1, K, N, 1, 0, st);
     }
     if (rc != VMTL_OK) return rc;
-    gate_apply_kernel<<<ew_grid(M, N), kEwThreads, 0, st>>>(zbuf, s, M, C4, ws.coefA, ws.coefB, y);
+    gate_apply_kernel<<<ew_grid(M, N, blocks_per_sm(gate_apply_kernel, kEwThreads, 0, 8)), kEwThreads, 0, st>>>(zbuf, s, M, C4, ws.coefA, ws.coefB, y);
     return launch_status();
   }
 
@@ -388,7 +388,7 @@ extern "C" int vmtl_gate_fwd(const float* h, const float* s, const float* W, con
                                                            ws.mean, ws.invstd, ws.coefA, ws.coefB,
                                                            save_mean, save_invstd);
   if ((rc = launch_status()) != VMTL_OK) return rc;
-  gate_apply_kernel<<<ew_grid(M, N), kEwThreads, 0, st>>>(save_z, s, M, C4, ws.coefA, ws.coefB, y);
+  gate_apply_kernel<<<ew_grid(M, N, blocks_per_sm(gate_apply_kernel, kEwThreads, 0, 8)), kEwThreads, 0, st>>>(save_z, s, M, C4, ws.coefA, ws.coefB, y);
   return launch_status();
 }
 
@@ -431,7 +431,7 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, co
                                                         ws.coefB, ws.mean, ws.invstd);
   if ((rc = launch_status()) != VMTL_OK) return rc;
   // phase A
-  const int nparts = ew_grid(M, N);
+  const int nparts = ew_grid(M, N, blocks_per_sm(gate_bwd_stats_kernel, kEwThreads, 0, 8));
   gate_bwd_stats_kernel<<<nparts, kEwThreads, 0, st>>>(dy, s, z, M, C4, ws.coefA, ws.coefB, ws.mean,
                                                        ws.invstd, ds, ws.partial);
   if ((rc = launch_status()) != VMTL_OK) return rc;

@@ -892,15 +892,18 @@ extern "C" int vmtl_ce_logits_fwd(const float* logits, const int64_t* target, in
   if (!cpad) return VMTL_EUNSUPPORTED;
   if (layout == VMTL_LAYOUT_NHWC && !aligned16(logits)) return VMTL_EALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = loss_grid(P, kLossThreads, 8);
+  int grid = loss_grid(P, kLossThreads, 8);  // upper bound; the launch uses the resident count
   if (workspace_bytes < (size_t)grid * 2 * sizeof(double)) return VMTL_EWORKSPACE;
   double* partial = static_cast<double*>(workspace);
   size_t smem = conf ? (size_t)C * C * sizeof(unsigned int) : 0;
   if (layout == VMTL_LAYOUT_NHWC) smem += (size_t)kLossThreads * (C | 1) * sizeof(float);
   unsigned long long* cf = reinterpret_cast<unsigned long long*>(conf);
 #define VMTL_CEF(CP, NH)                                                                          \
-  ce_logits_fwd_kernel<CP, NH><<<grid, kLossThreads, smem, st>>>(logits, target, P, HW, C,        \
-                                                                 ignore_index, partial, pred, cf)
+  do {                                                                                            \
+    grid = loss_grid(P, kLossThreads, blocks_per_sm(ce_logits_fwd_kernel<CP, NH>, kLossThreads, smem, 8)); \
+    ce_logits_fwd_kernel<CP, NH><<<grid, kLossThreads, smem, st>>>(logits, target, P, HW, C,      \
+                                                                   ignore_index, partial, pred, cf); \
+  } while (0)
   const bool nh = layout == VMTL_LAYOUT_NHWC;
   if (cpad == 16) { if (nh) VMTL_CEF(16, true); else VMTL_CEF(16, false); }
   else if (cpad == 20) { if (nh) VMTL_CEF(20, true); else VMTL_CEF(20, false); }
@@ -922,11 +925,14 @@ extern "C" int vmtl_ce_logits_bwd(const float* logits, const int64_t* target, in
   if (layout == VMTL_LAYOUT_NHWC && (!aligned16(logits) || !aligned16(dlogits))) return VMTL_EALIGN;
   if (P == 0) return VMTL_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = loss_grid(P, kLossThreads, 8);
   const size_t smem = layout == VMTL_LAYOUT_NHWC ? (size_t)kLossThreads * (C | 1) * sizeof(float) : 0;
 #define VMTL_CEB(CP, NH)                                                                          \
-  ce_logits_bwd_kernel<CP, NH><<<grid, kLossThreads, smem, st>>>(logits, target, P, HW, C,        \
-                                                                 ignore_index, fwd_out, gscale, dlogits)
+  do {                                                                                            \
+    const int grid =                                                                              \
+        loss_grid(P, kLossThreads, blocks_per_sm(ce_logits_bwd_kernel<CP, NH>, kLossThreads, smem, 8)); \
+    ce_logits_bwd_kernel<CP, NH><<<grid, kLossThreads, smem, st>>>(logits, target, P, HW, C,      \
+                                                                   ignore_index, fwd_out, gscale, dlogits); \
+  } while (0)
   const bool nh = layout == VMTL_LAYOUT_NHWC;
   if (cpad == 16) { if (nh) VMTL_CEB(16, true); else VMTL_CEB(16, false); }
   else if (cpad == 20) { if (nh) VMTL_CEB(20, true); else VMTL_CEB(20, false); }

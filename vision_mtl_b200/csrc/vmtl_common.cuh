@@ -28,6 +28,15 @@ inline int sm_count() {
   return cached[dev];
 }
 
+// Resident CTAs per SM of `kernel`, clipped to `want`: a persistent / grid-stride launch sized beyond what is
+// resident runs a second, partial wave (e.g. 8 x 256 threads requested at 48 registers -> 5 fit -> 1.6 waves).
+template <typename KernelT>
+inline int blocks_per_sm(KernelT kernel, int threads, size_t smem, int want) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
+  return n < want ? n : want;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline int launch_status() {

@@ -280,8 +280,6 @@ static int xs_fwd_launch(const XsFwdArgs& a, const float* alpha, int64_t n4, int
   const int threads = 256;
   constexpr int U = (T <= 2) ? 4 : (T <= 4 ? 2 : 1);
   int64_t want = (n4 + (int64_t)threads * U - 1) / ((int64_t)threads * U);
-  int64_t cap = (int64_t)sm_count() * 8;
-  int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
   size_t smem = cw ? (size_t)T * T * C4 * sizeof(float4) : 0;
   if (smem > 160 * 1024) return VMTL_EUNSUPPORTED;
 #define VMTL_XS_FWD(DIAG, CWB)                                                                   \
@@ -289,6 +287,9 @@ static int xs_fwd_launch(const XsFwdArgs& a, const float* alpha, int64_t n4, int
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(xstitch_fwd_kernel<T, DIAG, CWB>,                                     \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+    const int64_t cap =                                                                          \
+        (int64_t)sm_count() * blocks_per_sm(xstitch_fwd_kernel<T, DIAG, CWB>, threads, smem, 8); \
+    const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);                            \
     xstitch_fwd_kernel<T, DIAG, CWB><<<grid, threads, smem, st>>>(a, alpha, n4, C4);             \
   } while (0)
   const bool diag = (mode == VMTL_XS_REFERENCE_DIAG);
