@@ -175,7 +175,9 @@ def test_ce_logits(B, C, H, W, layout, ignore):
 
 # ----------------------------------------------------------------------------- fused heads
 @pytest.mark.parametrize("B,C,H,W", [(2, 19, 16, 32), (1, 13, 5, 9), (2, 14, 32, 32), (2, 19, 128, 256),
-                                     (1, 27, 20, 20), (1, 13, 15, 9), (3, 16, 33, 47), (1, 32, 24, 24)])
+                                     (1, 27, 20, 20), (1, 13, 15, 9), (3, 16, 33, 47), (1, 32, 24, 24),
+                                     # 5-6 and 7 tiles per CTA: every barrier ring (mod 2, 3, 4, 6, 8) wraps
+                                     (1, 19, 300, 321), (1, 19, 331, 400)])
 @pytest.mark.parametrize("ignore", [False, True])
 def test_head_ce(B, C, H, W, ignore):
     from vision_mtl_b200 import ops
@@ -269,7 +271,10 @@ def test_head_silog(B, H, W, cin):
 
 # ----------------------------------------------------------------------------- MTAN gate
 GATE_SHAPES = [(2, 32, 16, 24), (1, 64, 9, 13), (2, 128, 8, 8), (1, 256, 4, 8), (4, 32, 64, 64),
-               (3, 128, 20, 24), (2, 256, 12, 10), (1, 192, 16, 20)]
+               (3, 128, 20, 24), (2, 256, 12, 10), (1, 192, 16, 20),
+               # several 128-row tiles per CTA (148 CTAs): the persistent pipelines wrap their stage / TMEM
+               # buffers and mbarrier phases (3-4, 3-4 and 2-3 tiles per CTA)
+               (2, 32, 128, 256), (2, 64, 128, 256), (1, 128, 160, 256)]
 
 
 def _gate_case(B, N, H, W, seed=11):
