@@ -183,8 +183,12 @@ def run_reference(args):
         "impl": "reference", "metric": "mtl_train_step_images_per_sec", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {model} training step, {dataset}-shaped {H}x{W}, {C} classes",
-                   "per_gpu_batch": B, "cpu_sample_batch": bs},
+        "config": {"workload": f"{args.workload}: {model} training step (fwd + fused CE/SILog/metrics + bwd + Adam), "
+                               f"{dataset}-shaped {H}x{W}, {C} classes, per-GPU batch {B}",
+                   "global_batch": B * args.gpus, "parallelism": f"dp{args.gpus}", "conv_math": "fp32 (torch CPU)",
+                   "cpu_sample_batch": bs,
+                   "note": "the reference is single-process CPU code: rank 0 times it on all host cores, "
+                           "throughput does not depend on n_gpus"},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
