@@ -4,12 +4,12 @@
 //
 //   B1 gate_tc_dh_tma_kernel : unit = (128-row tile, 32-column atom a).  TMA brings dy_a, s_a, z_a
 //      ([128 x 32] each, 48 KB per unit, 3 stages).  Converter threads (one row each) rebuild
-//      dz = gamma*invstd*(du - c1 - zhat*c2), store its tf32 hi and lo parts once to global (they
-//      are B2's operands), put hi/lo into TMEM and accumulate db.  MMA: dh[128 x 128] +=
+//      dz = gamma*invstd*(du - c1 - zhat*c2), store it once to global (B2's operand), put its tf32 hi/lo
+//      parts into TMEM and accumulate db.  MMA: dh[128 x 128] +=
 //      dz_a[128 x 32] @ W[a*32.., :]  (A from TMEM, B = W^T atoms K-major in smem, 3xTF32).
 //   B2 gate_tc_dw_tma_kernel : unit = (tile, 64-row half).  TMA brings the h half ([64 x 128], raw)
-//      and the dz_hi / dz_lo halves straight into the MN-major tf32 operand layout
-//      (SWIZZLE_128B_ATOM_32B), so B needs no conversion.  Converter threads (one hidden channel k
+//      and the dz half straight into the MN-major tf32 operand layout (SWIZZLE_128B_ATOM_32B); the
+//      converter warps split it in place into hi / lo atoms (elementwise, layout-agnostic).  Converter threads (one hidden channel k
 //      each) transpose h^T into TMEM (lane = k, column = pixel row) as hi/lo.  MMA per 8 pixel rows:
 //          D[:, 0:2N] += h_hi^T @ [dz_hi | dz_lo] ,  D[:, 0:N] += h_lo^T @ dz_hi
 //      accumulating dW^T over ALL tiles of the CTA in TMEM; drained once.
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
                           const float* __restrict__ coefA, const float* __restrict__ coefB,
                           const float* __restrict__ mean, const float* __restrict__ invstd,
                           const float* __restrict__ c1, const float* __restrict__ c2, int64_t M,
-                          const __grid_constant__ CUtensorMap tmap_dzh_st, const __grid_constant__ CUtensorMap tmap_dzl_st,
+                          const __grid_constant__ CUtensorMap tmap_dz_st,
                           float* __restrict__ dh, float* __restrict__ db_partial /* [grid][n_total] */,
                           int n0 /* first gate column of this pass */, int n_total, int accumulate /* dh += */) {
   using namespace tc;
@@ -167,15 +167,14 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           hi[e] = tf32_hi(d[e]);
           lo[e] = d[e] - hi[e];
         }
-        // dz_hi / dz_lo leave through the stage buffer itself: once every converter holds its inputs in
-        // registers, slots 0/1 of the stage are rewritten (swizzled) and the TMA warp bulk-stores them
+        // dz (fp32, B2 splits it itself) leaves through the stage buffer: once every converter holds its
+        // inputs in registers, slot 0 of the stage is rewritten (swizzled) and the TMA warp bulk-stores it
         // before it refills the stage -- no row-per-thread global stores.
         named_barrier_sync(3, 256);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t o = sw128_off(row, ch * 4 + j);
-          *reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + o) = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-          *reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + L::kSlot + o) = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          *reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + o) = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
         }
         fence_proxy_async_smem();
         mbar_arrive(bar_empty(s));  // = "dz staged": the TMA warp stores it, then reuses the stage
@@ -249,8 +248,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
             mbar_wait(bar_empty(s), (uint32_t)(((u / S) - 1) & 1));
             const int64_t v = u - S;
             const int vrow0 = (int)((blockIdx.x + (v / NA) * gridDim.x) * kTileM), va = (int)(v % NA);
-            tma_store_2d(&tmap_dzh_st, n0 + va * 32, vrow0, smem_u32(smem + s * L::kStage));
-            tma_store_2d(&tmap_dzl_st, n0 + va * 32, vrow0, smem_u32(smem + s * L::kStage + L::kSlot));
+            tma_store_2d(&tmap_dz_st, n0 + va * 32, vrow0, smem_u32(smem + s * L::kStage));
             tma_store_commit();
             tma_store_wait_read();
           }
@@ -266,8 +264,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         const int s = (int)(v % S);
         mbar_wait(bar_empty(s), (uint32_t)((v / S) & 1));
         const int vrow0 = (int)((blockIdx.x + (v / NA) * gridDim.x) * kTileM), va = (int)(v % NA);
-        tma_store_2d(&tmap_dzh_st, n0 + va * 32, vrow0, smem_u32(smem + s * L::kStage));
-        tma_store_2d(&tmap_dzl_st, n0 + va * 32, vrow0, smem_u32(smem + s * L::kStage + L::kSlot));
+        tma_store_2d(&tmap_dz_st, n0 + va * 32, vrow0, smem_u32(smem + s * L::kStage));
         tma_store_commit();
       }
       tma_store_wait_all();
@@ -337,8 +334,8 @@ struct DwTmaSmem {
 template <int NA, bool SPLIT>
 __global__ void __launch_bounds__(kTmaThreads, 1)
     gate_tc_dw_tma_kernel(const __grid_constant__ CUtensorMap tmap_h /* box [32 x 64], SW128 */,
-                          const __grid_constant__ CUtensorMap tmap_dzh /* box [32 x 64], SW128_ATOM_32B */,
-                          const __grid_constant__ CUtensorMap tmap_dzl, int64_t M,
+                          const __grid_constant__ CUtensorMap tmap_dz /* box [32 x 64], SW128_ATOM_32B */,
+                          int64_t M,
                           float* __restrict__ dw_partial /* [grid][n_total][128] */, int n0, int n_total) {
   using namespace tc;
   using L = DwTmaSmem<NA>;
@@ -370,8 +367,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   if (warp == 17) tmem_alloc(smem_u32(s_tmem), kTmemCols);
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmap_h);
-    tma_prefetch_desc(&tmap_dzh);
-    tma_prefetch_desc(&tmap_dzl);
+    tma_prefetch_desc(&tmap_dz);
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -414,6 +410,21 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         tmem_st16(ta + g * 16, hi);
         if (SPLIT) tmem_st16(ta + 64 + g * 16, lo);
       }
+      if (SPLIT) {
+        // dz arrived raw (fp32) in the MN-major atoms [0, NA): split it in place into tf32 hi (same place) and
+        // lo (atoms [NA, 2NA)).  Elementwise, so the swizzle does not matter: walk the 16-byte chunks.
+        uint8_t* dzs = smem + s * L::kStage + L::kStageH;
+#pragma unroll
+        for (int i = 0; i < NA * 2; ++i) {
+          const uint32_t o = (uint32_t)(threadIdx.x + 256 * i) * 16u;  // NA * 8 KB / 16 B = NA * 512 chunks
+          const float4 a = *reinterpret_cast<const float4*>(dzs + o);
+          const float4 hi4 = make_float4(tf32_hi(a.x), tf32_hi(a.y), tf32_hi(a.z), tf32_hi(a.w));
+          *reinterpret_cast<float4*>(dzs + o) = hi4;
+          *reinterpret_cast<float4*>(dzs + NA * L::kSlotD + o) =
+              make_float4(a.x - hi4.x, a.y - hi4.y, a.z - hi4.z, a.w - hi4.w);
+        }
+        fence_proxy_async_smem();
+      }
       tmem_wait_st();
       tc_fence_before_sync();
       mbar_arrive(bar_aready(hb));
@@ -428,14 +439,13 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           mbar_wait(bar_umma(s), (uint32_t)(((u / S) - 1) & 1));
         }
         const int row0 = (int)((blockIdx.x + u * gridDim.x) * L::kHalfRows);
-        mbar_expect_tx(bar_full(s), (uint32_t)(L::kStageH + (SPLIT ? L::kStageD : L::kStageD / 2)));
+        mbar_expect_tx(bar_full(s), (uint32_t)(L::kStageH + L::kStageD / 2));
         const uint32_t dst = smem_u32(smem + s * L::kStage);
 #pragma unroll
         for (int a = 0; a < 4; ++a) tma_load_2d(dst + a * L::kSlotH, &tmap_h, a * 32, row0, bar_full(s));
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
-          tma_load_2d(dst + L::kStageH + a * L::kSlotD, &tmap_dzh, n0 + a * 32, row0, bar_full(s));
-          if (SPLIT) tma_load_2d(dst + L::kStageH + (NA + a) * L::kSlotD, &tmap_dzl, n0 + a * 32, row0, bar_full(s));
+          tma_load_2d(dst + L::kStageH + a * L::kSlotD, &tmap_dz, n0 + a * 32, row0, bar_full(s));
         }
       }
     }
@@ -521,14 +531,13 @@ template <int NA_DH, int NA_DW, bool SPLIT>
 static int launch_bwd_tma(const float* dy, const float* h, const float* s, const float* z, const float* W,
                           const GateWs& ws, int64_t M, int N, float* dh, float* dw_partial, float* db_partial,
                           int grid, cudaStream_t st) {
-  float* dz_hi = ws.dz;
-  float* dz_lo = ws.dz + (size_t)M * N;
-  CUtensorMap t_dy, t_s, t_z, t_h, t_dzh, t_dzl, t_dh, t_dzh_st, t_dzl_st;
+  float* dz = ws.dz;  // [M, N] fp32, written once by B1, read once by B2
+  CUtensorMap t_dy, t_s, t_z, t_h, t_dz, t_dh, t_dz_st;
   if (!make_tmap_2d_sw(&t_dy, dy, M, N, kTileM, false) || !make_tmap_2d_sw(&t_s, s, M, N, kTileM, false) ||
       !make_tmap_2d_sw(&t_z, z, M, N, kTileM, false) || !make_tmap_2d_sw(&t_h, h, M, 128, 64, false) ||
-      !make_tmap_2d_sw(&t_dzh, dz_hi, M, N, 64, true) || !make_tmap_2d_sw(&t_dzl, dz_lo, M, N, 64, true) ||
+      !make_tmap_2d_sw(&t_dz, dz, M, N, 64, true) ||
       !make_tmap_2d_sw(&t_dh, dh ? dh : h, M, 128, kTileM, false) ||
-      !make_tmap_2d_sw(&t_dzh_st, dz_hi, M, N, kTileM, false) || !make_tmap_2d_sw(&t_dzl_st, dz_lo, M, N, kTileM, false))
+      !make_tmap_2d_sw(&t_dz_st, dz, M, N, kTileM, false))
     return VMTL_ECUDA;
   auto k1 = gate_tc_dh_tma_kernel<NA_DH, SPLIT>;
   auto k2 = gate_tc_dw_tma_kernel<NA_DW, SPLIT>;
@@ -537,13 +546,13 @@ static int launch_bwd_tma(const float* dy, const float* h, const float* s, const
     return VMTL_ECUDA;
   for (int n0 = 0; n0 < N; n0 += NA_DH * 32) {
     k1<<<grid, kTmaThreads, DhTmaSmem<NA_DH>::kBytes, st>>>(t_dy, t_s, t_z, t_dh, W, ws.coefA, ws.coefB, ws.mean,
-                                                             ws.invstd, ws.c1, ws.c2, M, t_dzh_st, t_dzl_st, dh,
+                                                             ws.invstd, ws.c1, ws.c2, M, t_dz_st, dh,
                                                              db_partial, n0, N, n0 != 0);
     const int rc = launch_status();
     if (rc != VMTL_OK) return rc;
   }
   for (int n0 = 0; n0 < N; n0 += NA_DW * 32) {
-    k2<<<grid, kTmaThreads, DwTmaSmem<NA_DW>::kBytes, st>>>(t_h, t_dzh, t_dzl, M, dw_partial, n0, N);
+    k2<<<grid, kTmaThreads, DwTmaSmem<NA_DW>::kBytes, st>>>(t_h, t_dz, M, dw_partial, n0, N);
     const int rc = launch_status();
     if (rc != VMTL_OK) return rc;
   }
