@@ -163,13 +163,16 @@ __global__ void __launch_bounds__(kEwThreads)
 __global__ void __launch_bounds__(kEwThreads)
     gate_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ s,
                           const float* __restrict__ z, int64_t M, int C4,
-                          const float* __restrict__ coefA, const float* __restrict__ coefB,
+                          const float* __restrict__ gamma, const float* __restrict__ beta,
                           const float* __restrict__ mean, const float* __restrict__ invstd,
                           float* __restrict__ ds, float* __restrict__ partial) {
   const EwMap m = ew_map(C4);
   float4 acc[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
   if (m.active) {
-    const float4 A = ldc4(coefA, m.g), B = ldc4(coefB, m.g), mu = ldc4(mean, m.g), rs = ldc4(invstd, m.g);
+    // folded BN coefficients straight from the saved statistics (no separate coefficient launch)
+    const float4 ga = ldc4(gamma, m.g), be = ldc4(beta, m.g), mu = ldc4(mean, m.g), rs = ldc4(invstd, m.g);
+    const float4 A = make_float4(ga.x * rs.x, ga.y * rs.y, ga.z * rs.z, ga.w * rs.w);
+    const float4 B = make_float4(be.x - mu.x * A.x, be.y - mu.y * A.y, be.z - mu.z * A.z, be.w - mu.w * A.w);
     for (int64_t p = (int64_t)blockIdx.x * m.rows + m.r; p < M; p += (int64_t)gridDim.x * m.rows) {
       const int64_t i = p * C4 + m.g;
       const float4 g = ld4(dy, i), sv = ld4(s, i), zv = ld4(z, i);
@@ -187,10 +190,15 @@ __global__ void __launch_bounds__(kEwThreads)
   ew_block_reduce<2>(acc, m, C4, partial + (int64_t)blockIdx.x * 8 * C4);
 }
 
+// also publishes the folded BN coefficients for phase B (same arithmetic as gate_bwd_stats_kernel)
 __global__ void gate_bwd_stats_finalize(const float* __restrict__ partial, int nparts, int64_t M, int N,
                                         int training, float* __restrict__ dgamma,
                                         float* __restrict__ dbeta, float* __restrict__ c1,
-                                        float* __restrict__ c2) {
+                                        float* __restrict__ c2, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, const float* __restrict__ mean,
+                                        const float* __restrict__ invstd, float* __restrict__ coefA,
+                                        float* __restrict__ coefB, float* __restrict__ mean_out,
+                                        float* __restrict__ invstd_out) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double sb, sg;
   block_colsum2(partial, nparts, 2 * (int64_t)N, c < N ? c : 0, N + (c < N ? c : 0), c < N, &sb, &sg);
@@ -199,6 +207,11 @@ __global__ void gate_bwd_stats_finalize(const float* __restrict__ partial, int n
   dgamma[c] = (float)sg;
   c1[c] = training ? (float)(sb / (double)M) : 0.f;
   c2[c] = training ? (float)(sg / (double)M) : 0.f;
+  const float a = gamma[c] * invstd[c];
+  coefA[c] = a;
+  coefB[c] = beta[c] - mean[c] * a;
+  mean_out[c] = mean[c];
+  invstd_out[c] = invstd[c];
 }
 
 // ---- backward: materialise dz (fp32 FFMA path) + db partials ------------------------------
@@ -235,6 +248,19 @@ __global__ void rows_sum_finalize(const float* __restrict__ partial, int nparts,
                                   float* __restrict__ out) {
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   const double s = block_colsum(partial, nparts, (int64_t)len, j < len ? j : 0, j < len);
+  if (threadIdx.x < 32 && j < len) out[j] = (float)s;
+}
+
+// two independent row sums in one launch: blocks [0, ceil(len_a / 32)) take a, the rest b
+__global__ void rows_sum_finalize2(const float* __restrict__ part_a, int nparts_a, int len_a, float* __restrict__ out_a,
+                                   const float* __restrict__ part_b, int nparts_b, int len_b, float* __restrict__ out_b) {
+  const int nb_a = (len_a + 31) / 32;
+  const bool is_a = (int)blockIdx.x < nb_a;  // block-uniform
+  const float* part = is_a ? part_a : part_b;
+  const int nparts = is_a ? nparts_a : nparts_b, len = is_a ? len_a : len_b;
+  float* out = is_a ? out_a : out_b;
+  const int j = ((int)blockIdx.x - (is_a ? 0 : nb_a)) * 32 + (threadIdx.x & 31);
+  const double s = block_colsum(part, nparts, (int64_t)len, j < len ? j : 0, j < len);
   if (threadIdx.x < 32 && j < len) out[j] = (float)s;
 }
 
@@ -393,19 +419,6 @@ extern "C" int vmtl_gate_fwd(const float* h, const float* s, const float* W, con
 }
 
 // coefA/B from saved statistics (backward re-derives them instead of trusting workspace reuse)
-__global__ void gate_coef_from_saved(const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     const float* __restrict__ mean, const float* __restrict__ invstd,
-                                     int N, float* __restrict__ coefA, float* __restrict__ coefB,
-                                     float* __restrict__ mean_out, float* __restrict__ invstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
-  const float a = gamma[c] * invstd[c];
-  coefA[c] = a;
-  coefB[c] = beta[c] - mean[c] * a;
-  mean_out[c] = mean[c];
-  invstd_out[c] = invstd[c];
-}
-
 extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, const float* z,
                              const float* W, const float* gamma, const float* beta,
                              const float* save_mean, const float* save_invstd, int training,
@@ -427,16 +440,14 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, co
   const int C4 = N / 4;
   const int split3 = precision == VMTL_GATE_TC_3XTF32;
 
-  gate_coef_from_saved<<<(N + 127) / 128, 128, 0, st>>>(gamma, beta, save_mean, save_invstd, N, ws.coefA,
-                                                        ws.coefB, ws.mean, ws.invstd);
-  if ((rc = launch_status()) != VMTL_OK) return rc;
   // phase A
   const int nparts = ew_grid(M, N, blocks_per_sm(gate_bwd_stats_kernel, kEwThreads, 0, 8));
-  gate_bwd_stats_kernel<<<nparts, kEwThreads, 0, st>>>(dy, s, z, M, C4, ws.coefA, ws.coefB, ws.mean,
-                                                       ws.invstd, ds, ws.partial);
+  gate_bwd_stats_kernel<<<nparts, kEwThreads, 0, st>>>(dy, s, z, M, C4, gamma, beta, save_mean, save_invstd,
+                                                       ds, ws.partial);
   if ((rc = launch_status()) != VMTL_OK) return rc;
   gate_bwd_stats_finalize<<<(N + 31) / 32, kFinThreads, 0, st>>>(ws.partial, nparts, M, N, training, dgamma,
-                                                           dbeta, ws.c1, ws.c2);
+                                                           dbeta, ws.c1, ws.c2, gamma, beta, save_mean,
+                                                           save_invstd, ws.coefA, ws.coefB, ws.mean, ws.invstd);
   if ((rc = launch_status()) != VMTL_OK) return rc;
 
   // phase B
@@ -446,9 +457,8 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, co
     rc = gate_tc_bwd_gemm(dy, h, s, z, W, ws, gamma, M, K, N, split3, dh, ws.gemm_partial, ws.gemm_slots,
                           &nslots, ws.partial, st);
     if (rc == VMTL_OK) {
-      rows_sum_finalize<<<(N * K + 31) / 32, kFinThreads, 0, st>>>(ws.gemm_partial, nslots, N * K, dW);
-      if ((rc = launch_status()) != VMTL_OK) return rc;
-      rows_sum_finalize<<<(N + 31) / 32, kFinThreads, 0, st>>>(ws.partial, nslots, N, dbias);
+      rows_sum_finalize2<<<(N * K + 31) / 32 + (N + 31) / 32, kFinThreads, 0, st>>>(
+          ws.gemm_partial, nslots, N * K, dW, ws.partial, nslots, N, dbias);
       return launch_status();
     }
     if (rc != VMTL_EUNSUPPORTED) return rc;

@@ -43,7 +43,7 @@ class _Prof:
 
 # kernels enqueued by one C call (for the `gpu_launches` claim in bench.py)
 _KERNELS_PER_CALL = {
-    "xstitch_fwd": 1, "xstitch_bwd": 2, "gate_fwd": 3, "gate_bwd": 6, "head_ce_fwd": 2,
+    "xstitch_fwd": 1, "xstitch_bwd": 2, "gate_fwd": 3, "gate_bwd": 5, "head_ce_fwd": 2,
     "head_ce_bwd": 2, "ce_logits_fwd": 2, "ce_logits_bwd": 1, "head_silog_fwd": 2,
     "head_silog_bwd": 2, "confusion_accum": 1, "depth_err_sums": 2, "seg_metrics": 1,
 }
