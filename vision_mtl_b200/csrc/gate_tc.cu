@@ -749,12 +749,12 @@ int gate_tc_bwd_gemm(const float* dy, const float* h, const float* s, const floa
     return !(e && e[0] == 'b');
   }();
   if (use_tma || N > 64) {
-#define VMTL_BWD_TMA(NDH, NDW)                                                                                   \
-  (split3 ? launch_bwd_tma<NDH, NDW, true>(dy, h, s, z, W, ws, M, N, dh, dw_partial, db_partial, grid, st)       \
-          : launch_bwd_tma<NDH, NDW, false>(dy, h, s, z, W, ws, M, N, dh, dw_partial, db_partial, grid, st))
-    if (N == 32) return VMTL_BWD_TMA(1, 1);
-    if (N % 128 == 0) return VMTL_BWD_TMA(2, 4);
-    return VMTL_BWD_TMA(2, 2);
+#define VMTL_BWD_TMA(NDW)                                                                                    \
+  (split3 ? launch_bwd_tma<NDW, true>(dy, h, s, z, W, ws, M, N, dh, dw_partial, db_partial, grid, st)         \
+          : launch_bwd_tma<NDW, false>(dy, h, s, z, W, ws, M, N, dh, dw_partial, db_partial, grid, st))
+    if (N == 32) return VMTL_BWD_TMA(1);
+    if (N % 128 == 0) return VMTL_BWD_TMA(4);
+    return VMTL_BWD_TMA(2);
 #undef VMTL_BWD_TMA
   }
   if (N == 32)

@@ -30,7 +30,7 @@ struct DhTmaSmem {
   static constexpr int kBytes = kMisc + 256 + 6 * 64 * 4 + 1024;
 };
 
-template <int NA, bool SPLIT>
+template <int NA, int NCH, bool SPLIT>
 __global__ void __launch_bounds__(kTmaThreads, 1)
     gate_tc_dh_tma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_s,
                           const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_dh,
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   using namespace tc;
   using L = DhTmaSmem<NA>;
   constexpr int S = L::kStages;
-  constexpr int N = NA * 32;
+  constexpr int N = NA * 32;        // gate columns per chunk; the launch covers NCH chunks from column n0
   constexpr int KH = 128;
   constexpr uint32_t kACols = 256;  // two A buffers of 128 columns: atom a -> hi [a*64, +32), lo [a*64+32, +32)
   constexpr uint32_t kTmemCols = 512;
@@ -87,6 +87,27 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     tma_prefetch_desc(&tmap_s);
     tma_prefetch_desc(&tmap_z);
   }
+  // W^T operand of chunk c: element (k, n) = W[n0 + c*N + n][k]; rows k, K-major along n, atom = n / 32
+  auto stage_w = [&](int c) {
+    const float* Wc = W + ((int64_t)n0 + c * N) * KH;
+    constexpr int PER = N * KH / 256;  // elements per converter thread
+#pragma unroll
+    for (int i0 = 0; i0 < PER; i0 += 8) {
+      float w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = __ldg(Wc + threadIdx.x + 256 * (i0 + i));  // 8 loads in flight, then the stores
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int e = threadIdx.x + 256 * (i0 + i);
+        const int n = e / KH, k = e - n * KH;
+        const float hi = tf32_hi(w[i]);
+        const uint32_t off = (uint32_t)((n >> 5) * L::kSlot) + sw128_off(k, (n & 31) >> 2) + (uint32_t)((n & 3) << 2);
+        *reinterpret_cast<float*>(sBhi + off) = hi;
+        if (SPLIT) *reinterpret_cast<float*>(sBlo + off) = w[i] - hi;
+      }
+    }
+    fence_proxy_async_smem();
+  };
   for (int i = threadIdx.x; i < N; i += kTmaThreads) {
     s_coef[0 * 64 + i] = coefA[n0 + i];
     s_coef[1 * 64 + i] = coefB[n0 + i];
@@ -95,17 +116,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     s_coef[4 * 64 + i] = c1[n0 + i];
     s_coef[5 * 64 + i] = c2[n0 + i];
   }
-  if (warp < 8) {  // W^T operand: element (k, n) = W[n][k]; rows k, K-major along n, atom = n / 32
-    for (int e = threadIdx.x; e < N * KH; e += 256) {
-      const int n = e / KH, k = e - n * KH;
-      const float w = W[(int64_t)n0 * KH + e];
-      const float hi = tf32_hi(w);
-      const uint32_t off = (uint32_t)((n >> 5) * L::kSlot) + sw128_off(k, (n & 31) >> 2) + (uint32_t)((n & 3) << 2);
-      *reinterpret_cast<float*>(sBhi + off) = hi;
-      if (SPLIT) *reinterpret_cast<float*>(sBlo + off) = w - hi;
-    }
-    fence_proxy_async_smem();
-  }
+  if (NCH == 1 && warp < 8) stage_w(0);  // several chunks: the converters restage W per (tile, chunk)
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -114,82 +125,105 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 
   const int64_t ntiles = (M + kTileM - 1) / kTileM;
   const int64_t nitems = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  float db_acc[NA];
+  float db_acc[NCH * NA];
 #pragma unroll
-  for (int a = 0; a < NA; ++a) db_acc[a] = 0.f;
+  for (int a = 0; a < NCH * NA; ++a) db_acc[a] = 0.f;
 
   if (warp < 8) {
     // ------------------------------------------------------------------ converters (thread = row)
     const int quad = warp & 3, ch = warp >> 2;  // lane quadrant, 16-column half of the atom
     const int row = quad * 32 + lane;
-    uint32_t ph_amma[2] = {0, 0};
-    int64_t u = 0;
+    int64_t u = 0;   // unit = (tile, chunk, atom): one TMA stage
+    int64_t tc = 0;  // (tile, chunk): one TMEM A buffer, one W^T chunk in shared memory
     for (int64_t it = 0; it < nitems; ++it) {
-      const int tb = (int)(it & 1);
       const int64_t grow = (blockIdx.x + it * gridDim.x) * kTileM + row;
       const bool row_ok = grow < M;
 #pragma unroll
-      for (int a = 0; a < NA; ++a, ++u) {
-        const int s = (int)(u % S);
-        mbar_wait(bar_full(s), (uint32_t)((u / S) & 1));
-        const uint8_t* st = smem + s * L::kStage;
-        float4 vdy[4], vs[4], vz[4];
+      for (int c = 0; c < NCH; ++c, ++tc) {
+        const int tb = (int)(tc & 1);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t o = sw128_off(row, ch * 4 + j);
-          vdy[j] = *reinterpret_cast<const float4*>(st + o);
-          vs[j] = *reinterpret_cast<const float4*>(st + L::kSlot + o);
-          vz[j] = *reinterpret_cast<const float4*>(st + 2 * L::kSlot + o);
-        }
-        float d[16];
+        for (int a = 0; a < NA; ++a, ++u) {
+          const int s = (int)(u % S);
+          mbar_wait(bar_full(s), (uint32_t)((u / S) & 1));
+          const uint8_t* st = smem + s * L::kStage;
+          float4 vdy[4], vs[4], vz[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c4 = (a * 32 + ch * 16 + j * 4) >> 2;
-          const float4 A = reinterpret_cast<const float4*>(s_coef)[0 * 16 + c4];
-          const float4 B = reinterpret_cast<const float4*>(s_coef)[1 * 16 + c4];
-          const float4 mu = reinterpret_cast<const float4*>(s_coef)[2 * 16 + c4];
-          const float4 rs = reinterpret_cast<const float4*>(s_coef)[3 * 16 + c4];
-          const float4 k1 = reinterpret_cast<const float4*>(s_coef)[4 * 16 + c4];
-          const float4 k2 = reinterpret_cast<const float4*>(s_coef)[5 * 16 + c4];
-          auto dz1 = [](float g, float sv, float zv, float A_, float B_, float mu_, float r_, float k1_, float k2_) {
-            const float act = sigmoidf_acc(fmaf(A_, zv, B_));
-            return A_ * (g * sv * act * (1.f - act) - k1_ - (zv - mu_) * r_ * k2_);
-          };
-          d[4 * j] = dz1(vdy[j].x, vs[j].x, vz[j].x, A.x, B.x, mu.x, rs.x, k1.x, k2.x);
-          d[4 * j + 1] = dz1(vdy[j].y, vs[j].y, vz[j].y, A.y, B.y, mu.y, rs.y, k1.y, k2.y);
-          d[4 * j + 2] = dz1(vdy[j].z, vs[j].z, vz[j].z, A.z, B.z, mu.z, rs.z, k1.z, k2.z);
-          d[4 * j + 3] = dz1(vdy[j].w, vs[j].w, vz[j].w, A.w, B.w, mu.w, rs.w, k1.w, k2.w);
-        }
-        float hi[16], lo[16];
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t o = sw128_off(row, ch * 4 + j);
+            vdy[j] = *reinterpret_cast<const float4*>(st + o);
+            vs[j] = *reinterpret_cast<const float4*>(st + L::kSlot + o);
+            vz[j] = *reinterpret_cast<const float4*>(st + 2 * L::kSlot + o);
+          }
+          float d[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          if (!row_ok) d[e] = 0.f;
-          hi[e] = tf32_hi(d[e]);
-          lo[e] = d[e] - hi[e];
-        }
-        // dz (fp32, B2 splits it itself) leaves through the stage buffer: once every converter holds its
-        // inputs in registers, slot 0 of the stage is rewritten (swizzled) and the TMA warp bulk-stores it
-        // before it refills the stage -- no row-per-thread global stores.
-        named_barrier_sync(3, 256);
+          for (int j = 0; j < 4; ++j) {
+            float4 A, B, mu, rs, k1, k2;
+            if (NCH == 1) {
+              const int c4 = (a * 32 + ch * 16 + j * 4) >> 2;
+              A = reinterpret_cast<const float4*>(s_coef)[0 * 16 + c4];
+              B = reinterpret_cast<const float4*>(s_coef)[1 * 16 + c4];
+              mu = reinterpret_cast<const float4*>(s_coef)[2 * 16 + c4];
+              rs = reinterpret_cast<const float4*>(s_coef)[3 * 16 + c4];
+              k1 = reinterpret_cast<const float4*>(s_coef)[4 * 16 + c4];
+              k2 = reinterpret_cast<const float4*>(s_coef)[5 * 16 + c4];
+            } else {  // several chunks: per-column coefficients straight from global (L1-resident, 6 KB)
+              const int col = n0 + c * N + a * 32 + ch * 16 + j * 4;
+              A = __ldg(reinterpret_cast<const float4*>(coefA + col));
+              B = __ldg(reinterpret_cast<const float4*>(coefB + col));
+              mu = __ldg(reinterpret_cast<const float4*>(mean + col));
+              rs = __ldg(reinterpret_cast<const float4*>(invstd + col));
+              k1 = __ldg(reinterpret_cast<const float4*>(c1 + col));
+              k2 = __ldg(reinterpret_cast<const float4*>(c2 + col));
+            }
+            auto dz1 = [](float g, float sv, float zv, float A_, float B_, float mu_, float r_, float k1_, float k2_) {
+              const float act = sigmoidf_acc(fmaf(A_, zv, B_));
+              return A_ * (g * sv * act * (1.f - act) - k1_ - (zv - mu_) * r_ * k2_);
+            };
+            d[4 * j] = dz1(vdy[j].x, vs[j].x, vz[j].x, A.x, B.x, mu.x, rs.x, k1.x, k2.x);
+            d[4 * j + 1] = dz1(vdy[j].y, vs[j].y, vz[j].y, A.y, B.y, mu.y, rs.y, k1.y, k2.y);
+            d[4 * j + 2] = dz1(vdy[j].z, vs[j].z, vz[j].z, A.z, B.z, mu.z, rs.z, k1.z, k2.z);
+            d[4 * j + 3] = dz1(vdy[j].w, vs[j].w, vz[j].w, A.w, B.w, mu.w, rs.w, k1.w, k2.w);
+          }
+          float hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t o = sw128_off(row, ch * 4 + j);
-          *reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + o) = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+          for (int e = 0; e < 16; ++e) {
+            if (!row_ok) d[e] = 0.f;
+            hi[e] = tf32_hi(d[e]);
+            lo[e] = d[e] - hi[e];
+          }
+          // dz (fp32, B2 splits it itself) leaves through the stage buffer: once every converter holds its
+          // inputs in registers, slot 0 of the stage is rewritten (swizzled) and the TMA warp bulk-stores it
+          // before it refills the stage -- no row-per-thread global stores.
+          named_barrier_sync(3, 256);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t o = sw128_off(row, ch * 4 + j);
+            *reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + o) = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(bar_empty(s));  // = "dz staged": the TMA warp stores it, then reuses the stage
+          if (a == 0) {
+            if (NCH > 1) {
+              // W^T of this chunk replaces the previous one: the MMAs of (tile, chunk) tc-1 must be done
+              // (they retire in order, so tc-2 -- the previous user of this A buffer -- is done too)
+              if (tc >= 1) {
+                mbar_wait(bar_amma((int)((tc - 1) & 1)), (uint32_t)(((tc - 1) >> 1) & 1));
+                tc_fence_after_sync();
+              }
+              stage_w(c);
+            } else if (tc >= 2) {  // the MMAs of tile tc-2 have consumed this A buffer
+              mbar_wait(bar_amma(tb), (uint32_t)(((tc >> 1) - 1) & 1));
+              tc_fence_after_sync();
+            }
+          }
+          const uint32_t ta = tmem_base + (((uint32_t)quad * 32) << 16) + (uint32_t)(tb * 128 + a * 64 + ch * 16);
+          tmem_st16(ta, hi);
+          if (SPLIT) tmem_st16(ta + 32, lo);
+          tmem_wait_st();
+          tc_fence_before_sync();
+          mbar_arrive(bar_aready(tb, a));
+          db_acc[c * NA + a] += butterfly_colsum<16>(d, lane);  // lanes l and l+16 both hold column (l % 16)
         }
-        fence_proxy_async_smem();
-        mbar_arrive(bar_empty(s));  // = "dz staged": the TMA warp stores it, then reuses the stage
-        if (a == 0 && it >= 2) {  // the MMAs of tile it-2 have consumed this A buffer
-          mbar_wait(bar_amma(tb), ph_amma[tb]);
-          ph_amma[tb] ^= 1u;
-          tc_fence_after_sync();
-        }
-        const uint32_t ta = tmem_base + (((uint32_t)quad * 32) << 16) + (uint32_t)(tb * 128 + a * 64 + ch * 16);
-        tmem_st16(ta, hi);
-        if (SPLIT) tmem_st16(ta + 32, lo);
-        tmem_wait_st();
-        tc_fence_before_sync();
-        mbar_arrive(bar_aready(tb, a));
-        db_acc[a] += butterfly_colsum<16>(d, lane);  // lanes l and l+16 both hold column (l % 16)
       }
     }
   } else if (warp < 16) {
@@ -239,32 +273,31 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   } else if (warp == 16) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int64_t u = 0;
-      for (int64_t it = 0; it < nitems; ++it) {
-        const int row0 = (int)((blockIdx.x + it * gridDim.x) * kTileM);
-        for (int a = 0; a < NA; ++a, ++u) {
-          const int s = (int)(u % S);
-          if (u >= S) {  // unit u-S: its dz is staged in this stage -> bulk-store it, then the stage is free
-            mbar_wait(bar_empty(s), (uint32_t)(((u / S) - 1) & 1));
-            const int64_t v = u - S;
-            const int vrow0 = (int)((blockIdx.x + (v / NA) * gridDim.x) * kTileM), va = (int)(v % NA);
-            tma_store_2d(&tmap_dz_st, n0 + va * 32, vrow0, smem_u32(smem + s * L::kStage));
-            tma_store_commit();
-            tma_store_wait_read();
-          }
-          mbar_expect_tx(bar_full(s), (uint32_t)L::kStage);
-          const uint32_t dst = smem_u32(smem + s * L::kStage);
-          tma_load_2d(dst, &tmap_dy, n0 + a * 32, row0, bar_full(s));
-          tma_load_2d(dst + L::kSlot, &tmap_s, n0 + a * 32, row0, bar_full(s));
-          tma_load_2d(dst + 2 * L::kSlot, &tmap_z, n0 + a * 32, row0, bar_full(s));
+      constexpr int UPT = NCH * NA;  // units (32-column atoms) per tile
+      // unit v -> first row of its tile / first gate column of its atom
+      auto unit_row0 = [&](int64_t v) { return (int)((blockIdx.x + (v / UPT) * gridDim.x) * kTileM); };
+      auto unit_col0 = [&](int64_t v) { return n0 + (int)(v % UPT) * 32; };
+      const int64_t nunits = nitems * UPT;
+      for (int64_t u = 0; u < nunits; ++u) {
+        const int s = (int)(u % S);
+        if (u >= S) {  // unit u-S: its dz is staged in this stage -> bulk-store it, then the stage is free
+          mbar_wait(bar_empty(s), (uint32_t)(((u / S) - 1) & 1));
+          tma_store_2d(&tmap_dz_st, unit_col0(u - S), unit_row0(u - S), smem_u32(smem + s * L::kStage));
+          tma_store_commit();
+          tma_store_wait_read();
         }
+        mbar_expect_tx(bar_full(s), (uint32_t)L::kStage);
+        const uint32_t dst = smem_u32(smem + s * L::kStage);
+        const int row0 = unit_row0(u), col0 = unit_col0(u);
+        tma_load_2d(dst, &tmap_dy, col0, row0, bar_full(s));
+        tma_load_2d(dst + L::kSlot, &tmap_s, col0, row0, bar_full(s));
+        tma_load_2d(dst + 2 * L::kSlot, &tmap_z, col0, row0, bar_full(s));
       }
-      const int64_t nunits = nitems * NA;  // drain: the last min(S, nunits) units are still staged
+      // drain: the last min(S, nunits) units are still staged
       for (int64_t v = nunits > S ? nunits - S : 0; v < nunits; ++v) {
         const int s = (int)(v % S);
         mbar_wait(bar_empty(s), (uint32_t)((v / S) & 1));
-        const int vrow0 = (int)((blockIdx.x + (v / NA) * gridDim.x) * kTileM), va = (int)(v % NA);
-        tma_store_2d(&tmap_dz_st, n0 + va * 32, vrow0, smem_u32(smem + s * L::kStage));
+        tma_store_2d(&tmap_dz_st, unit_col0(v), unit_row0(v), smem_u32(smem + s * L::kStage));
         tma_store_commit();
       }
       tma_store_wait_all();
@@ -273,28 +306,33 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = idesc_tf32(kTileM, KH, 0, 0);
     const uint32_t bH = smem_u32(sBhi), bL = smem_u32(sBlo);
+    int64_t tc = 0;
     for (int64_t it = 0; it < nitems; ++it) {
       const int b = (int)(it & 1);
       const uint32_t d_tmem = tmem_d0 + (uint32_t)(b * KH);
       if (it >= 2) mbar_wait(bar_dfree(b), (uint32_t)(((it >> 1) - 1) & 1));
 #pragma unroll
-      for (int a = 0; a < NA; ++a) {
-        mbar_wait(bar_aready(b, a), (uint32_t)((it >> 1) & 1));
-        tc_fence_after_sync();
+      for (int c = 0; c < NCH; ++c, ++tc) {  // dh of the tile accumulates in TMEM over all column chunks
+        const int tb = (int)(tc & 1);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t a_hi = tmem_base + (uint32_t)(b * 128 + a * 64 + ks * 8);
-          const uint64_t dBh = smem_desc_sw128(bH + a * L::kSlot + ks * 32, 16, 1024);
-          if (SPLIT) {
-            mma_tf32_ts(d_tmem, a_hi + 32, dBh, idesc, (a | ks) != 0);
-            mma_tf32_ts(d_tmem, a_hi, smem_desc_sw128(bL + a * L::kSlot + ks * 32, 16, 1024), idesc, 1);
-            mma_tf32_ts(d_tmem, a_hi, dBh, idesc, 1);
-          } else {
-            mma_tf32_ts(d_tmem, a_hi, dBh, idesc, (a | ks) != 0);
+        for (int a = 0; a < NA; ++a) {
+          mbar_wait(bar_aready(tb, a), (uint32_t)((tc >> 1) & 1));
+          tc_fence_after_sync();
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t a_hi = tmem_base + (uint32_t)(tb * 128 + a * 64 + ks * 8);
+            const uint64_t dBh = smem_desc_sw128(bH + a * L::kSlot + ks * 32, 16, 1024);
+            if (SPLIT) {
+              mma_tf32_ts(d_tmem, a_hi + 32, dBh, idesc, (c | a | ks) != 0);
+              mma_tf32_ts(d_tmem, a_hi, smem_desc_sw128(bL + a * L::kSlot + ks * 32, 16, 1024), idesc, 1);
+              mma_tf32_ts(d_tmem, a_hi, dBh, idesc, 1);
+            } else {
+              mma_tf32_ts(d_tmem, a_hi, dBh, idesc, (c | a | ks) != 0);
+            }
           }
         }
+        mma_commit(bar_amma(tb));  // A buffer tb and the W^T chunk are consumed
       }
-      mma_commit(bar_amma(b));
       mma_commit(bar_dfull(b));
     }
   }
@@ -302,17 +340,18 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   __syncthreads();
   if (warp == 17) tmem_dealloc(tmem_base, kTmemCols);
   // db partial of this CTA: the four quadrant warps of each 16-column group, fixed order
-  float* s_red = reinterpret_cast<float*>(smem);  // [8 converter warps][NA][16]
+  constexpr int NAT = NCH * NA;                  // 32-column atoms of this launch
+  float* s_red = reinterpret_cast<float*>(smem);  // [8 converter warps][NAT][16]
   if (warp < 8 && lane < 16) {
 #pragma unroll
-    for (int a = 0; a < NA; ++a) s_red[(warp * NA + a) * 16 + lane] = db_acc[a];
+    for (int a = 0; a < NAT; ++a) s_red[(warp * NAT + a) * 16 + lane] = db_acc[a];
   }
   __syncthreads();
-  for (int col = threadIdx.x; col < N; col += kTmaThreads) {
+  for (int col = threadIdx.x; col < NAT * 32; col += kTmaThreads) {
     const int a = col >> 5, ch = (col >> 4) & 1, l = col & 15;
     float acc = 0.f;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc += s_red[((ch * 4 + q) * NA + a) * 16 + l];
+    for (int q = 0; q < 4; ++q) acc += s_red[((ch * 4 + q) * NAT + a) * 16 + l];
     db_partial[(int64_t)blockIdx.x * n_total + n0 + col] = acc;
   }
 }
@@ -523,11 +562,23 @@ inline bool make_tmap_2d_sw(CUtensorMap* m, const float* base, int64_t rows, int
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// N = any multiple of 64 (or 32): dh runs in column passes of NA_DH*32 gate columns (W^T hi/lo, the
-// stages and the dh staging fill the 227 KB of shared memory at 64 columns), passes after the first
-// accumulate into dh with TMA reduce-adds; dW runs in passes of NA_DW*32 columns (2*NA_DW*32 accumulator
-// columns in TMEM), each pass re-reading h.
-template <int NA_DH, int NA_DW, bool SPLIT>
+// N = 32 or any multiple of 64.  dh: one launch covers up to 256 gate columns (NCH chunks of 64 whose dh
+// contributions accumulate in TMEM, W^T restaged per chunk); wider gates take further launches that add into
+// dh with TMA reduce-adds.  dW: passes of NA_DW*32 columns (2*NA_DW*32 accumulator columns in TMEM), each
+// pass re-reading h.
+template <int NA_DH, int NCH, bool SPLIT>
+static int launch_dh_tma(const CUtensorMap& t_dy, const CUtensorMap& t_s, const CUtensorMap& t_z, const CUtensorMap& t_dh,
+                         const CUtensorMap& t_dz_st, const float* W, const GateWs& ws, int64_t M, int N, float* dh,
+                         float* db_partial, int n0, int grid, cudaStream_t st) {
+  auto k1 = gate_tc_dh_tma_kernel<NA_DH, NCH, SPLIT>;
+  if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, DhTmaSmem<NA_DH>::kBytes) != cudaSuccess)
+    return VMTL_ECUDA;
+  k1<<<grid, kTmaThreads, DhTmaSmem<NA_DH>::kBytes, st>>>(t_dy, t_s, t_z, t_dh, W, ws.coefA, ws.coefB, ws.mean, ws.invstd,
+                                                           ws.c1, ws.c2, M, t_dz_st, dh, db_partial, n0, N, n0 != 0);
+  return launch_status();
+}
+
+template <int NA_DW, bool SPLIT>
 static int launch_bwd_tma(const float* dy, const float* h, const float* s, const float* z, const float* W,
                           const GateWs& ws, int64_t M, int N, float* dh, float* dw_partial, float* db_partial,
                           int grid, cudaStream_t st) {
@@ -539,17 +590,28 @@ static int launch_bwd_tma(const float* dy, const float* h, const float* s, const
       !make_tmap_2d_sw(&t_dh, dh ? dh : h, M, 128, kTileM, false) ||
       !make_tmap_2d_sw(&t_dz_st, dz, M, N, kTileM, false))
     return VMTL_ECUDA;
-  auto k1 = gate_tc_dh_tma_kernel<NA_DH, SPLIT>;
   auto k2 = gate_tc_dw_tma_kernel<NA_DW, SPLIT>;
-  if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, DhTmaSmem<NA_DH>::kBytes) != cudaSuccess ||
-      cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, DwTmaSmem<NA_DW>::kBytes) != cudaSuccess)
+  if (cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, DwTmaSmem<NA_DW>::kBytes) != cudaSuccess)
     return VMTL_ECUDA;
-  for (int n0 = 0; n0 < N; n0 += NA_DH * 32) {
-    k1<<<grid, kTmaThreads, DhTmaSmem<NA_DH>::kBytes, st>>>(t_dy, t_s, t_z, t_dh, W, ws.coefA, ws.coefB, ws.mean,
-                                                             ws.invstd, ws.c1, ws.c2, M, t_dz_st, dh,
-                                                             db_partial, n0, N, n0 != 0);
-    const int rc = launch_status();
+  if (N == 32) {
+    const int rc = launch_dh_tma<1, 1, SPLIT>(t_dy, t_s, t_z, t_dh, t_dz_st, W, ws, M, N, dh, db_partial, 0, grid, st);
     if (rc != VMTL_OK) return rc;
+  } else {
+    // One launch over several chunks pays a W^T restage per (tile, chunk); it wins only where a CTA has a
+    // single tile anyway (then the alternative is one latency-bound launch per chunk).  Otherwise: one
+    // 64-column pass per launch, later passes add into dh.
+    const int cols_per_launch = (M + kTileM - 1) / kTileM <= grid ? 256 : 64;
+    for (int n0 = 0; n0 < N; n0 += cols_per_launch) {
+      const int nch = (N - n0 >= cols_per_launch ? cols_per_launch : N - n0) / 64;
+      int rc;
+      switch (nch) {
+        case 1: rc = launch_dh_tma<2, 1, SPLIT>(t_dy, t_s, t_z, t_dh, t_dz_st, W, ws, M, N, dh, db_partial, n0, grid, st); break;
+        case 2: rc = launch_dh_tma<2, 2, SPLIT>(t_dy, t_s, t_z, t_dh, t_dz_st, W, ws, M, N, dh, db_partial, n0, grid, st); break;
+        case 3: rc = launch_dh_tma<2, 3, SPLIT>(t_dy, t_s, t_z, t_dh, t_dz_st, W, ws, M, N, dh, db_partial, n0, grid, st); break;
+        default: rc = launch_dh_tma<2, 4, SPLIT>(t_dy, t_s, t_z, t_dh, t_dz_st, W, ws, M, N, dh, db_partial, n0, grid, st); break;
+      }
+      if (rc != VMTL_OK) return rc;
+    }
   }
   for (int n0 = 0; n0 < N; n0 += NA_DW * 32) {
     k2<<<grid, kTmaThreads, DwTmaSmem<NA_DW>::kBytes, st>>>(t_h, t_dz, M, dw_partial, n0, N);
