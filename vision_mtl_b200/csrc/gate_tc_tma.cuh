@@ -114,9 +114,16 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   if (warp == 16 && lane == 0) tma_prefetch_desc(&tmap_h);
   for (int i = threadIdx.x; i < NC; i += kTmaThreads) s_bias[i] = bias[chunk * NC + i];
   if (warp < 8) {  // stacked W operand: row n = W_hi[n], row NC + n = W_lo[n]; K-major, SW128
-    for (int q = threadIdx.x; q < NC * 32; q += 256) {
+    constexpr int PER = NC * 32 / 256;  // float4 per thread (4 or 8): all loads in flight, then the stores
+    float4 wv[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+      wv[i] = __ldg(reinterpret_cast<const float4*>(W) + (int64_t)chunk * NC * 32 + threadIdx.x + 256 * i);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int q = threadIdx.x + 256 * i;
       const int n = q >> 5, kc = q & 31;
-      const float4 w = __ldg(reinterpret_cast<const float4*>(W) + (int64_t)chunk * NC * 32 + q);
+      const float4 w = wv[i];
       const float4 hi = make_float4(tf32_hi(w.x), tf32_hi(w.y), tf32_hi(w.z), tf32_hi(w.w));
       uint8_t* atom = sB + (kc >> 3) * L::kAtomB;
       *reinterpret_cast<float4*>(atom + sw128_off(n, kc & 7)) = hi;
