@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--no-graph-events", action="store_true",
+                    help="skip the instrumented graph copy; per-op times then come from the eager pass")
     ap.add_argument("--workload", choices=list(WORKLOADS), default="csnet")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
@@ -354,6 +356,26 @@ def main():
     ms_e2e = ev2.elapsed_time(ev3)
     _phase("e2e region done")
 
+    # ---- per-op device time INSIDE graph replays: an instrumented copy of the step graph whose library
+    # calls are bracketed by external CUDA events (replayed after the timed region; single GPU only)
+    events_from = ("eager pass of the identical step right before the timed graph replays, device kept "
+                   "busy ahead of the host so events bracket kernel execution") if graphed is not None else "the timed region"
+    if graphed is not None and world == 1 and not args.no_graph_events:
+        try:
+            prof = GraphedTrainStep(module, opt, resident, warmup=1, after_backward=metric_exchange, profile=True)
+            for _ in range(3):
+                prof()
+            torch.cuda.synchronize()
+            gstats = prof.kernel_stats()
+            if gstats and all(v["ms"] > 0 for v in gstats.values()):
+                kstats, ksteps = gstats, 1
+                events_from = ("external CUDA events around every library call inside an instrumented copy of the "
+                               "step graph (third replay, right after the timed region)")
+            del prof
+        except Exception as exc:  # keep the eager-pass numbers
+            sys.stderr.write(f"[bench] in-graph event pass unavailable: {exc!r}\n")
+        _phase("in-graph event pass done")
+
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -384,9 +406,7 @@ def main():
         roofline = {"bound": "hbm", "kernel": "vmtl_" + name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                     "peak_source": peak_src,
-                    "events_from": ("eager pass of the identical step right before the timed graph replays, device kept "
-                                    "busy ahead of the host so events bracket kernel execution"
-                                    if graphed is not None else "the timed region"),
+                    "events_from": events_from,
                     "launches_timed": d["calls"], "avg_launch_ms": d["ms"] / d["calls"],
                     "algorithmic_bytes_per_launch": d["bytes"] / d["calls"]}
     line = {

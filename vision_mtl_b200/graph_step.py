@@ -22,9 +22,12 @@ from .lit_module import MTLModule
 
 class GraphedTrainStep:
     def __init__(self, module: MTLModule, optimizer: torch.optim.Optimizer, example_batch: dict,
-                 warmup: int = 3, after_backward: t.Optional[t.Callable[[], None]] = None):
+                 warmup: int = 3, after_backward: t.Optional[t.Callable[[], None]] = None,
+                 profile: bool = False):
         """``example_batch`` fixes shapes/dtypes; ``after_backward`` (e.g. a metric all-reduce) is
-        captured between backward and the optimizer step."""
+        captured between backward and the optimizer step.  ``profile=True`` captures a pair of external
+        CUDA events around every library call, so ``kernel_stats()`` reports per-op device time of the
+        last replay (an instrumented copy for measurement; the event nodes cost a little step time)."""
         self.module, self.optimizer = module, optimizer
         dev = example_batch["img"].device
         self.static = {k: torch.empty_like(v) for k, v in example_batch.items()}
@@ -41,11 +44,28 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         optimizer.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
-            self.loss = self._eager_step()
-            self.scalars = module.last_step_scalars
-            self.confusion = module.last_confusion
+        self.kernel_records: list = []
+        if profile:
+            from . import ops
+
+            with ops.kernel_timing() as records, torch.cuda.graph(self.graph):
+                self._capture()
+            self.kernel_records = list(records)
+        else:
+            with torch.cuda.graph(self.graph):
+                self._capture()
         self._trim_step_outputs()
+
+    def _capture(self) -> None:
+        self.loss = self._eager_step()
+        self.scalars = self.module.last_step_scalars
+        self.confusion = self.module.last_confusion
+
+    def kernel_stats(self) -> dict:
+        """name -> {calls, ms, bytes, gbps} of the last replay (``profile=True``; synchronise first)."""
+        from . import ops
+
+        return ops.summarize_timing(self.kernel_records)
 
     def _eager_step(self) -> torch.Tensor:
         self.optimizer.zero_grad(set_to_none=True)

@@ -85,8 +85,11 @@ def _call(name: str, algo_bytes: int, *args) -> None:
     fn = getattr(_lib.load(), "vmtl_" + name)
     _Prof.launches += _KERNELS_PER_CALL.get(name, 1)
     if _Prof.enabled:
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
+        # inside a stream capture the events must be "external" to become timing-capable graph nodes
+        # (they are then re-recorded by every replay)
+        ext = torch.cuda.is_current_stream_capturing()
+        e0 = torch.cuda.Event(enable_timing=True, external=ext)
+        e1 = torch.cuda.Event(enable_timing=True, external=ext)
         e0.record()
         rc = fn(*args)
         e1.record()
