@@ -22,6 +22,7 @@
 
 #include "gate_internal.cuh"
 #include "tcgen05.cuh"
+#include "tma_host.cuh"
 
 namespace vmtl {
 

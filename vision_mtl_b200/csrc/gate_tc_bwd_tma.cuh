@@ -544,24 +544,6 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   if (warp == 17) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-#ifndef CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
-#define VMTL_NO_ATOM32B 1
-#endif
-
-// [rows, cols] fp32, box [box_rows x 32 floats]; mn32 selects the 128B swizzle with 32-byte atoms
-inline bool make_tmap_2d_sw(CUtensorMap* m, const float* base, int64_t rows, int cols, int box_rows, bool mn32) {
-  PFN_encodeTiled enc = tma_encode_fn();
-  if (!enc) return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
-  const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
-  const cuuint32_t estr[2] = {1u, 1u};
-  const CUtensorMapSwizzle sw = mn32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 // N = 32 or any multiple of 64.  dh: one launch covers up to 256 gate columns (NCH chunks of 64 whose dh
 // contributions accumulate in TMEM, W^T restaged per chunk); wider gates take further launches that add into
 // dh with TMA reduce-adds.  dW: passes of NA_DW*32 columns (2*NA_DW*32 accumulator columns in TMEM), each

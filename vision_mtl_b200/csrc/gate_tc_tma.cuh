@@ -36,35 +36,6 @@ struct TmaSmem {
   static constexpr int kBytes = kMisc + 256 + 64 * 4 + 1024;
 };
 
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-inline PFN_encodeTiled tma_encode_fn() {
-  static PFN_encodeTiled fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return reinterpret_cast<PFN_encodeTiled>(p);
-  }();
-  return fn;
-}
-
-// row-major fp32 [rows, cols] matrix, box = [box_rows x 32 floats], 128B swizzle, OOB rows -> 0
-inline bool make_tmap_2d(CUtensorMap* m, const float* base, int64_t rows, int cols, int box_rows) {
-  PFN_encodeTiled enc = tma_encode_fn();
-  if (!enc) return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
-  const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
-  const cuuint32_t estr[2] = {1u, 1u};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <int NC, int NCH, bool SPLIT>
 __global__ void __launch_bounds__(kTmaThreads, 1)
     gate_tc_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_h, const float* __restrict__ W,

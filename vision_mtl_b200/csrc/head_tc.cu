@@ -22,6 +22,7 @@
 
 #include "head_internal.cuh"
 #include "tcgen05.cuh"
+#include "tma_host.cuh"
 
 namespace vmtl {
 
@@ -38,29 +39,6 @@ struct HtSmem {
   static constexpr int kConf = kMisc + 512;             // uint32 [32*32]
   static constexpr int kBytes = kConf + 32 * 32 * 4 + 1024;
 };
-
-typedef CUresult (*PFN_encodeTiledH)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static bool ht_make_tmap(CUtensorMap* m, const float* base, int64_t rows) {
-  static PFN_encodeTiledH enc = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return reinterpret_cast<PFN_encodeTiledH>(p);
-  }();
-  if (!enc) return false;
-  const cuuint64_t dims[2] = {32, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {32 * sizeof(float)};
-  const cuuint32_t box[2] = {32u, (cuuint32_t)kHtTile};
-  const cuuint32_t estr[2] = {1u, 1u};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
 
 __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
   asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -364,7 +342,7 @@ int head_ce_tc_fwd(const float* feat, const float* W, const float* b, const int6
                    int64_t* conf, cudaStream_t st) {
   if (C > 32 || P < 1) return VMTL_EUNSUPPORTED;
   CUtensorMap tmap;
-  if (!ht_make_tmap(&tmap, feat, P)) return VMTL_ECUDA;
+  if (!make_tmap_2d(&tmap, feat, P, 32, kHtTile)) return VMTL_ECUDA;
   const int64_t ntiles = (P + kHtTile - 1) / kHtTile;
   int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
   if (grid > max_blocks) grid = max_blocks;

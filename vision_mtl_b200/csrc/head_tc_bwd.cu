@@ -25,6 +25,7 @@
 
 #include "head_internal.cuh"
 #include "tcgen05.cuh"
+#include "tma_host.cuh"
 
 namespace vmtl {
 
@@ -46,29 +47,6 @@ struct HbSmem {
   static constexpr int kMisc = kW2 + 64 * 128;
   static constexpr int kBytes = kMisc + 512 + 1024;
 };
-
-typedef CUresult (*PFN_encodeTiledB)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static bool hb_make_tmap(CUtensorMap* m, const float* base, int64_t rows) {
-  static PFN_encodeTiledB enc = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return reinterpret_cast<PFN_encodeTiledB>(p);
-  }();
-  if (!enc) return false;
-  const cuuint64_t dims[2] = {32, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {32 * sizeof(float)};
-  const cuuint32_t box[2] = {32u, (cuuint32_t)kHbTile};
-  const cuuint32_t estr[2] = {1u, 1u};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
 
 #ifdef VMTL_HT_PROF
 __device__ long long g_hb_prof[148][8];
@@ -458,7 +436,8 @@ int head_ce_tc_bwd(const float* feat, const float* W, const float* b, const int6
                    int max_blocks, int* grid_out, cudaStream_t st) {
   if (C > 32 || P < 1) return VMTL_EUNSUPPORTED;
   CUtensorMap tmap_f, tmap_df;
-  if (!hb_make_tmap(&tmap_f, feat, P) || !hb_make_tmap(&tmap_df, dfeat ? dfeat : feat, P)) return VMTL_ECUDA;
+  if (!make_tmap_2d(&tmap_f, feat, P, 32, kHbTile) || !make_tmap_2d(&tmap_df, dfeat ? dfeat : feat, P, 32, kHbTile))
+    return VMTL_ECUDA;
   const int64_t ntiles = (P + kHbTile - 1) / kHbTile;
   int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
   if (grid > max_blocks) grid = max_blocks;
