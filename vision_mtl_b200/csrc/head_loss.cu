@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include "head_internal.cuh"
+#include "tcgen05.cuh"
 #include "vmtl_common.cuh"
 
 namespace vmtl {
@@ -533,6 +534,122 @@ __global__ void __launch_bounds__(kLossThreads)
 }
 
 // ---------------------------------------------------------------------------------------
+// NHWC logits through bulk async copies.  A 256-pixel tile of [P, C] logits is ONE contiguous run of
+// 256*C floats: a single cp.async.bulk brings it into shared memory as is (double-buffered, issued one
+// tile ahead by thread 0), each thread then reads its own pixel's C floats (stride C words).  No
+// per-element staging stores, no index arithmetic; the backward sends dlogits back the same way
+// (cp.async.bulk shared -> global).  The ragged last tile (npx < 256) is read / written directly.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
+               : "memory");
+}
+
+template <int CPAD, bool BWD>
+__global__ void __launch_bounds__(kLossThreads)
+    ce_logits_nhwc_bulk_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target, int64_t P, int C,
+                               int64_t ignore_index, double* __restrict__ partial, uint8_t* __restrict__ pred,
+                               unsigned long long* __restrict__ conf, const double* __restrict__ fwd_out,
+                               const float* __restrict__ gscale, float* __restrict__ dlogits) {
+  using namespace tc;
+  extern __shared__ __align__(128) uint8_t s_raw[];  // [2 stages][256*C floats] | conf hist (fwd) | 2 mbarriers
+  const uint32_t tile_bytes = (uint32_t)kLossThreads * (uint32_t)C * 4u;
+  float* s_tile = reinterpret_cast<float*>(s_raw);
+  unsigned int* s_conf = reinterpret_cast<unsigned int*>(s_raw + 2 * tile_bytes);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_raw + 2 * tile_bytes + ((!BWD && conf) ? (size_t)C * C * 4 : 0));
+  s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_bar) + 7) & ~(uintptr_t)7);
+  const uint32_t bar0 = smem_u32(s_bar);
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_mbar_init();
+  }
+  if (!BWD && conf)
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_conf[i] = 0u;
+  __syncthreads();
+
+  const float scale = BWD ? gscale[0] / (float)fwd_out[1] : 0.f;
+  const int64_t nfull = P / kLossThreads;  // full tiles only; the ragged tail is handled below
+  const int64_t nt = blockIdx.x < nfull ? (nfull - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto tile_of = [&](int64_t i) { return blockIdx.x + i * gridDim.x; };
+  auto issue = [&](int64_t i) {  // thread 0: tile i -> stage i & 1
+    const uint32_t b = bar0 + 8u * (uint32_t)(i & 1);
+    mbar_expect_tx(b, tile_bytes);
+    bulk_load_1d(smem_u32(s_raw) + (uint32_t)(i & 1) * tile_bytes, logits + tile_of(i) * kLossThreads * C, tile_bytes, b);
+  };
+  double loss_acc = 0.0, n_acc = 0.0;
+
+  auto pixel = [&](float (&l)[CPAD], int64_t p) {  // forward bookkeeping or dl, for one pixel held in l[]
+    const int64_t t = __ldg(target + p);
+    PixelCE<CPAD> ce;
+    ce.run(l, C);
+    const bool valid = target_valid(t, C, ignore_index);
+    if (!BWD) {
+      if (pred) pred[p] = (uint8_t)ce.arg;
+      if (valid) {
+        loss_acc += (double)(ce.lse - pick<CPAD>(l, (int)t));
+        n_acc += 1.0;
+        if (conf) atomicAdd(&s_conf[(int)t * C + ce.arg], 1u);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CPAD; ++c) l[c] = valid ? (ce.prob(l[c]) - (c == (int)t ? 1.f : 0.f)) * scale : 0.f;
+    }
+  };
+
+  if (threadIdx.x == 0 && nt > 0) issue(0);
+  for (int64_t i = 0; i < nt; ++i) {
+    const int s = (int)(i & 1);
+    if (threadIdx.x == 0 && i + 1 < nt) {
+      if (BWD) tma_store_wait_read();  // the store of tile i-1 has finished reading stage s^1
+      issue(i + 1);
+    }
+    mbar_wait(bar0 + 8u * (uint32_t)s, (uint32_t)((i >> 1) & 1));
+    float* row = s_tile + (size_t)s * (tile_bytes / 4) + (size_t)threadIdx.x * C;
+    float l[CPAD];
+#pragma unroll
+    for (int c = 0; c < CPAD; ++c) l[c] = VMTL_HAS_CLASS(c, C) ? row[c] : 0.f;
+    const int64_t p = tile_of(i) * kLossThreads + threadIdx.x;
+    pixel(l, p);
+    if (BWD) {
+#pragma unroll
+      for (int c = 0; c < CPAD; ++c)
+        if (VMTL_HAS_CLASS(c, C)) row[c] = l[c];
+      fence_proxy_async_smem();
+    }
+    __syncthreads();  // stage s fully consumed (fwd) / fully rewritten with dl (bwd)
+    if (BWD && threadIdx.x == 0) {
+      bulk_store_1d(dlogits + tile_of(i) * kLossThreads * C, smem_u32(s_raw) + (uint32_t)s * tile_bytes, tile_bytes);
+      tma_store_commit();
+    }
+  }
+  if (BWD && threadIdx.x == 0) tma_store_wait_all();
+  // ragged tail: the last P % 256 pixels, one CTA, straight from / to global memory
+  const int64_t p_tail = nfull * kLossThreads + threadIdx.x;
+  if (blockIdx.x == (unsigned)(nfull % gridDim.x) && p_tail < P) {
+    float l[CPAD];
+#pragma unroll
+    for (int c = 0; c < CPAD; ++c) l[c] = VMTL_HAS_CLASS(c, C) ? __ldg(logits + p_tail * C + c) : 0.f;
+    pixel(l, p_tail);
+    if (BWD) {
+#pragma unroll
+      for (int c = 0; c < CPAD; ++c)
+        if (VMTL_HAS_CLASS(c, C)) dlogits[p_tail * C + c] = l[c];
+    }
+  }
+  if (!BWD) {
+    __syncthreads();
+    if (conf) flush_conf(s_conf, C * C, conf);
+    block_partial2(loss_acc, n_acc, partial);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Depth head + sigmoid + SILog moments + error sums.
 // LPP lanes cooperate on one pixel (LPP = Cin/4 float4 per pixel); LPP == 1 means the
 // input already is the depth logit (basic / csnet).
@@ -772,6 +889,14 @@ __global__ void silog_bwd_finalize(const float* __restrict__ partial, int nblock
     db[0] = (float)s;
 }
 
+static bool ce_bulk_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("VMTL_CE_LOGITS");
+    return !(e && strcmp(e, "staged") == 0);
+  }();
+  return on;
+}
+
 static int cpad_for(int C) { return C <= 16 ? 16 : (C <= 20 ? 20 : (C <= 32 ? 32 : 0)); }
 
 }  // namespace vmtl
@@ -905,7 +1030,21 @@ extern "C" int vmtl_ce_logits_fwd(const float* logits, const int64_t* target, in
                                                                    ignore_index, partial, pred, cf); \
   } while (0)
   const bool nh = layout == VMTL_LAYOUT_NHWC;
-  if (cpad == 16) { if (nh) VMTL_CEF(16, true); else VMTL_CEF(16, false); }
+  if (nh && ce_bulk_enabled()) {  // NHWC: tiles arrive by bulk async copy (VMTL_CE_LOGITS=staged: per-element staging)
+    const size_t bsmem = 2 * (size_t)kLossThreads * C * 4 + (conf ? (size_t)C * C * 4 : 0) + 32;
+#define VMTL_CEFB(CP)                                                                                           \
+  do {                                                                                                          \
+    auto kern = ce_logits_nhwc_bulk_kernel<CP, false>;                                                          \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);                        \
+    grid = loss_grid(P, kLossThreads, blocks_per_sm(kern, kLossThreads, bsmem, 8));                             \
+    kern<<<grid, kLossThreads, bsmem, st>>>(logits, target, P, C, ignore_index, partial, pred, cf, nullptr,     \
+                                            nullptr, nullptr);                                                  \
+  } while (0)
+    if (cpad == 16) VMTL_CEFB(16);
+    else if (cpad == 20) VMTL_CEFB(20);
+    else VMTL_CEFB(32);
+#undef VMTL_CEFB
+  } else if (cpad == 16) { if (nh) VMTL_CEF(16, true); else VMTL_CEF(16, false); }
   else if (cpad == 20) { if (nh) VMTL_CEF(20, true); else VMTL_CEF(20, false); }
   else { if (nh) VMTL_CEF(32, true); else VMTL_CEF(32, false); }
 #undef VMTL_CEF
@@ -934,6 +1073,22 @@ extern "C" int vmtl_ce_logits_bwd(const float* logits, const int64_t* target, in
                                                                    ignore_index, fwd_out, gscale, dlogits); \
   } while (0)
   const bool nh = layout == VMTL_LAYOUT_NHWC;
+  if (nh && ce_bulk_enabled()) {
+    const size_t bsmem = 2 * (size_t)kLossThreads * C * 4 + 32;
+#define VMTL_CEBB(CP)                                                                                           \
+  do {                                                                                                          \
+    auto kern = ce_logits_nhwc_bulk_kernel<CP, true>;                                                           \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);                        \
+    const int grid = loss_grid(P, kLossThreads, blocks_per_sm(kern, kLossThreads, bsmem, 8));                   \
+    kern<<<grid, kLossThreads, bsmem, st>>>(logits, target, P, C, ignore_index, nullptr, nullptr, nullptr,      \
+                                            fwd_out, gscale, dlogits);                                          \
+  } while (0)
+    if (cpad == 16) VMTL_CEBB(16);
+    else if (cpad == 20) VMTL_CEBB(20);
+    else VMTL_CEBB(32);
+#undef VMTL_CEBB
+    return launch_status();
+  }
   if (cpad == 16) { if (nh) VMTL_CEB(16, true); else VMTL_CEB(16, false); }
   else if (cpad == 20) { if (nh) VMTL_CEB(20, true); else VMTL_CEB(20, false); }
   else { if (nh) VMTL_CEB(32, true); else VMTL_CEB(32, false); }
