@@ -43,7 +43,7 @@ extern "C" {
 
 /* gate contraction precision */
 #define VMTL_GATE_FP32_FFMA 0 /* CUDA-core fp32 FMA contraction                        */
-#define VMTL_GATE_TC_3XTF32 1 /* tcgen05 kind::tf32, hi/lo split, 3 MMAs (fp32-grade) */
+#define VMTL_GATE_TC_3XTF32 1 /* tcgen05 kind::tf32, hi/lo split (3xTF32, fp32-grade) */
 #define VMTL_GATE_TC_TF32 2   /* tcgen05 kind::tf32, single pass                      */
 
 /* logits layouts for the *_logits loss kernels */

@@ -18,7 +18,7 @@ struct GateWs {
   int partial_rows;
   float* gemm_partial;  // [gemm_slots][N*K] split-K / per-CTA dW partials
   int gemm_slots;
-  float* dz;            // [M,N] (fp32 FFMA backward only)
+  float* dz;            // [M,N] fp32: written once by the dh kernel, read once by the dW kernel
 };
 
 inline size_t gate_ws_floats(int64_t M, int K, int N, int precision, int backward, GateWs* ws,
@@ -41,7 +41,7 @@ inline size_t gate_ws_floats(int64_t M, int K, int N, int precision, int backwar
   w.gemm_slots = backward ? sm_count() * 2 : 0;
   w.gemm_partial = take((size_t)w.gemm_slots * N * K);
   (void)precision;
-  w.dz = backward ? take((size_t)M * N * 2) : nullptr;  // dz, or its tf32 hi and lo parts (TMA kernels)
+  w.dz = backward ? take((size_t)M * N) : nullptr;
   if (ws) *ws = w;
   return off;
 }
