@@ -308,9 +308,37 @@ def main():
             return graphed(None if batch is resident else batch)
         return eager_step(batch)
 
+    # e2e input pipeline (graph mode): every step's batch is copied from pinned host memory on a copy stream
+    # into one of two device staging buffers WHILE the previous step's graph runs, then moved into the
+    # graph's static inputs by a device copy -- the usual prefetching loader, one H2D of the full batch per
+    # step inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    staging = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+    staged = [torch.cuda.Event(), torch.cuda.Event()]     # H2D into staging[b] complete
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]   # staging[b] copied into the static inputs
+    e2e_state = {"i": 0, "primed": False}
+
+    def prefetch(b):
+        copy_stream.wait_event(consumed[b])
+        with torch.cuda.stream(copy_stream):
+            for k, v in host.items():
+                staging[b][k].copy_(v, non_blocking=True)
+            staged[b].record(copy_stream)
+
     def e2e_step():
         if graphed is not None:
-            graphed(host)  # H2D copies into the static inputs, one graph launch
+            if not e2e_state["primed"]:
+                for ev in consumed:
+                    ev.record()
+                prefetch(0)
+                e2e_state["primed"] = True
+            b = e2e_state["i"] & 1
+            e2e_state["i"] += 1
+            torch.cuda.current_stream().wait_event(staged[b])
+            graphed.load(staging[b])          # device copy into the static inputs
+            consumed[b].record()
+            prefetch(b ^ 1)                   # next step's H2D overlaps this step's graph
+            graphed()
         else:
             eager_step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
         return module.last_step_scalars.cpu()  # one D2H copy: loss + 4 metrics
