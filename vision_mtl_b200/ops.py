@@ -247,6 +247,13 @@ class GateFunction(torch.autograd.Function):
         _call("gate_bwd", nbytes, _p(dy), _p(h), _p(s), _p(z), _p(w2), _p(gamma.detach()),
               _p(beta.detach()), _p(mean), _p(invstd), 1 if ctx.training else 0, ctx.precision, M, K, N,
               _p(dh), _p(ds), _p(dW), _p(dbias), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream())
+        if ctx.precision != 0 and N > 64 and K == 128 and N % 64 == 0:
+            # wider gates run extra column launches (csrc/gate_tc_bwd_tma.cuh): dh per 64 columns, or per 256
+            # when every CTA owns a single 128-row tile; dW per 128 (64) columns
+            one_tile = (M + 127) // 128 <= lib.vmtl_sm_count()
+            n_dh = -(-N // 256) if one_tile else N // 64
+            n_dw = N // 128 if N % 128 == 0 else N // 64
+            _Prof.launches += (n_dh - 1) + (n_dw - 1)
         return (dh, ds, dW.reshape(ctx.wshape), dbias, dgamma, dbeta, None, None, None, None, None, None)
 
 
