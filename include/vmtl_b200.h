@@ -80,13 +80,16 @@ int vmtl_xstitch_bwd(const float* const* dy_host, const float* const* x_host,
  * MTAN attention gate:  y = s * sigmoid(BN(h @ W^T + bias)).
  * Replaces conv2 -> bn2 -> sigmoid -> mul at vision_mtl/models/mtan_model.py:71-75
  * (encoder) and :158-162 (decoder).
- *   h [M,K]  hidden activations (K % 32 == 0, K <= 256; the reference uses K = 128)
- *   s [M,N]  shared features    (N % 16 == 0, 16 <= N <= 256)
+ *   h [M,K]  hidden activations (the reference uses K = 128)
+ *   s [M,N]  shared features    (N % 4 == 0, N <= 1024)
  *   W [N,K], bias/gamma/beta/running_mean/running_var [N]
+ * The tcgen05 kernels cover K == 128 with N == 32 or N % 64 == 0; any other shape (and
+ * VMTL_GATE_FP32_FFMA) runs the CUDA-core contraction of the same library.
  * training != 0: batch statistics (biased var for normalisation, unbiased for the
  *   running update, momentum as nn.BatchNorm2d); z = h@W^T+bias is written to save_z and
  *   (mean, invstd) to save_mean/save_invstd for the backward.  running_* may be NULL.
- * training == 0: running statistics, single pass, save_* may be NULL.
+ * training == 0: running statistics, save_* may be NULL (save_z == NULL: single fused pass on the
+ *   tensor-core path, z is never stored).
  * ---------------------------------------------------------------------------------- */
 /* backward != 0: size for vmtl_gate_bwd, else for vmtl_gate_fwd */
 size_t vmtl_gate_workspace_bytes(int64_t M, int K, int N, int precision, int backward);

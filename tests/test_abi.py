@@ -34,7 +34,8 @@ def test_library_exports_every_declared_symbol():
     # sizing helpers are host-only and must work without a GPU
     assert typed.vmtl_xstitch_bwd_workspace_bytes(2, 1 << 20, 32, 1) > 0
     assert typed.vmtl_gate_workspace_bytes(1 << 20, 128, 32, 1, 1) > 4 * (1 << 20) * 32
-    assert typed.vmtl_gate_workspace_bytes(1 << 20, 100, 32, 1, 1) == 0  # unsupported K
+    assert typed.vmtl_gate_workspace_bytes(1 << 20, 100, 32, 1, 1) > 0   # any K: CUDA-core contraction
+    assert typed.vmtl_gate_workspace_bytes(1 << 20, 128, 30, 1, 1) == 0  # N must be a multiple of 4
     assert typed.vmtl_loss_workspace_bytes(1 << 20) > 0
 
 

@@ -20,8 +20,9 @@ SOURCES = ["capi.cu", "xstitch.cu", "metrics.cu", "head_loss.cu", "head_tc.cu", 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+OBJ_DIR = os.path.join(PKG_DIR, "build")  # git-ignored; one object per translation unit
 
 
 def _nvcc() -> str:
@@ -39,23 +40,52 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > lib_m for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into ``vision_mtl_b200/libvmtl_b200.so``."""
-    if not force and not is_stale():
-        return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC]
+def _compile_one(nvcc: str, src: str, extra: list, verbose: bool) -> str:
+    """One translation unit -> object file; recompiled only when it or a header is newer."""
+    obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+    path = os.path.join(CSRC, src)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps = [path, os.path.join(INCLUDE, "vmtl_b200.h"), os.path.abspath(__file__), *headers]
+    flags_tag = obj + ".flags"
+    flags = " ".join(NVCC_FLAGS + extra)
+    if (os.path.exists(obj) and os.path.exists(flags_tag) and open(flags_tag).read() == flags
+            and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps)):
+        return obj
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", INCLUDE, "-I", CSRC, "-c", path, "-o", obj]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += os.environ.get("VMTL_NVCC_EXTRA", "").split()  # e.g. -DVMTL_HT_PROF for the role-timing probes
-    cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    tmp = LIB_PATH + ".tmp"
-    cmd += ["-o", tmp, "-lcuda"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
-        raise RuntimeError("nvcc failed building libvmtl_b200.so")
+        raise RuntimeError(f"nvcc failed on {src}")
     if verbose:
         sys.stderr.write(proc.stderr)
+    with open(flags_tag, "w") as f:
+        f.write(flags)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a (translation units in parallel) and link
+    ``vision_mtl_b200/libvmtl_b200.so``."""
+    if not force and not is_stale():
+        return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+
+    nvcc = _nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJ_DIR):
+            os.remove(os.path.join(OBJ_DIR, f))
+    extra = os.environ.get("VMTL_NVCC_EXTRA", "").split()  # e.g. -DVMTL_HT_PROF for the role-timing probes
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(lambda s: _compile_one(nvcc, s, extra, verbose), SOURCES))
+    tmp = LIB_PATH + ".tmp"
+    proc = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", tmp, "-lcuda"],
+                          capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("linking libvmtl_b200.so failed")
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 

@@ -341,8 +341,8 @@ static int sgemm64(const float* A, const float* B, float* C, const float* bias, 
 }
 
 static int gate_check(int64_t M, int K, int N, int precision) {
-  if (M < 1 || K < 32 || N < 16) return VMTL_EINVAL;
-  if (K % 32 != 0 || K > 256 || N % 16 != 0 || N > 256) return VMTL_EUNSUPPORTED;
+  if (M < 1 || K < 1 || N < 4) return VMTL_EINVAL;
+  if (N % 4 != 0 || N > 4 * kEwThreads) return VMTL_EUNSUPPORTED;  // float4 channel groups, one block row
   if (precision != VMTL_GATE_FP32_FFMA && precision != VMTL_GATE_TC_3XTF32 && precision != VMTL_GATE_TC_TF32)
     return VMTL_EINVAL;
   return VMTL_OK;
@@ -383,11 +383,12 @@ extern "C" int vmtl_gate_fwd(const float* h, const float* s, const float* W, con
                                                              ws.invstd, ws.coefA, ws.coefB, save_mean,
                                                              save_invstd);
     if ((rc = launch_status()) != VMTL_OK) return rc;
-    if (precision != VMTL_GATE_FP32_FFMA && !save_z)  // inference: single fused pass, z never stored
+    const bool tc = precision != VMTL_GATE_FP32_FFMA && gate_tc_supported(K, N);
+    if (tc && !save_z)  // inference: single fused pass, z never stored
       return gate_tc_fwd_eval(h, s, W, bias, ws.coefA, ws.coefB, M, K, N, split3, y, st);
-    if (!save_z) return VMTL_EINVAL;  // the CUDA-core path needs a z buffer even in eval mode
-    float* zbuf = save_z;
-    if (precision != VMTL_GATE_FP32_FFMA) {
+    float* zbuf = save_z ? save_z : ws.zbuf;  // the CUDA-core path stages z (workspace when not saved)
+    if (!zbuf) return VMTL_EWORKSPACE;
+    if (tc) {
       int unused = 0;  // a backward will follow: keep z (batch partials are computed but unused)
       rc = gate_tc_fwd_gemm(h, W, bias, M, K, N, split3, zbuf, ws.partial, ws.partial_rows, &unused, st);
     } else {
@@ -399,7 +400,7 @@ extern "C" int vmtl_gate_fwd(const float* h, const float* s, const float* W, con
   }
 
   int nparts = 0;
-  if (precision != VMTL_GATE_FP32_FFMA) {
+  if (precision != VMTL_GATE_FP32_FFMA && gate_tc_supported(K, N)) {
     rc = gate_tc_fwd_gemm(h, W, bias, M, K, N, split3, save_z, ws.partial, ws.partial_rows, &nparts, st);
     if (rc != VMTL_OK) return rc;
   } else {

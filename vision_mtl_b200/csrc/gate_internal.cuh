@@ -19,7 +19,12 @@ struct GateWs {
   float* gemm_partial;  // [gemm_slots][N*K] split-K / per-CTA dW partials
   int gemm_slots;
   float* dz;            // [M,N] fp32: written once by the dh kernel, read once by the dW kernel
+  float* zbuf;          // [M,N] forward scratch for z when the caller passes no save_z and the shape is
+                        // outside the tensor-core kernels (CUDA-core path, eval mode)
 };
+
+// shapes the tcgen05 kernels cover (everything else takes the CUDA-core path in gate.cu)
+bool gate_tc_supported(int K, int N);
 
 inline size_t gate_ws_floats(int64_t M, int K, int N, int precision, int backward, GateWs* ws,
                              float* base) {
@@ -40,8 +45,9 @@ inline size_t gate_ws_floats(int64_t M, int K, int N, int precision, int backwar
   w.partial = take((size_t)w.partial_rows * 2 * N);
   w.gemm_slots = backward ? sm_count() * 2 : 0;
   w.gemm_partial = take((size_t)w.gemm_slots * N * K);
-  (void)precision;
   w.dz = backward ? take((size_t)M * N) : nullptr;
+  const bool tc = precision != VMTL_GATE_FP32_FFMA && gate_tc_supported(K, N);
+  w.zbuf = (!backward && !tc) ? take((size_t)M * N) : nullptr;
   if (ws) *ws = w;
   return off;
 }

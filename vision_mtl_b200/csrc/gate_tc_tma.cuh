@@ -1,5 +1,6 @@
-// MTAN gate forward (training mode, K = 128, N in {32, 64}): TMA -> smem -> TMEM -> tcgen05.
-// Included by gate_tc.cu.
+// MTAN gate forward (K = 128, N = 32 or a multiple of 64): TMA -> smem -> TMEM -> tcgen05.
+// Included by gate_tc.cu.  TRAIN: z + per-CTA column partials of (sum z, sum z^2).  EVAL: BatchNorm folded
+// into (coefA, coefB), y = s * sigmoid(coefA * z + coefB) straight from the accumulator, z never stored.
 //
 // Why this shape (measured on B200, scratch/mma_probe*.cu and ncu, profiles/):
 //  * the contraction is HBM-bound only if >= ~128 KB per SM are in flight; a register-staged
@@ -33,18 +34,23 @@ struct TmaSmem {
   static constexpr int kAtomB = 2 * NC * 128;              // rows [0,NC) = W_hi, [NC,2NC) = W_lo
   static constexpr int kB = kStages * kStage;
   static constexpr int kMisc = kB + 4 * kAtomB;
-  static constexpr int kBytes = kMisc + 256 + 64 * 4 + 1024;
+  static constexpr int kBytes = kMisc + 256 + 3 * 64 * 4 + 1024;
 };
 
-template <int NC, int NCH, bool SPLIT>
+// N = NC * nch.  nch > 1: column chunks of NC are spread over CTAs (chunk = blockIdx.x % nch, fixed per CTA so
+// its W operand is staged once); gridDim.x is a multiple of nch.
+template <int NC, bool SPLIT, bool EVAL>
 __global__ void __launch_bounds__(kTmaThreads, 1)
     gate_tc_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_h, const float* __restrict__ W,
-                           const float* __restrict__ bias, int64_t M, float* __restrict__ z_out,
-                           float* __restrict__ partial /* [gridDim.x][2][N] */) {
+                           const float* __restrict__ bias, int64_t M, int nch,
+                           float* __restrict__ out /* TRAIN: z ; EVAL: y */,
+                           float* __restrict__ partial /* TRAIN: [gridDim.x][2][N] */,
+                           const float* __restrict__ s_in /* EVAL: shared features [M,N] */,
+                           const float* __restrict__ coefA, const float* __restrict__ coefB) {
   using namespace tc;
   using L = TmaSmem<NC>;
   constexpr int S = L::kStages;
-  constexpr int N = NC * NCH;  // N > 64: column chunks of NC are spread over CTAs (chunk = blockIdx.x % NCH)
+  const int N = NC * nch;
   constexpr int V = NC / 2;                  // columns per epilogue thread
   constexpr int DC = SPLIT ? 2 * NC : NC;    // accumulator columns per buffer
   constexpr uint32_t kACols = 256;           // TMEM: A halves [h*128, +64) hi, [+64, +128) lo
@@ -55,11 +61,13 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::kMisc);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::kMisc + 192);
   float* s_bias = reinterpret_cast<float*>(smem + L::kMisc + 256);
+  float* s_cA = s_bias + 64;
+  float* s_cB = s_cA + 64;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunk = blockIdx.x % NCH;          // this CTA's column chunk (fixed: W staged once)
-  const int cslot = blockIdx.x / NCH;          // position among the CTAs that share the chunk
-  const int cgrid = gridDim.x / NCH;
+  const int chunk = blockIdx.x % nch;          // this CTA's column chunk (fixed: W staged once)
+  const int cslot = blockIdx.x / nch;          // position among the CTAs that share the chunk
+  const int cgrid = gridDim.x / nch;
   const uint32_t bar0 = smem_u32(s_bar);
   auto bar_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };            // [0,4)
   auto bar_empty = [&](int s) { return bar0 + 32u + 8u * (uint32_t)s; };     // [4,8)
@@ -83,7 +91,13 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   }
   if (warp == 17) tmem_alloc(smem_u32(s_tmem), kTmemCols);
   if (warp == 16 && lane == 0) tma_prefetch_desc(&tmap_h);
-  for (int i = threadIdx.x; i < NC; i += kTmaThreads) s_bias[i] = bias[chunk * NC + i];
+  for (int i = threadIdx.x; i < NC; i += kTmaThreads) {
+    s_bias[i] = bias[chunk * NC + i];
+    if (EVAL) {
+      s_cA[i] = coefA[chunk * NC + i];
+      s_cB[i] = coefB[chunk * NC + i];
+    }
+  }
   if (warp < 8) {  // stacked W operand: row n = W_hi[n], row NC + n = W_lo[n]; K-major, SW128
     constexpr int PER = NC * 32 / 256;  // float4 per thread (4 or 8): all loads in flight, then the stores
     float4 wv[PER];
@@ -157,12 +171,18 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     const int ew = warp - 8;
     for (int64_t it = 0; it < nitems; ++it) {
       const int b = (int)(it & 1);
-      mbar_wait(bar_dfull(b), (uint32_t)((it >> 1) & 1));
-      tc_fence_after_sync();
       const int64_t tile = cslot + it * cgrid;
       const int col0 = (ew >> 2) * V;
       const int64_t grow = tile * kTileM + (ew & 3) * 32 + lane;
       const bool row_ok = grow < M;
+      float4 sv[EVAL ? V / 4 : 1];
+      if (EVAL && row_ok) {  // the shared features of this row: in flight while the MMAs finish
+        const float4* sp = reinterpret_cast<const float4*>(s_in + grow * N + chunk * NC + col0);
+#pragma unroll
+        for (int j = 0; j < V / 4; ++j) sv[j] = ldg_stream(sp + j);
+      }
+      mbar_wait(bar_dfull(b), (uint32_t)((it >> 1) & 1));
+      tc_fence_after_sync();
       const uint32_t taddr = tmem_d0 + (((uint32_t)(ew & 3) * 32) << 16) + (uint32_t)(b * DC + col0);
       float v[V];
 #pragma unroll
@@ -179,8 +199,23 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       }
       tc_fence_before_sync();
       mbar_arrive(bar_dfree(b));
+      if (EVAL) {
+        if (row_ok) {
+          float4* yp = reinterpret_cast<float4*>(out + grow * N + chunk * NC + col0);
+#pragma unroll
+          for (int j = 0; j < V; j += 4) {
+            float4 y;
+            y.x = sv[j / 4].x * sigmoidf_acc(fmaf(s_cA[col0 + j], v[j], s_cB[col0 + j]));
+            y.y = sv[j / 4].y * sigmoidf_acc(fmaf(s_cA[col0 + j + 1], v[j + 1], s_cB[col0 + j + 1]));
+            y.z = sv[j / 4].z * sigmoidf_acc(fmaf(s_cA[col0 + j + 2], v[j + 2], s_cB[col0 + j + 2]));
+            y.w = sv[j / 4].w * sigmoidf_acc(fmaf(s_cA[col0 + j + 3], v[j + 3], s_cB[col0 + j + 3]));
+            stg_stream(yp + j / 4, y);
+          }
+        }
+        continue;
+      }
       if (row_ok) {
-        float4* zp = reinterpret_cast<float4*>(z_out + grow * N + chunk * NC + col0);
+        float4* zp = reinterpret_cast<float4*>(out + grow * N + chunk * NC + col0);
 #pragma unroll
         for (int j = 0; j < V; j += 4) stg_stream(zp + j / 4, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
       }
@@ -237,6 +272,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 17) tmem_dealloc(tmem_base, kTmemCols);
+  if (EVAL) return;
   // per-CTA column partials: the four quadrant warps of a column half, summed in fixed order
   double* s_red = reinterpret_cast<double*>(smem);  // [8 epilogue warps][V][2]; stage 0 is idle now
   if (warp >= 8 && warp < 16 && lane < V) {
@@ -259,17 +295,38 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   }
 }
 
-template <int NC, int NCH, bool SPLIT>
-static int launch_fwd_tma(const float* h, const float* W, const float* bias, int64_t M, float* z, float* partial,
-                          int grid, cudaStream_t st) {
+template <int NC, bool SPLIT, bool EVAL>
+static int launch_fwd_tma(const float* h, const float* W, const float* bias, int64_t M, int nch, float* out,
+                          float* partial, const float* s_in, const float* coefA, const float* coefB, int grid,
+                          cudaStream_t st) {
   using L = TmaSmem<NC>;
   CUtensorMap tmap;
   if (!make_tmap_2d(&tmap, h, M, 128, kTileM)) return VMTL_ECUDA;
-  auto kern = gate_tc_fwd_tma_kernel<NC, NCH, SPLIT>;
+  auto kern = gate_tc_fwd_tma_kernel<NC, SPLIT, EVAL>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes) != cudaSuccess)
     return VMTL_ECUDA;
-  kern<<<grid, kTmaThreads, L::kBytes, st>>>(tmap, W, bias, M, z, partial);
+  kern<<<grid, kTmaThreads, L::kBytes, st>>>(tmap, W, bias, M, nch, out, partial, s_in, coefA, coefB);
   return launch_status();
+}
+
+// grid of the forward: (row tile, column chunk) items over the SMs, a multiple of nch
+static int fwd_tma_grid(int64_t M, int nch) {
+  const int64_t items = ((M + kTileM - 1) / kTileM) * nch;
+  int grid = (int)(items < sm_count() ? items : sm_count());
+  grid = grid / nch * nch;
+  return grid < nch ? nch : grid;
+}
+
+template <bool EVAL>
+static int dispatch_fwd_tma(const float* h, const float* W, const float* bias, int64_t M, int N, int split3,
+                            float* out, float* partial, const float* s_in, const float* coefA, const float* coefB,
+                            int grid, cudaStream_t st) {
+  const int nch = N <= 64 ? 1 : N / 64;
+  if (N == 32)
+    return split3 ? launch_fwd_tma<32, true, EVAL>(h, W, bias, M, 1, out, partial, s_in, coefA, coefB, grid, st)
+                  : launch_fwd_tma<32, false, EVAL>(h, W, bias, M, 1, out, partial, s_in, coefA, coefB, grid, st);
+  return split3 ? launch_fwd_tma<64, true, EVAL>(h, W, bias, M, nch, out, partial, s_in, coefA, coefB, grid, st)
+                : launch_fwd_tma<64, false, EVAL>(h, W, bias, M, nch, out, partial, s_in, coefA, coefB, grid, st);
 }
 
 }  // namespace vmtl

@@ -889,14 +889,6 @@ __global__ void silog_bwd_finalize(const float* __restrict__ partial, int nblock
     db[0] = (float)s;
 }
 
-static bool ce_bulk_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("VMTL_CE_LOGITS");
-    return !(e && strcmp(e, "staged") == 0);
-  }();
-  return on;
-}
-
 static int cpad_for(int C) { return C <= 16 ? 16 : (C <= 20 ? 20 : (C <= 32 ? 32 : 0)); }
 
 }  // namespace vmtl
@@ -920,12 +912,8 @@ extern "C" int vmtl_head_ce_fwd(const float* feat, const float* W, const float* 
   if (!aligned16(feat)) return VMTL_EALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* partial = static_cast<double*>(workspace);
-  // tensor-core projection (head_tc.cu) unless VMTL_HEAD_FWD=ffma; tiny inputs keep the CUDA-core kernel
-  static const bool use_tc = [] {
-    const char* e = getenv("VMTL_HEAD_FWD");
-    return !(e && strcmp(e, "ffma") == 0);
-  }();
-  if (use_tc && P >= 128) {
+  // tensor-core projection (head_tc.cu); inputs smaller than one tile keep the CUDA-core kernel
+  if (P >= 128) {
     int g = 0;
     const int max_blocks = (int)(workspace_bytes / (2 * sizeof(double)));
     const int rc = head_ce_tc_fwd(feat, W, b, target, P, C, ignore_index, partial, max_blocks, &g, pred, conf, st);
@@ -964,11 +952,7 @@ extern "C" int vmtl_head_ce_bwd(const float* feat, const float* W, const float* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int ROW = cpad * (kHeadCin + 1);
   float* partial = static_cast<float*>(workspace);
-  static const bool use_tc = [] {  // VMTL_HEAD_BWD=ffma selects the CUDA-core kernel
-    const char* e = getenv("VMTL_HEAD_BWD");
-    return !(e && strcmp(e, "ffma") == 0);
-  }();
-  if (use_tc && P >= 128) {
+  if (P >= 128) {
     int g = 0;
     const int max_blocks = (int)(workspace_bytes / ((size_t)ROW * sizeof(float)));
     const int rc = head_ce_tc_bwd(feat, W, b, target, P, C, ignore_index, fwd_out, gscale, dfeat, partial,
@@ -1030,7 +1014,7 @@ extern "C" int vmtl_ce_logits_fwd(const float* logits, const int64_t* target, in
                                                                    ignore_index, partial, pred, cf); \
   } while (0)
   const bool nh = layout == VMTL_LAYOUT_NHWC;
-  if (nh && ce_bulk_enabled()) {  // NHWC: tiles arrive by bulk async copy (VMTL_CE_LOGITS=staged: per-element staging)
+  if (nh) {  // NHWC: tiles arrive by bulk async copy
     const size_t bsmem = 2 * (size_t)kLossThreads * C * 4 + (conf ? (size_t)C * C * 4 : 0) + 32;
 #define VMTL_CEFB(CP)                                                                                           \
   do {                                                                                                          \
@@ -1044,9 +1028,9 @@ extern "C" int vmtl_ce_logits_fwd(const float* logits, const int64_t* target, in
     else if (cpad == 20) VMTL_CEFB(20);
     else VMTL_CEFB(32);
 #undef VMTL_CEFB
-  } else if (cpad == 16) { if (nh) VMTL_CEF(16, true); else VMTL_CEF(16, false); }
-  else if (cpad == 20) { if (nh) VMTL_CEF(20, true); else VMTL_CEF(20, false); }
-  else { if (nh) VMTL_CEF(32, true); else VMTL_CEF(32, false); }
+  } else if (cpad == 16) VMTL_CEF(16, false);
+  else if (cpad == 20) VMTL_CEF(20, false);
+  else VMTL_CEF(32, false);
 #undef VMTL_CEF
   int rc = launch_status();
   if (rc != VMTL_OK) return rc;
@@ -1073,7 +1057,7 @@ extern "C" int vmtl_ce_logits_bwd(const float* logits, const int64_t* target, in
                                                                    ignore_index, fwd_out, gscale, dlogits); \
   } while (0)
   const bool nh = layout == VMTL_LAYOUT_NHWC;
-  if (nh && ce_bulk_enabled()) {
+  if (nh) {
     const size_t bsmem = 2 * (size_t)kLossThreads * C * 4 + 32;
 #define VMTL_CEBB(CP)                                                                                           \
   do {                                                                                                          \
@@ -1089,9 +1073,9 @@ extern "C" int vmtl_ce_logits_bwd(const float* logits, const int64_t* target, in
 #undef VMTL_CEBB
     return launch_status();
   }
-  if (cpad == 16) { if (nh) VMTL_CEB(16, true); else VMTL_CEB(16, false); }
-  else if (cpad == 20) { if (nh) VMTL_CEB(20, true); else VMTL_CEB(20, false); }
-  else { if (nh) VMTL_CEB(32, true); else VMTL_CEB(32, false); }
+  if (cpad == 16) VMTL_CEB(16, false);
+  else if (cpad == 20) VMTL_CEB(20, false);
+  else VMTL_CEB(32, false);
 #undef VMTL_CEB
   return launch_status();
 }
