@@ -62,12 +62,14 @@ def fill_state_dict(sd: dict, salt: int = 0) -> dict:
     return out
 
 
-def image_batch(B: int, H: int, W: int, num_classes: int, key: str = "batch", depth_zero_frac: float = 0.2) -> dict:
+def image_batch(B: int, H: int, W: int, num_classes: int, key: str = "batch", depth_zero_frac: float = 0.2,
+                depth_max: float = 0.5) -> dict:
     """Synthetic Cityscapes-shaped batch: img U(0,1), mask randint(0,C), depth U(0,0.5)
-    with a fraction of exact zeros, layouts as the reference datasets produce them."""
+    with a fraction of exact zeros, layouts as the reference datasets produce them.  NYUv2-shaped:
+    ``depth_zero_frac=0, depth_max=1`` (depth U(0,10)/10, no zeros)."""
     img = tensor((B, 3, H, W), key + "/img", 0.5) + 0.5
     mask = labels((B, H, W), num_classes, key + "/mask")
-    depth = (tensor((B, H, W, 1), key + "/depth", 0.25) + 0.25).clamp_min(0.0)
+    depth = (tensor((B, H, W, 1), key + "/depth", depth_max / 2) + depth_max / 2).clamp_min(0.0)
     zero = (tensor((B, H, W, 1), key + "/zero", 0.5) + 0.5) < depth_zero_frac
     depth = torch.where(zero, torch.zeros_like(depth), depth)
     return {"img": img, "mask": mask, "depth": depth}

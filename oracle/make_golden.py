@@ -35,6 +35,16 @@ MTAN_CASES = {  # name -> (hidden, first_channel, levels, B, H, W, classes)
     "mtan_h128": (128, 32, 2, 1, 16, 32, 19),
     "mtan_h64": (64, 32, 2, 1, 16, 16, 14),
 }
+# Full-width MTAN (hidden 128, first channel 32, 4 levels = the bench model, 13.28 M parameters) at the
+# BASELINE.json image shapes.  No flip-free fixture exists at this size, so gradients are stored twice --
+# the reference in fp32 and in fp64 -- and tests use the fp64 run as the yardstick:
+#   err(product vs fp64)  <=  k * err(reference fp32 vs fp64)
+FULL_CASES = {  # name -> (B, H, W, classes, depth_zero_frac, depth_max)
+    "mtan_nyu": (2, 256, 256, 14, 0.0, 1.0),
+    "mtan_city": (2, 128, 256, 19, 0.2, 0.5),
+}
+NEAR_TIE = 1e-4  # top-2 logit gap below which an argmax may legitimately differ between fp32 implementations
+
 # A ReLU input (or a max-pool runner-up) closer to the decision boundary than this can flip
 # between two correct fp32 implementations; one flipped element perturbs every upstream weight
 # gradient by ~1e-2 relative.  Golden MTAN cases are searched (over the fixture salt) to have no
@@ -147,6 +157,74 @@ def gen_mtan(ref, out):
         out[f"{name}/eval_depth"] = FX.summarize(raw_e["depth"], 16)
 
 
+def gen_mtan_full(ref, out):
+    for name, (B, H, W, C, zf, dmax) in FULL_CASES.items():
+        batch = FX.image_batch(B, H, W, C, name, depth_zero_frac=zf, depth_max=dmax)
+
+        def step(dtype):
+            net = ref["MTANMiniUnet"](3, {"depth": 1, "segm": C}, task_subnets_hidden_channels=128,
+                                      encoder_first_channel=32, encoder_num_channels=4)
+            net.load_state_dict(FX.fill_state_dict(net.state_dict(), salt=1))
+            net = net.to(dtype).train()
+            raw = net(batch["img"].to(dtype))
+            depth_pred = torch.sigmoid(raw["depth"]).permute(0, 2, 3, 1)
+            loss_segm = nn.CrossEntropyLoss()(raw["segm"], batch["mask"])
+            loss_depth = ref["SILogLoss"]()(depth_pred, batch["depth"].to(dtype))
+            loss = 1.0 * loss_segm + 1.0 * loss_depth
+            loss.backward()
+            return net, raw, depth_pred, (loss, loss_segm, loss_depth)
+
+        net, raw, depth_pred, losses = step(torch.float32)
+        out[f"{name}/losses"] = np.array([v.item() for v in losses], dtype=np.float64)
+        out[f"{name}/mae"] = np.array([(depth_pred - batch["depth"]).abs().mean().item()])
+        out[f"{name}/segm_logits"] = FX.summarize(raw["segm"], 64)
+        out[f"{name}/depth_logits"] = FX.summarize(raw["depth"], 64)
+        preds = torch.argmax(F.softmax(raw["segm"], dim=1), dim=1)
+        out[f"{name}/preds"] = _np(preds).astype(np.int8)
+        top2 = raw["segm"].detach().permute(0, 2, 3, 1).topk(2, dim=-1).values
+        tie = ((top2[..., 0] - top2[..., 1]) < NEAR_TIE).reshape(-1)
+        out[f"{name}/near_tie_pixels"] = _np(torch.nonzero(tie).reshape(-1)).astype(np.int32)
+        for k, p_ in net.named_parameters():
+            out[f"{name}/grad/{k}"] = FX.summarize(p_.grad)
+        for k, b_ in net.named_buffers():
+            out[f"{name}/buf/{k}"] = FX.summarize(b_.float())
+        net64, _, _, losses64 = step(torch.float64)
+        out[f"{name}/losses64"] = np.array([v.item() for v in losses64], dtype=np.float64)
+        for k, p_ in net64.named_parameters():
+            out[f"{name}/grad64/{k}"] = FX.summarize(p_.grad)
+        print(f"{name}: loss {losses[0].item():.6f} (fp64 {losses64[0].item():.6f}), near-tie pixels {int(tie.sum())}")
+
+
+def _act_margin(net, img):
+    """Smallest distance of any activation input of the task networks from a kink of its activation
+    (ReLU: 0; Hardswish: -3 and +3)."""
+    margins = []
+
+    def relu_hook(_m, inp, _out):
+        margins.append(float(inp[0].detach().abs().min()))
+
+    def hsw_hook(_m, inp, _out):
+        x = inp[0].detach()
+        margins.append(float(torch.minimum((x + 3).abs(), (x - 3).abs()).min()))
+
+    hooks = []
+    for m in net.modules():
+        if isinstance(m, nn.ReLU):
+            m.inplace = False
+            hooks.append(m.register_forward_hook(relu_hook))
+        elif isinstance(m, nn.Hardswish):
+            m.inplace = False
+            hooks.append(m.register_forward_hook(hsw_hook))
+    with torch.no_grad():
+        net(img)
+    for h in hooks:
+        h.remove()
+    return min(margins)
+
+
+CSNET_SMALL = ("csnet_small", 2, 32, 32, 19)  # flip-free fixture (searched over the salt): gradients at 1e-4
+
+
 def gen_csnet(ref, out):
     """Reference CSNet class over the stand-in backbone (smp/timm are not installable)."""
     from vision_mtl_b200.utils.model_utils import get_model_with_dense_preds
@@ -176,6 +254,89 @@ def gen_csnet(ref, out):
         for k, p_ in net.named_parameters():
             if p_.grad is not None:
                 out[f"{name}/grad/{k}"] = FX.summarize(p_.grad)
+    _gen_csnet_extra(ref, out)
+
+
+def _csnet_models(C):
+    from vision_mtl_b200.utils.model_utils import get_model_with_dense_preds
+
+    return {
+        "depth": get_model_with_dense_preds(segm_classes=1, activation=None, backbone_params=dict(encoder_weights=None)),
+        "segm": get_model_with_dense_preds(segm_classes=C, activation=None, backbone_params=dict(encoder_weights=None)),
+    }
+
+
+def _csnet_step(ref, net, batch, dtype):
+    net = net.to(dtype).train()
+    raw = net(batch["img"].to(dtype))
+    loss_segm = nn.CrossEntropyLoss()(raw["segm"], batch["mask"])
+    depth_pred = torch.sigmoid(raw["depth"]).permute(0, 2, 3, 1)
+    loss_depth = ref["SILogLoss"]()(depth_pred, batch["depth"].to(dtype))
+    (loss_segm + loss_depth).backward()
+    return raw, (loss_segm + loss_depth, loss_segm, loss_depth)
+
+
+def _gen_csnet_extra(ref, out):
+    """(a) fp64 runs of the two 64x64 cases: the yardstick for gradient comparisons at sizes where ReLU /
+    Hardswish near-flips are unavoidable; (b) a small flip-free case whose gradients are reproducible to
+    fp32 round-off between two correct implementations."""
+    for name, cw in (("csnet_cw", True), ("csnet_lw", False)):
+        torch.manual_seed(0)
+        net = ref["CSNet"](_csnet_models(19), channel_wise_stitching=cw)
+        net.load_state_dict(FX.fill_state_dict(net.state_dict()))
+        _, losses = _csnet_step(ref, net, FX.image_batch(2, 64, 64, 19, name), torch.float64)
+        out[f"{name}/losses64"] = np.array([v.item() for v in losses])
+        for k, p_ in net.named_parameters():
+            if p_.grad is not None:
+                out[f"{name}/grad64/{k}"] = FX.summarize(p_.grad)
+    name, B, H, W, C = CSNET_SMALL
+    for salt in range(2000):
+        torch.manual_seed(0)
+        net = ref["CSNet"](_csnet_models(C), channel_wise_stitching=True)
+        net.load_state_dict(FX.fill_state_dict(net.state_dict(), salt=salt))
+        batch = FX.image_batch(B, H, W, C, f"{name}/{salt}")
+        margin = _act_margin(net.train(), batch["img"])
+        if margin > FLIP_MARGIN:
+            break
+    else:
+        raise RuntimeError("no flip-free csnet fixture found")
+    print(f"{name}: salt {salt}, activation margin {margin:.2e}")
+    # the margin pass ran a training-mode forward: rebuild so the running statistics start from the fixture
+    torch.manual_seed(0)
+    net = ref["CSNet"](_csnet_models(C), channel_wise_stitching=True)
+    net.load_state_dict(FX.fill_state_dict(net.state_dict(), salt=salt))
+    raw, losses = _csnet_step(ref, net, batch, torch.float32)
+    out[f"{name}/salt"] = np.array([salt], dtype=np.int64)
+    out[f"{name}/margin"] = np.array([margin])
+    out[f"{name}/segm_logits"] = _np(raw["segm"]).astype(np.float32)
+    out[f"{name}/depth_logits"] = _np(raw["depth"]).astype(np.float32)
+    out[f"{name}/losses"] = np.array([v.item() for v in losses])
+    for k, p_ in net.named_parameters():
+        if p_.grad is not None:
+            out[f"{name}/grad/{k}"] = FX.summarize(p_.grad)
+    for k, b_ in net.named_buffers():
+        out[f"{name}/buf/{k}"] = FX.summarize(b_.float())
+
+
+def gen_epoch_summary(ref, out):
+    """summarize_epoch_metrics / print_metrics of the reference (utils/loss_utils.py:27-64) on a fixed
+    history of per-step scalars (0-d tensors, like MTLModule.step_outputs holds)."""
+    lu = ref["loss_utils"]
+    keys = ("loss", "accuracy", "jaccard_index", "fbeta_score", "mae")
+    hist = {k: [FX.tensor((), f"epoch/{k}/{i}", 2.0) + 2.0 for i in range(7)] for k in keys}
+    res = lu.summarize_epoch_metrics({k: list(v) for k, v in hist.items()}, metric_name_prefix="train")
+    out["epoch/keys"] = np.array(list(res.keys()))
+    out["epoch/values"] = np.array([res[k] for k in res], dtype=np.float64)
+    res2 = lu.summarize_epoch_metrics({k: list(v) for k, v in hist.items()})
+    out["epoch/keys_noprefix"] = np.array(list(res2.keys()))
+    import contextlib
+    import io
+
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        line = lu.print_metrics("epoch", res)
+    out["epoch/print_line"] = np.array([line])
+    out["epoch/print_stdout"] = np.array([buf.getvalue()])
 
 
 def main():
@@ -183,8 +344,11 @@ def main():
     torch.backends.mkldnn.enabled = True
     ref = ref_shims.load()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    for fname, gens in (("kernels.npz", (gen_xstitch, gen_silog)), ("mtan.npz", (gen_mtan,)),
-                        ("csnet.npz", (gen_csnet,))):
+    only = sys.argv[1:]
+    for fname, gens in (("kernels.npz", (gen_xstitch, gen_silog, gen_epoch_summary)), ("mtan.npz", (gen_mtan,)),
+                        ("csnet.npz", (gen_csnet,)), ("mtan_full.npz", (gen_mtan_full,))):
+        if only and fname not in only:
+            continue
         out = {}
         for g in gens:
             g(ref, out)

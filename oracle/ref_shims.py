@@ -46,6 +46,7 @@ def load():
     from vision_mtl.losses import SILogLoss
     from vision_mtl.models.cross_stitch_model import CrossStitchLayer, CSNet
     from vision_mtl.models.mtan_model import MTANMiniUnet
+    from vision_mtl.utils import loss_utils
 
     return {"SILogLoss": SILogLoss, "CrossStitchLayer": CrossStitchLayer, "CSNet": CSNet,
-            "MTANMiniUnet": MTANMiniUnet}
+            "MTANMiniUnet": MTANMiniUnet, "loss_utils": loss_utils}

@@ -72,10 +72,14 @@ def test_xstitch_full_size_oracle_and_linearity():
         assert torch.equal(xd[a].grad, dys[a] * ad.detach()[a, a].view(1, Cc, 1, 1))
 
 
-def test_gate_full_size_oracle_and_properties():
+# the four MTAN gate sites of BASELINE.json: N = 32 @ full resolution (M = 1 048 576), 64 @ /2
+# (262 144), 128 @ /4 (65 536), 256 @ /8 (16 384).  The wide sites take the column-chunk paths of the
+# forward and of both backward kernels; at M = 16 384 fewer tiles than SMs exist.
+@pytest.mark.parametrize("N,down", [(32, 1), (64, 2), (128, 4), (256, 8)])
+def test_gate_full_size_oracle_and_properties(N, down):
     from vision_mtl_b200 import ops
 
-    N = 32
+    H, W = globals()["H"] // down, globals()["W"] // down
     g = torch.Generator().manual_seed(11)
     h = torch.relu(torch.randn(B, 128, H, W, generator=g))
     s = torch.relu(torch.randn(B, N, H, W, generator=g))
