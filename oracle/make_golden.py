@@ -222,7 +222,7 @@ def _act_margin(net, img):
     return min(margins)
 
 
-CSNET_SMALL = ("csnet_small", 2, 32, 32, 19)  # flip-free fixture (searched over the salt): gradients at 1e-4
+CSNET_SMALL = ("csnet_small", 2, 64, 64, 19)  # flip-free fixture (searched over the salt): gradients at 1e-4
 
 
 def gen_csnet(ref, out):
@@ -290,7 +290,7 @@ def _gen_csnet_extra(ref, out):
             if p_.grad is not None:
                 out[f"{name}/grad64/{k}"] = FX.summarize(p_.grad)
     name, B, H, W, C = CSNET_SMALL
-    for salt in range(2000):
+    for salt in range(5000):
         torch.manual_seed(0)
         net = ref["CSNet"](_csnet_models(C), channel_wise_stitching=True)
         net.load_state_dict(FX.fill_state_dict(net.state_dict(), salt=salt))
@@ -316,6 +316,14 @@ def _gen_csnet_extra(ref, out):
             out[f"{name}/grad/{k}"] = FX.summarize(p_.grad)
     for k, b_ in net.named_buffers():
         out[f"{name}/buf/{k}"] = FX.summarize(b_.float())
+    # fp64 run of the same fixture: tells analytically-zero gradients (noise in fp32) from real ones
+    torch.manual_seed(0)
+    net = ref["CSNet"](_csnet_models(C), channel_wise_stitching=True)
+    net.load_state_dict(FX.fill_state_dict(net.state_dict(), salt=salt))
+    _csnet_step(ref, net, batch, torch.float64)
+    for k, p_ in net.named_parameters():
+        if p_.grad is not None:
+            out[f"{name}/grad64/{k}"] = FX.summarize(p_.grad)
 
 
 def gen_epoch_summary(ref, out):
