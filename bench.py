@@ -2,18 +2,25 @@
 """Benchmark of the multi-task training step (BASELINE.json metric: MTL train-step images/sec;
 fused-kernel HBM GB/s vs peak).
 
-    python bench.py --gpus N --steps K --warmup W [--workload csnet|mtan|mtan_nyu] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload all|mtan|csnet|mtan_nyu] [--impl reference]
 
 One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  Prints ONE JSON line.
+With no ``--workload`` the three GPU configurations of BASELINE.json run back to back in one process:
+the headline record is ``mtan`` (configs[2]: attention-gated step, Cityscapes-shaped 128x256, per-GPU batch
+32 -- the configuration whose step is built on the tcgen05 gate and fused-head kernels); ``csnet``
+(configs[1]) and ``mtan_nyu`` (configs[3]) are complete sub-records under ``workloads``.
 
 * ``value``  : images/s, whole job, batch resident in HBM, CUDA-event timed, max over ranks.
 * ``e2e``    : same step through the public API with the batch copied from pinned host memory and
                the five step scalars read back every step.
-* ``roofline``: the dominant hand-written kernel of the step, algorithmic bytes / CUDA-event time
-               measured live in the timed region, against MEASURED_PEAKS.json.
-* ``cpu_baseline`` (rank 0, N = 1) and ``--impl reference``: the reference's own CPU path --
-               restated in ``oracle/`` and pinned to the reference by tests/golden -- timed on the
-               host cores on a bounded sample of the same workload.
+* ``roofline``: the hand-written kernel with the largest share of the step: ALGORITHMIC bytes of SURVEY 8(d)
+               / CUDA-event time (external events around every library call inside an instrumented copy of
+               the step graph, same method at every N), against MEASURED_PEAKS.json; ``issued_bytes`` (what
+               the kernels request) and ``traffic`` (ncu dram bytes of a captured launch) reported beside it.
+* ``cpu_baseline`` (rank 0, N = 1) and ``--impl reference``: the reference's OWN loop
+               (``training_lit.run_pipe`` -> ``lit_module.MTLModule``, unmodified, from /root/reference or
+               the shipped baseline/_ref copy; import stubs in oracle/ref_runtime.py) timed on the host cores
+               on a bounded sample of the same workload; the oracle port is timed as a cross-check.
 """
 from __future__ import annotations
 
@@ -48,13 +55,15 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--no-graph-events", action="store_true",
                     help="skip the instrumented graph copy; per-op times then come from the eager pass")
-    ap.add_argument("--workload", choices=list(WORKLOADS), default="csnet")
+    ap.add_argument("--workload", choices=["all", *WORKLOADS], default="all",
+                    help="all = mtan (headline) + csnet + mtan_nyu sub-records")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
     ap.add_argument("--conv-tf32", action="store_true", help="allow TF32 in the cuDNN 3x3 convs (default: strict fp32)")
     ap.add_argument("--gate-precision", default="tc_3xtf32", choices=["tc_3xtf32", "tc_tf32", "fp32_ffma"])
     ap.add_argument("--stitch-mode", default="reference_diag", choices=["reference_diag", "full_mix"])
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--cpu-steps", type=int, default=5, help="timed steps of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lr", type=float, default=5e-4)
     ap.add_argument("--no-graph", action="store_true", help="eager step instead of the whole-step CUDA graph")
@@ -113,7 +122,8 @@ def cpu_reference_step_fn(workload: str, batch_size: int, lr: float):
     return step, threads
 
 
-def time_cpu_reference(workload: str, batch_size: int, lr: float, steps: int, warmup: int):
+def time_cpu_port(workload: str, batch_size: int, lr: float, steps: int, warmup: int):
+    """Oracle port of the reference's CPU path (cross-check of the reference-loop timing)."""
     step, threads = cpu_reference_step_fn(workload, batch_size, lr)
     for _ in range(warmup):
         step()
@@ -122,6 +132,44 @@ def time_cpu_reference(workload: str, batch_size: int, lr: float, steps: int, wa
         step()
     dt = time.perf_counter() - t0
     return batch_size * steps / dt, dt / steps, threads
+
+
+def time_cpu_reference(workload: str, batch_size: int, lr: float, steps: int, warmup: int):
+    """The reference's own ``run_pipe`` loop on a batch-``batch_size`` sample: (images/s, s/step, threads, kind)."""
+    from vision_mtl_b200.synthetic import make_batch
+
+    model, dataset, C, H, W, _ = WORKLOADS[workload]
+    batch = make_batch(batch_size, H, W, C, dataset, seed=11)
+    try:
+        from oracle import ref_runtime
+
+        ips, sec, threads = ref_runtime.time_reference_loop(model, batch, C, lr, steps, warmup)
+        return ips, sec, threads, "reference"
+    except Exception as exc:  # no reference tree on this box: time the port and say so
+        sys.stderr.write(f"[bench] reference loop unavailable ({exc!r}); timing the oracle port\n")
+        ips, sec, threads = time_cpu_port(workload, batch_size, lr, steps, warmup)
+        return ips, sec, threads, "port"
+
+
+def workload_text(name: str, batch: int) -> str:
+    model, dataset, C, H, W, _ = WORKLOADS[name]
+    return (f"{name}: {model} training step (fwd + fused CE/SILog/metrics + bwd + Adam), "
+            f"{dataset}-shaped {H}x{W}, {C} classes, per-GPU batch {batch}")
+
+
+def cpu_baseline_record(name: str, args, steps: int, with_port: bool) -> dict:
+    model, dataset, C, H, W, _ = WORKLOADS[name]
+    bs = args.cpu_sample_batch
+    ips, sec, threads, kind = time_cpu_reference(name, bs, args.lr, steps, 1)
+    what = ("the reference's own training_lit.run_pipe + lit_module.MTLModule (unmodified; torchmetrics "
+            "restated, see oracle/ref_runtime.py)") if kind == "reference" else "oracle port of the reference's PyTorch CPU path"
+    rec = {"value": ips, "unit": "images/s", "cores": threads, "kind": kind,
+           "sample": f"1 warm-up + {steps} timed {model} train steps on a batch-{bs} sample of the same {H}x{W} workload "
+                     f"({sec:.2f} s/step), {what}, fp32, torch CPU"}
+    if with_port and kind == "reference":
+        pips, psec, _ = time_cpu_port(name, bs, args.lr, 2, 1)
+        rec["port_cross_check"] = {"value": pips, "unit": "images/s", "sample": f"oracle port, 2 timed steps ({psec:.2f} s/step)"}
+    return rec
 
 
 # ------------------------------------------------------------------------------------------
@@ -173,27 +221,40 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
+HEADLINE = "mtan"
+ALL_ORDER = ("mtan", "csnet", "mtan_nyu")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    model, dataset, C, H, W, B = WORKLOADS[args.workload]
-    bs = args.cpu_sample_batch
-    ips, sec, threads = time_cpu_reference(args.workload, bs, args.lr, max(args.steps, 1), min(args.warmup, 1))
-    sample = f"{model} train step (fwd+CE/SILog+metrics+bwd+Adam) on a batch-{bs} sample of the {H}x{W} workload, fp32, torch CPU"
-    line = {
-        "impl": "reference", "metric": "mtl_train_step_images_per_sec", "value": ips, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {model} training step (fwd + fused CE/SILog/metrics + bwd + Adam), "
-                               f"{dataset}-shaped {H}x{W}, {C} classes, per-GPU batch {B}",
-                   "global_batch": B * args.gpus, "parallelism": f"dp{args.gpus}", "conv_math": "fp32 (torch CPU)",
-                   "cpu_sample_batch": bs,
-                   "note": "the reference is single-process CPU code: rank 0 times it on all host cores, "
-                           "throughput does not depend on n_gpus"},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
+    names = list(ALL_ORDER) if args.workload == "all" else [args.workload]
+    recs = {}
+    for i, name in enumerate(names):
+        model, dataset, C, H, W, B = WORKLOADS[name]
+        bs = args.cpu_sample_batch
+        steps = max(args.steps, 1) if i == 0 else max(min(args.steps, args.cpu_steps), 1)  # sub-records: bounded
+        ips, sec, threads, kind = time_cpu_reference(name, bs, args.lr, steps, min(args.warmup, 1))
+        what = ("reference training_lit.run_pipe + lit_module.MTLModule, unmodified (torchmetrics restated)"
+                if kind == "reference" else "oracle port of the reference's PyTorch CPU path")
+        sample = (f"{model} train step (fwd+CE/SILog+metrics+bwd+Adam) on a batch-{bs} sample of the {H}x{W} workload, "
+                  f"{steps} timed steps, {what}, fp32, torch CPU")
+        recs[name] = {
+            "impl": "reference", "metric": "mtl_train_step_images_per_sec", "value": ips, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_text(name, B if not args.batch else args.batch),
+                       "global_batch": (args.batch or B) * args.gpus, "parallelism": f"dp{args.gpus}",
+                       "conv_math": "fp32 (torch CPU)", "cpu_sample_batch": bs,
+                       "note": "the reference is single-process CPU code: rank 0 times it on all host cores, "
+                               "throughput does not depend on n_gpus"},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+    line = recs[names[0]]
+    if len(names) > 1:
+        line["workloads"] = {n: recs[n] for n in names[1:]}
     print(json.dumps(line))
 
 
@@ -207,30 +268,20 @@ def _phase(msg: str) -> None:
         sys.stderr.flush()
 
 
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
+def run_workload(args, name: str, rank: int, local_rank: int, world: int, with_port: bool) -> dict:
+    """One workload end to end on this rank; returns the record (complete on rank 0)."""
+    import gc
 
     import torch.distributed as dist
 
     from vision_mtl_b200 import dist as vdist
     from vision_mtl_b200 import ops
+    from vision_mtl_b200.graph_step import GraphedTrainStep
     from vision_mtl_b200.synthetic import make_batch
     from vision_mtl_b200.utils.pipeline_utils import DataShape, init_model
 
-    rank, local_rank, world = vdist.init_distributed()
-    _phase(f"process group ready (world {world})")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    torch.backends.cudnn.allow_tf32 = bool(args.conv_tf32)
-    torch.backends.cuda.matmul.allow_tf32 = bool(args.conv_tf32)
-    torch.backends.cudnn.benchmark = True
-    ops.default_gate_precision = args.gate_precision
-
-    model, dataset, C, H, W, B = WORKLOADS[args.workload]
+    model, dataset, C, H, W, B = WORKLOADS[name]
     if args.batch:
         B = args.batch
     torch.manual_seed(11)  # identical weights on every rank
@@ -248,7 +299,7 @@ def main():
             vdist.wrap_data_parallel(module, local_rank)
         torch.cuda.current_stream().wait_stream(side)
     opt = torch.optim.Adam(module.parameters(), lr=args.lr, fused=True, capturable=use_graph)
-    _phase("model + optimizer built")
+    _phase(f"[{name}] model + optimizer built")
 
     host = make_batch(B, H, W, C, dataset, seed=11 + rank, pin=True)          # pinned host copy
     resident = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
@@ -275,33 +326,22 @@ def main():
     for _ in range(max(args.warmup, 3)):
         eager_step(resident)
     barrier()
-    _phase("eager warm-up done")
+    _phase(f"[{name}] eager warm-up done")
 
-    # ---- per-launch kernel events (roofline): recorded around every library call ---------------
-    # eager mode: inside the timed region; graph mode: in an eager pass of the identical step, because
-    # a graph replay exposes no per-launch host hooks
+    # launches per step (the `gpu_launches` claim): counted on one eager pass of the identical step
+    ops.reset_launch_count()
+    eager_step(resident)
+    barrier()
+    launches_per_step = ops.launch_count()
+
     sampler = ClockSampler(local_rank)
     graphed = None
     if use_graph:
-        ops.reset_launch_count()
-        with ops.kernel_timing() as records:
-            for _ in range(min(args.steps, 5)):
-                # keep the device behind the host for the whole step: the events then bracket back-to-back
-                # kernel execution, not the host's launch latency (an eager csnet step is host-bound)
-                torch.cuda._sleep(100_000_000)  # ~50 ms of device time queued ahead of the step
-                eager_step(resident)
-            barrier()
-        launches_per_step = ops.launch_count() // min(args.steps, 5)
-        kstats = ops.summarize_timing(records)
-        ksteps = min(args.steps, 5)
-        from vision_mtl_b200.graph_step import GraphedTrainStep
-
-        _phase("per-kernel event pass done")
         graphed = GraphedTrainStep(module, opt, resident, warmup=11 if world > 1 else 3, after_backward=metric_exchange)
         for _ in range(3):
             graphed()
         barrier()
-        _phase("step graph captured and replayed")
+        _phase(f"[{name}] step graph captured and replayed")
 
     def train_step(batch):
         if graphed is not None:
@@ -347,28 +387,15 @@ def main():
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if graphed is None:
-        ops.reset_launch_count()
-        with ops.kernel_timing() as records:
-            barrier()
-            ev0.record()
-            for _ in range(args.steps):
-                train_step(resident)
-            ev1.record()
-            barrier()
-        launches_per_step = ops.launch_count() // args.steps
-        kstats = ops.summarize_timing(records)
-        ksteps = args.steps
-    else:
-        barrier()
-        ev0.record()
-        for _ in range(args.steps):
-            train_step(resident)
-        ev1.record()
-        barrier()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        train_step(resident)
+    ev1.record()
+    barrier()
     launches = launches_per_step * args.steps
     ms = ev0.elapsed_time(ev1)
-    _phase("timed region done")
+    _phase(f"[{name}] timed region done")
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host batch in, step scalars out, every step ------------------------------------
@@ -382,100 +409,141 @@ def main():
     ev3.record()
     barrier()
     ms_e2e = ev2.elapsed_time(ev3)
-    _phase("e2e region done")
+    _phase(f"[{name}] e2e region done")
 
-    # ---- per-op device time INSIDE graph replays: an instrumented copy of the step graph whose library
-    # calls are bracketed by external CUDA events (replayed after the timed region; single GPU only)
-    events_from = ("eager pass of the identical step right before the timed graph replays, device kept "
-                   "busy ahead of the host so events bracket kernel execution") if graphed is not None else "the timed region"
-    if graphed is not None and world == 1 and not args.no_graph_events:
+    # ---- per-op device time: external CUDA events around every library call inside an instrumented copy
+    # of the step graph, replayed right after the timed region.  Same method at every N (the copy contains
+    # the same NCCL nodes as the timed graph, so all ranks capture and replay it together).
+    kstats, ksteps, events_from = {}, 1, None
+    if graphed is not None and not args.no_graph_events:
         try:
             prof = GraphedTrainStep(module, opt, resident, warmup=1, after_backward=metric_exchange, profile=True)
             for _ in range(3):
                 prof()
-            torch.cuda.synchronize()
+            barrier()
             gstats = prof.kernel_stats()
             if gstats and all(v["ms"] > 0 for v in gstats.values()):
-                kstats, ksteps = gstats, 1
+                kstats = gstats
                 events_from = ("external CUDA events around every library call inside an instrumented copy of the "
                                "step graph (third replay, right after the timed region)")
             del prof
-        except Exception as exc:  # keep the eager-pass numbers
+        except Exception as exc:
             sys.stderr.write(f"[bench] in-graph event pass unavailable: {exc!r}\n")
-        _phase("in-graph event pass done")
+    if not kstats:  # eager mode, or the instrumented capture failed: events around the calls of eager steps
+        n = min(args.steps, 5)
+        with ops.kernel_timing() as records:
+            for _ in range(n):
+                torch.cuda._sleep(100_000_000)  # keep the device behind the host: events bracket kernel execution
+                eager_step(resident)
+            barrier()
+        kstats, ksteps = ops.summarize_timing(records), n
+        events_from = "eager pass of the identical step, device kept busy ahead of the host so events bracket kernel execution"
+    _phase(f"[{name}] per-kernel event pass done")
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
-    if rank != 0:  # see the exit note at the end of main(): no NCCL teardown under live graphs
-        sys.stdout.flush()
-        sys.stderr.flush()
-        graphed = None
-        barrier()
-        os._exit(0)
 
-    ips = B * world * args.steps / (ms * 1e-3)
-    ips_e2e = B * world * args.steps / (ms_e2e * 1e-3)
-    peak, peak_src = measured_peak()
-    top = max(kstats.items(), key=lambda kv: kv[1]["ms"]) if kstats else None
-    roofline = None
-    if top is not None:
-        name, d = top
-        achieved = d["gbps"]
-        traffic, traffic_note = None, None
-        tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath):  # dram__bytes_read+write of ONE captured launch (ncu --set full)
-            rec = json.load(open(tpath)).get(args.workload, {}).get(name)
-            if rec:
-                traffic = rec["bytes"]
-                traffic_note = (f"captured launch: {rec['site']}; algorithmic bytes of that launch "
-                                f"{rec['algorithmic_bytes_same_launch']}")
-        roofline = {"bound": "hbm", "kernel": "vmtl_" + name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
-                    "peak_source": peak_src,
-                    "events_from": events_from,
-                    "launches_timed": d["calls"], "avg_launch_ms": d["ms"] / d["calls"],
-                    "algorithmic_bytes_per_launch": d["bytes"] / d["calls"]}
-    line = {
-        "metric": "mtl_train_step_images_per_sec", "value": ips, "unit": "images/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {
-            "workload": f"{args.workload}: {model} training step (fwd + fused CE/SILog/metrics + bwd + Adam), "
-                        f"{dataset}-shaped {H}x{W}, {C} classes, per-GPU batch {B}",
-            "global_batch": B * world, "parallelism": f"dp{world}",
-            "conv_math": "tf32 (cuDNN)" if args.conv_tf32 else "fp32 (cuDNN, TF32 off)",
-            "gate_precision": args.gate_precision, "stitch_mode": args.stitch_mode,
-            "step_launch": "one CUDA graph per step (fwd + fused losses/metrics + bwd + Adam)" if graphed is not None else "eager",
-            "l2": "per-step working set (activations of a batch-%d step) >> 126 MB L2; no explicit flush" % B,
-            "backbone": "stand-in MobileNetV3-Large/Unet (smp/timm not installable offline)" if model != "mtan" else "reference MTAN mini-UNet",
-        },
-        "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes * world,
-                "d2h_bytes_per_step": int(scal.numel() * scal.element_size()) * world,
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches,
-        "clocks": clocks,
-        "roofline": roofline,
-        "kernels": {k: {"calls": v["calls"], "ms_per_step": v["ms"] / ksteps, "gbps": v["gbps"],
-                        "frac_of_peak": v["gbps"] / peak} for k, v in sorted(kstats.items())},
-    }
-    if world == 1 and not args.no_cpu_baseline:
-        bs = args.cpu_sample_batch
-        cips, csec, threads = time_cpu_reference(args.workload, bs, args.lr, 2, 1)
-        line["cpu_baseline"] = {
-            "value": cips, "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": f"1 warm-up + 2 timed {model} train steps on a batch-{bs} sample of the same {H}x{W} workload "
-                      f"({csec:.1f} s/step), oracle port of the reference's PyTorch CPU path"}
-    print(json.dumps(line))
+    rec = None
+    if rank == 0:
+        ips = B * world * args.steps / (ms * 1e-3)
+        ips_e2e = B * world * args.steps / (ms_e2e * 1e-3)
+        peak, peak_src = measured_peak()
+        top = max(kstats.items(), key=lambda kv: kv[1]["ms"]) if kstats else None
+        roofline = None
+        if top is not None:
+            kname, d = top
+            traffic, traffic_note = None, None
+            tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
+            if os.path.exists(tpath):  # dram__bytes_read+write of ONE captured launch (ncu --set full)
+                trec = json.load(open(tpath)).get(name, {}).get(kname)
+                if trec:
+                    traffic = trec["bytes"]
+                    traffic_note = (f"captured launch: {trec['site']}; algorithmic bytes of that launch "
+                                    f"{trec['algorithmic_bytes_same_launch']}")
+            roofline = {"bound": "hbm", "kernel": "vmtl_" + kname, "achieved": d["gbps"], "peak": peak, "unit": "GB/s",
+                        "frac": d["gbps"] / peak, "traffic": traffic, "traffic_note": traffic_note,
+                        "peak_source": peak_src, "events_from": events_from,
+                        "bytes_model": "SURVEY 8(d) algorithmic bytes (ops.gate_bytes and the _call sites of ops.py)",
+                        "launches_timed": d["calls"], "avg_launch_ms": d["ms"] / d["calls"],
+                        "algorithmic_bytes_per_launch": d["bytes"] / d["calls"],
+                        "issued_bytes_per_launch": d["issued_bytes"] / d["calls"],
+                        "frac_on_issued_bytes": d["issued_bytes"] / (d["ms"] * 1e-3) / 1e9 / peak}
+        rec = {
+            "metric": "mtl_train_step_images_per_sec", "value": ips, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": workload_text(name, B),
+                "global_batch": B * world, "parallelism": f"dp{world}",
+                "conv_math": "tf32 (cuDNN)" if args.conv_tf32 else "fp32 (cuDNN, TF32 off)",
+                "gate_precision": args.gate_precision, "stitch_mode": args.stitch_mode,
+                "step_launch": "one CUDA graph per step (fwd + fused losses/metrics + bwd + Adam)" if graphed is not None else "eager",
+                "l2": "per-step working set (activations of a batch-%d step) >> 126 MB L2; no explicit flush" % B,
+                "backbone": "stand-in MobileNetV3-Large/Unet (smp/timm not installable offline)" if model != "mtan" else "reference MTAN mini-UNet",
+            },
+            "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes * world,
+                    "d2h_bytes_per_step": int(scal.numel() * scal.element_size()) * world,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "kernels": {k: {"calls": v["calls"], "ms_per_step": v["ms"] / ksteps, "gbps": v["gbps"],
+                            "frac_of_peak": v["gbps"] / peak,
+                            "issued_over_algorithmic_bytes": v["issued_bytes"] / max(v["bytes"], 1)}
+                        for k, v in sorted(kstats.items())},
+            "hand_written_ms_per_step": sum(v["ms"] for v in kstats.values()) / ksteps,
+        }
+    # release this workload's graphs / buffers before the next one is built
+    graphed = None
+    del module, opt, resident, staging, host
+    gc.collect()
+    barrier()
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rec["cpu_baseline"] = cpu_baseline_record(name, args, args.cpu_steps, with_port)
+        _phase(f"[{name}] cpu baseline done")
+    return rec
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+
+    from vision_mtl_b200 import dist as vdist
+    from vision_mtl_b200 import ops
+
+    rank, local_rank, world = vdist.init_distributed()
+    _phase(f"process group ready (world {world})")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    torch.backends.cudnn.allow_tf32 = bool(args.conv_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.conv_tf32)
+    torch.backends.cudnn.benchmark = True
+    ops.default_gate_precision = args.gate_precision
+
+    names = list(ALL_ORDER) if args.workload == "all" else [args.workload]
+    recs = {}
+    for i, name in enumerate(names):
+        recs[name] = run_workload(args, name, rank, local_rank, world, with_port=(i == 0))
+    if rank == 0:
+        line = recs[names[0]]
+        if len(names) > 1:
+            line["workloads"] = {n: recs[n] for n in names[1:]}
+        print(json.dumps(line))
     if world > 1:
-        # Tearing NCCL down while captured graphs still reference the communicator blocks for minutes
-        # (destroy_process_group waits on work the graphs own).  Everything is measured and printed:
-        # release the graph, line the ranks up and leave without the teardown.
+        # Tearing NCCL down after captured graphs referenced the communicator can block for minutes
+        # (destroy_process_group waits on work the graphs owned).  Everything is measured and printed:
+        # line the ranks up and leave without the teardown.
         sys.stdout.flush()
         sys.stderr.flush()
-        graphed = None
-        barrier()
+        dist.barrier()
+        torch.cuda.synchronize()
         os._exit(0)
 
 

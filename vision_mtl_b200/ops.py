@@ -37,8 +37,13 @@ default_gate_precision = "tc_3xtf32"
 # --------------------------------------------------------------------------------------
 class _Prof:
     enabled = False
-    records: list = []  # (name, algorithmic_bytes, start_event, end_event)
+    records: list = []  # (name, algorithmic_bytes, issued_bytes, start_event, end_event)
     launches = 0  # kernels launched by this library since the last reset
+    nvtx = False  # NVTX range around every library call (tools/site_bench.py --nvtx, profiling runs)
+
+
+def enable_nvtx(on: bool = True) -> None:
+    _Prof.nvtx = bool(on)
 
 
 # kernels enqueued by one C call (for the `gpu_launches` claim in bench.py)
@@ -69,21 +74,32 @@ def kernel_timing():
 
 
 def summarize_timing(records) -> dict:
-    """name -> {calls, ms, bytes, gbps}; call after torch.cuda.synchronize()."""
+    """name -> {calls, ms, bytes, issued_bytes, gbps}; call after torch.cuda.synchronize().
+    ``bytes`` are the ALGORITHMIC bytes of SURVEY 8(d) (what ``gbps`` and every roofline fraction are
+    computed from); ``issued_bytes`` are what the kernels of the call actually request from HBM."""
     out: dict = {}
-    for name, nbytes, e0, e1 in records:
-        d = out.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0})
+    for name, nbytes, issued, e0, e1 in records:
+        d = out.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0, "issued_bytes": 0})
         d["calls"] += 1
         d["ms"] += e0.elapsed_time(e1)
         d["bytes"] += nbytes
+        d["issued_bytes"] += issued
     for d in out.values():
         d["gbps"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
     return out
 
 
-def _call(name: str, algo_bytes: int, *args) -> None:
+def _call(name: str, algo_bytes: int, *args, issued: Optional[int] = None) -> None:
     fn = getattr(_lib.load(), "vmtl_" + name)
     _Prof.launches += _KERNELS_PER_CALL.get(name, 1)
+    if _Prof.nvtx:
+        torch.cuda.nvtx.range_push("vmtl_" + name)
+        try:
+            rc = fn(*args)
+        finally:
+            torch.cuda.nvtx.range_pop()
+        _lib.check(rc, "vmtl_" + name)
+        return
     if _Prof.enabled:
         # inside a stream capture the events must be "external" to become timing-capable graph nodes
         # (they are then re-recorded by every replay)
@@ -93,7 +109,7 @@ def _call(name: str, algo_bytes: int, *args) -> None:
         e0.record()
         rc = fn(*args)
         e1.record()
-        _Prof.records.append((name, algo_bytes, e0, e1))
+        _Prof.records.append((name, algo_bytes, algo_bytes if issued is None else issued, e0, e1))
     else:
         rc = fn(*args)
     _lib.check(rc, "vmtl_" + name)
@@ -197,6 +213,34 @@ def cross_stitch(xs: Sequence[torch.Tensor], alpha: torch.Tensor, mode: str = "r
 # --------------------------------------------------------------------------------------
 # MTAN attention gate
 # --------------------------------------------------------------------------------------
+def _gate_bwd_passes(M: int, N: int):
+    """(dh launches, dW launches) of the tensor-core backward (csrc/gate_tc_bwd_tma.cuh)."""
+    if N <= 64:
+        return 1, 1
+    one_tile = (M + 127) // 128 <= _lib.load().vmtl_sm_count()
+    n_dh = -(-N // 256) if one_tile else N // 64
+    n_dw = N // 128 if N % 128 == 0 else N // 64
+    return n_dh, n_dw
+
+
+def gate_bytes(M: int, K: int, N: int, training: bool, backward: bool, stored_z: bool = True):
+    """(algorithmic, issued) HBM bytes of one gate call.
+
+    Algorithmic = SURVEY 8(d): forward ``4M(K + 2N)`` in eval mode, ``4M(K + 2N + min(K, 2N))`` with batch
+    statistics (z must be stored or recomputed for the second phase); backward
+    ``4M(2K + 4N + min(K, 2N))``.  Issued = what the kernels of this library request: the forward stores and
+    re-reads z (``4M(K + 4N)``); the backward reads (dy, s, z) in the statistics pass and again in the dh
+    pass, round-trips dz in fp32 and re-reads h / re-adds dh once per column pass."""
+    if not backward:
+        algo = 4 * M * (K + 2 * N + (min(K, 2 * N) if training else 0))
+        issued = 4 * M * (K + (4 * N if training or stored_z else 2 * N))
+        return algo, issued
+    n_dh, n_dw = _gate_bwd_passes(M, N) if K == 128 else (1, 1)
+    algo = 4 * M * (2 * K + 4 * N + min(K, 2 * N))
+    issued = 4 * M * (9 * N + K * (n_dh + n_dw))
+    return algo, issued
+
+
 class GateFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, s, weight, bias, gamma, beta, running_mean, running_var, training, momentum,
@@ -217,11 +261,11 @@ class GateFunction(torch.autograd.Function):
         invstd = torch.empty(N, dtype=torch.float32, device=h.device)
         lib = _lib.load()
         ws = _workspace(lib.vmtl_gate_workspace_bytes(M, K, N, precision, 0), h.device)
-        nbytes = 4 * M * (K + (4 * N if training else 2 * N))
-        _call("gate_fwd", nbytes, _p(h), _p(s), _p(w2), _p(bias.detach()), _p(gamma.detach()),
+        algo, issued = gate_bytes(M, K, N, training, backward=False, stored_z=z is not None)
+        _call("gate_fwd", algo, _p(h), _p(s), _p(w2), _p(bias.detach()), _p(gamma.detach()),
               _p(beta.detach()), _p(running_mean), _p(running_var), float(momentum), float(eps),
               1 if training else 0, precision, M, K, N, _p(y), _p(z), _p(mean), _p(invstd), _p(ws),
-              ws.numel(), _stream())
+              ws.numel(), _stream(), issued=issued)
         ctx.training = bool(training)
         ctx.precision = precision
         ctx.dims = (M, K, N)
@@ -243,16 +287,15 @@ class GateFunction(torch.autograd.Function):
         dbeta = torch.empty_like(dbias)
         lib = _lib.load()
         ws = _workspace(lib.vmtl_gate_workspace_bytes(M, K, N, ctx.precision, 1), h.device)
-        nbytes = 4 * M * (2 * K + 7 * N)
-        _call("gate_bwd", nbytes, _p(dy), _p(h), _p(s), _p(z), _p(w2), _p(gamma.detach()),
+        algo, issued = gate_bytes(M, K, N, ctx.training, backward=True)
+        _call("gate_bwd", algo, _p(dy), _p(h), _p(s), _p(z), _p(w2), _p(gamma.detach()),
               _p(beta.detach()), _p(mean), _p(invstd), 1 if ctx.training else 0, ctx.precision, M, K, N,
-              _p(dh), _p(ds), _p(dW), _p(dbias), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream())
+              _p(dh), _p(ds), _p(dW), _p(dbias), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream(),
+              issued=issued)
         if ctx.precision != 0 and N > 64 and K == 128 and N % 64 == 0:
-            # wider gates run extra column launches (csrc/gate_tc_bwd_tma.cuh): dh per 64 columns, or per 256
-            # when every CTA owns a single 128-row tile; dW per 128 (64) columns
-            one_tile = (M + 127) // 128 <= lib.vmtl_sm_count()
-            n_dh = -(-N // 256) if one_tile else N // 64
-            n_dw = N // 128 if N % 128 == 0 else N // 64
+            # wider gates run extra column launches: dh per 64 columns, or per 256 when every CTA owns a
+            # single 128-row tile; dW per 128 (64) columns
+            n_dh, n_dw = _gate_bwd_passes(M, N)
             _Prof.launches += (n_dh - 1) + (n_dw - 1)
         return (dh, ds, dW.reshape(ctx.wshape), dbias, dgamma, dbeta, None, None, None, None, None, None)
 
