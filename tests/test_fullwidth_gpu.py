@@ -147,7 +147,7 @@ def test_csnet_step_gradients_vs_reference(name, cw):
 
 def test_csnet_small_flip_free_step_vs_reference():
     """A CSNet fixture searched to have no activation within 4e-6 of a ReLU / Hardswish kink: loss, logits,
-    running statistics and EVERY gradient of the product step against the reference's fp32 run directly."""
+    running statistics against the reference's fp32 run at 1e-4, every gradient against the fp64 yardstick."""
     from vision_mtl_b200.lit_module import MTLModule
 
     name, B, H, W, C = CSNET_SMALL
@@ -162,33 +162,11 @@ def test_csnet_small_flip_free_step_vs_reference():
     loss = module.training_step(batch, 0)
     loss.backward()
     assert abs(loss.item() - g[f"{name}/losses"][0]) <= TOL * abs(g[f"{name}/losses"][0])
-    l2 = np.array([g[f"{name}/grad64/{k}"][1] for k, _ in net.named_parameters() if f"{name}/grad64/{k}" in g.files])
-    typical = np.median(l2)
-    devs, within, worst, worst_k = [], 0, 0.0, None
-    for k, p in net.named_parameters():
-        key = f"{name}/grad/{k}"
-        if key not in g.files:
-            continue
-        ref, r64 = g[key], g[f"{name}/grad64/{k}"]
-        if r64[1] < 1e-6 * typical:  # analytically zero (the fp64 run says so): fp32 noise on both sides
-            assert p.grad is None or float(p.grad.norm()) < 1e-3 * typical, k
-            continue
-        d = float(np.abs(FX.summarize(p.grad) - ref).max() / r64[1])
-        cond = float(np.abs(ref - r64).max() / r64[1])  # the reference's own fp32 error for this parameter
-        devs.append(d)
-        within += d <= max(3.0 * cond, 5e-4)
-        if d > worst:
-            worst, worst_k = d, k
-    devs = np.array(devs)
-    print(f"[csnet_small] {len(devs)} gradients vs the reference's fp32 run: median deviation {np.median(devs):.3e} of the "
-          f"gradient norm, p90 {np.quantile(devs, 0.9):.3e}, worst {worst:.3e} at {worst_k}; "
-          f"{within}/{len(devs)} within max(5e-4, 3x the reference's own fp32-vs-fp64 error)")
-    # The fixture has no activation within 4e-6 of a kink IN THE REFERENCE'S RUN.  Through ~190 layers of
-    # strict-fp32 convolutions (cuDNN NHWC here, mkldnn NCHW there) activations drift by more than that, so a
-    # few flips -- each moving every parameter upstream of it in one task network -- cannot be excluded even
-    # here; the bulk of the parameters must agree to round-off.
-    assert np.median(devs) <= TOL, f"median gradient deviation {np.median(devs):.3e}"
-    assert within >= 0.5 * len(devs) and worst <= 0.5, f"{worst_k}: {worst:.3e}"
+    # No activation of the REFERENCE's run sits within 4e-6 of a kink, but through ~190 layers of strict-fp32
+    # convolutions (cuDNN NHWC here, mkldnn NCHW there) activations drift by more than that, and the fixture has
+    # dead channels in front of training-mode BNs (round-off amplified by 1/sqrt(eps)): the reference's own fp32
+    # run is 5e-4 (median) from its fp64 run.  Same yardstick as above.
+    yardstick([(k, p.grad) for k, p in net.named_parameters()], g, name, name)
     for k, b in net.named_buffers():
         if "num_batches_tracked" not in k:
             ref = g[f"{name}/buf/{k}"]

@@ -1,18 +1,15 @@
-// MTAN gate backward, phase B on tensor cores, TMA generation (K = 128, N = 32 or a multiple of 64).
-// Included by gate_tc.cu.  Same machinery as gate_tc_tma.cuh: raw fp32 tiles arrive in shared memory
-// by TMA (>= 128 KB per SM in flight), the tf32 hi/lo A operand lives in TENSOR MEMORY.
+// MTAN gate backward on tensor cores, TMA generation (K = 128, N = 32 or a multiple of 64).
+// Included by gate_tc.cu.  Same machinery as gate_tc_tma.cuh: raw fp32 tiles arrive in shared memory by TMA
+// (>= 128 KB per SM in flight), the tf32 hi/lo A operand lives in TENSOR MEMORY.
 //
-//   B1 gate_tc_dh_tma_kernel : unit = (128-row tile, 32-column atom a).  TMA brings dy_a, s_a, z_a
-//      ([128 x 32] each, 48 KB per unit, 3 stages).  Converter threads (one row each) rebuild
-//      dz = gamma*invstd*(du - c1 - zhat*c2), store it once to global (B2's operand), put its tf32 hi/lo
-//      parts into TMEM and accumulate db.  MMA: dh[128 x 128] +=
-//      dz_a[128 x 32] @ W[a*32.., :]  (A from TMEM, B = W^T atoms K-major in smem, 3xTF32).
-//   B2 gate_tc_dw_tma_kernel : unit = (tile, 64-row half).  TMA brings the h half ([64 x 128], raw)
-//      and the dz half straight into the MN-major tf32 operand layout (SWIZZLE_128B_ATOM_32B); the
-//      converter warps split it in place into hi / lo atoms (elementwise, layout-agnostic).  Converter threads (one hidden channel k
-//      each) transpose h^T into TMEM (lane = k, column = pixel row) as hi/lo.  MMA per 8 pixel rows:
-//          D[:, 0:2N] += h_hi^T @ [dz_hi | dz_lo] ,  D[:, 0:N] += h_lo^T @ dz_hi
-//      accumulating dW^T over ALL tiles of the CTA in TMEM; drained once.
+//   pass 1  gate_tc_sdw_tma_kernel : ds, the batch sums of the BatchNorm backward and the two pixel
+//           contractions dW is linear in (see the comment at the kernel), one read of (dy, s, z, h);
+//   finalize (gate.cu)             : dgamma, dbeta, c1, c2, dbias and dW from the per-CTA partials (fp64);
+//   pass 2  gate_tc_dh_tma_kernel  : unit = (128-row tile, 32-column atom a).  TMA brings dy_a, s_a, z_a
+//           ([128 x 32] each, 48 KB per unit).  Converter threads (one row each) rebuild
+//           dz = gamma*invstd*(du - c1 - zhat*c2) in registers and put its tf32 hi/lo parts into TMEM.
+//           MMA: dh[128 x 128] += dz_a[128 x 32] @ W[a*32.., :]  (A from TMEM, B = W^T atoms K-major in smem,
+//           3xTF32); dh leaves as TMA bulk stores.  dz never touches HBM.
 #pragma once
 
 namespace vmtl {
@@ -38,9 +35,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
                           const float* __restrict__ coefA, const float* __restrict__ coefB,
                           const float* __restrict__ mean, const float* __restrict__ invstd,
                           const float* __restrict__ c1, const float* __restrict__ c2, int64_t M,
-                          const __grid_constant__ CUtensorMap tmap_dz_st,
-                          float* __restrict__ dh, float* __restrict__ db_partial /* [grid][n_total] */,
-                          int n0 /* first gate column of this pass */, int n_total, int accumulate /* dh += */) {
+                          float* __restrict__ dh, int n0 /* first gate column of this pass */,
+                          int accumulate /* dh += */) {
   using namespace tc;
   using L = DhTmaSmem<NA>;
   constexpr int S = L::kStages;
@@ -125,9 +121,6 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 
   const int64_t ntiles = (M + kTileM - 1) / kTileM;
   const int64_t nitems = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  float db_acc[NCH * NA];
-#pragma unroll
-  for (int a = 0; a < NCH * NA; ++a) db_acc[a] = 0.f;
 
   if (warp < 8) {
     // ------------------------------------------------------------------ converters (thread = row)
@@ -191,17 +184,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
             hi[e] = tf32_hi(d[e]);
             lo[e] = d[e] - hi[e];
           }
-          // dz (fp32, B2 splits it itself) leaves through the stage buffer: once every converter holds its
-          // inputs in registers, slot 0 of the stage is rewritten (swizzled) and the TMA warp bulk-stores it
-          // before it refills the stage -- no row-per-thread global stores.
-          named_barrier_sync(3, 256);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t o = sw128_off(row, ch * 4 + j);
-            *reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + o) = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
-          }
-          fence_proxy_async_smem();
-          mbar_arrive(bar_empty(s));  // = "dz staged": the TMA warp stores it, then reuses the stage
+          mbar_arrive(bar_empty(s));  // this thread holds everything it needs from stage s in registers
           if (a == 0) {
             if (NCH > 1) {
               // W^T of this chunk replaces the previous one: the MMAs of (tile, chunk) tc-1 must be done
@@ -222,7 +205,6 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           tmem_wait_st();
           tc_fence_before_sync();
           mbar_arrive(bar_aready(tb, a));
-          db_acc[c * NA + a] += butterfly_colsum<16>(d, lane);  // lanes l and l+16 both hold column (l % 16)
         }
       }
     }
@@ -280,12 +262,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       const int64_t nunits = nitems * UPT;
       for (int64_t u = 0; u < nunits; ++u) {
         const int s = (int)(u % S);
-        if (u >= S) {  // unit u-S: its dz is staged in this stage -> bulk-store it, then the stage is free
-          mbar_wait(bar_empty(s), (uint32_t)(((u / S) - 1) & 1));
-          tma_store_2d(&tmap_dz_st, unit_col0(u - S), unit_row0(u - S), smem_u32(smem + s * L::kStage));
-          tma_store_commit();
-          tma_store_wait_read();
-        }
+        if (u >= S) mbar_wait(bar_empty(s), (uint32_t)(((u / S) - 1) & 1));  // every converter has read unit u-S
         mbar_expect_tx(bar_full(s), (uint32_t)L::kStage);
         const uint32_t dst = smem_u32(smem + s * L::kStage);
         const int row0 = unit_row0(u), col0 = unit_col0(u);
@@ -293,14 +270,6 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         tma_load_2d(dst + L::kSlot, &tmap_s, col0, row0, bar_full(s));
         tma_load_2d(dst + 2 * L::kSlot, &tmap_z, col0, row0, bar_full(s));
       }
-      // drain: the last min(S, nunits) units are still staged
-      for (int64_t v = nunits > S ? nunits - S : 0; v < nunits; ++v) {
-        const int s = (int)(v % S);
-        mbar_wait(bar_empty(s), (uint32_t)((v / S) & 1));
-        tma_store_2d(&tmap_dz_st, unit_col0(v), unit_row0(v), smem_u32(smem + s * L::kStage));
-        tma_store_commit();
-      }
-      tma_store_wait_all();
     }
   } else if (lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
@@ -339,65 +308,72 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 17) tmem_dealloc(tmem_base, kTmemCols);
-  // db partial of this CTA: the four quadrant warps of each 16-column group, fixed order
-  constexpr int NAT = NCH * NA;                  // 32-column atoms of this launch
-  float* s_red = reinterpret_cast<float*>(smem);  // [8 converter warps][NAT][16]
-  if (warp < 8 && lane < 16) {
-#pragma unroll
-    for (int a = 0; a < NAT; ++a) s_red[(warp * NAT + a) * 16 + lane] = db_acc[a];
-  }
-  __syncthreads();
-  for (int col = threadIdx.x; col < NAT * 32; col += kTmaThreads) {
-    const int a = col >> 5, ch = (col >> 4) & 1, l = col & 15;
-    float acc = 0.f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc += s_red[((ch * 4 + q) * NAT + a) * 16 + l];
-    db_partial[(int64_t)blockIdx.x * n_total + n0 + col] = acc;
-  }
 }
 
-// ------------------------------------------------------------------------------------------- B2
+// ------------------------------------------------------------------------------------------- pass 1
+// Statistics + dW in ONE pass over (dy, s, z, h).  dz = A (du - c1 - zhat c2) needs the batch sums c1 = sum(du)/M,
+// c2 = sum(du zhat)/M first -- but dW is LINEAR in them:
+//     dW[n,k] = sum_r dz[r,n] h[r,k] = A_n ( P1[n,k] - c1_n hsum[k] - c2_n P2[n,k] ),
+//     P1 = du^T h,  P2 = zhat^T h,  hsum = sum_r h[r,:]
+// so this kernel accumulates P1, P2, hsum and the column sums (sum du, sum du zhat, sum zhat) while it writes
+// ds = dy a, and a finalize kernel combines them once the sums are known.  No dz tensor is ever written, and
+// (dy, s, z) are read here once and in the dh pass once: 4M(2K + 7N) bytes per gate backward instead of 4M(2K + 9N).
+//
+// unit = 64 pixel rows x NA 32-column atoms.  TMA brings the h half ([64 x 128], SW128) and dy, z, s straight into the
+// MN-major tf32 operand layout (SWIZZLE_128B_ATOM_32B).  Converter warps: (i) transpose h^T into TMEM as hi/lo
+// (lane = hidden channel, column = pixel row), (ii) walk the 16-byte chunks of dy / z / s in place -- elementwise,
+// so the swizzle only matters for finding a chunk's columns -- and overwrite them with the B operand
+//     [du_hi | zhat_hi | du_lo | zhat_lo]   (4 NA atoms; du_hi <- dy's slot, zhat_hi <- z's, du_lo <- s's)
+// while ds leaves for global memory as full 128-byte lines.  MMA per 8 pixel rows:
+//     D[:, 0:4N'] += h_hi^T @ [du_hi | zhat_hi | du_lo | zhat_lo] ,  D[:, 0:2N'] += h_lo^T @ [du_hi | zhat_hi]
+// accumulating over ALL units of the CTA in TMEM (4 N' = 128 or 256 columns); drained once.
 template <int NA>
-struct DwTmaSmem {
+struct SdwSmem {
   static constexpr int kHalfRows = 64;
   static constexpr int kSlotH = kHalfRows * 128;             // one K-atom of the h half [64 rows x 128 B]
   static constexpr int kStageH = 4 * kSlotH;                 // 32 KB
-  static constexpr int kSlotD = kHalfRows * 128;             // one 32-column atom of a dz half, MN-major
-  static constexpr int kStageD = 2 * NA * kSlotD;            // atoms [hi_0.. hi_NA-1, lo_0.. lo_NA-1]
-  static constexpr int kStage = kStageH + kStageD;           // 48 KB (N=32) / 64 KB (N=64)
-  static constexpr int kStages = NA == 1 ? 4 : (NA == 2 ? 3 : 2);  // 48 / 64 / 96 KB per stage
+  static constexpr int kSlotD = kHalfRows * 128;             // one 32-column atom of a [64 x N'] operand, MN-major
+  static constexpr int kStageD = 4 * NA * kSlotD;            // atom groups: du_hi, zhat_hi, du_lo, zhat_lo
+  static constexpr int kStage = kStageH + kStageD;           // 64 KB (N' = 32) / 96 KB (N' = 64)
+  static constexpr int kStages = NA == 1 ? 3 : 2;            // 192 KB in flight either way
   static constexpr int kMisc = kStages * kStage;
-  static constexpr int kBytes = kMisc + 256 + 1024;
+  static constexpr int kCoef = 4 * NA * 32 * 4;              // A, B, mean, invstd of this launch's columns
+  static constexpr int kBytes = kMisc + 256 + kCoef + 1024;
 };
 
 template <int NA, bool SPLIT>
 __global__ void __launch_bounds__(kTmaThreads, 1)
-    gate_tc_dw_tma_kernel(const __grid_constant__ CUtensorMap tmap_h /* box [32 x 64], SW128 */,
-                          const __grid_constant__ CUtensorMap tmap_dz /* box [32 x 64], SW128_ATOM_32B */,
-                          int64_t M,
-                          float* __restrict__ dw_partial /* [grid][n_total][128] */, int n0, int n_total) {
+    gate_tc_sdw_tma_kernel(const __grid_constant__ CUtensorMap tmap_h /* box [32 x 64], SW128 */,
+                           const __grid_constant__ CUtensorMap tmap_dy /* box [32 x 64], SW128_ATOM_32B */,
+                           const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_s,
+                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                           const float* __restrict__ mean, const float* __restrict__ invstd, int64_t M,
+                           float* __restrict__ ds /* [M, n_total] or nullptr */,
+                           float* __restrict__ pw_partial /* [grid][2][n_total][128]: P1, P2 */,
+                           float* __restrict__ hs_partial /* [grid][128] (written by the n0 == 0 launch) */,
+                           float* __restrict__ col_partial /* [grid][3][n_total]: sum du, sum du zhat, sum zhat */,
+                           int n0, int n_total) {
   using namespace tc;
-  using L = DwTmaSmem<NA>;
+  using L = SdwSmem<NA>;
   constexpr int S = L::kStages;
   constexpr int N = NA * 32;
   constexpr int KH = 128;
-  constexpr int DC = SPLIT ? 2 * N : N;
+  constexpr int DC = SPLIT ? 4 * N : 2 * N;  // accumulator columns
   constexpr uint32_t kACols = 256;  // A half buffer hb: hi [hb*128, +64), lo [hb*128+64, +64); column = pixel row
   constexpr uint32_t kTmemCols = 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer (LDS/STS, not generic LD/ST)
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::kMisc);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::kMisc + 192);
+  float* s_coef = reinterpret_cast<float*>(smem + L::kMisc + 256);  // [4][N]: A, B, mean, invstd
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(s_bar);
   auto bar_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
-  auto bar_hfree = [&](int s) { return bar0 + 32u + 8u * (uint32_t)s; };   // converters done with the h part
   auto bar_aready = [&](int b) { return bar0 + 64u + 8u * (uint32_t)b; };
   auto bar_umma = [&](int s) { return bar0 + 80u + 8u * (uint32_t)s; };    // MMAs of the unit in stage s done
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_hfree(s), 256);
       mbar_init(bar_umma(s), 1);
     }
     for (int i = 0; i < 2; ++i) mbar_init(bar_aready(i), 256);
@@ -406,7 +382,16 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   if (warp == 17) tmem_alloc(smem_u32(s_tmem), kTmemCols);
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmap_h);
-    tma_prefetch_desc(&tmap_dz);
+    tma_prefetch_desc(&tmap_dy);
+    tma_prefetch_desc(&tmap_z);
+    tma_prefetch_desc(&tmap_s);
+  }
+  for (int i = threadIdx.x; i < N; i += kTmaThreads) {
+    const float a = gamma[n0 + i] * invstd[n0 + i];
+    s_coef[i] = a;
+    s_coef[N + i] = beta[n0 + i] - mean[n0 + i] * a;
+    s_coef[2 * N + i] = mean[n0 + i];
+    s_coef[3 * N + i] = invstd[n0 + i];
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -417,53 +402,98 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   const int64_t nhalves = (M + L::kHalfRows - 1) / L::kHalfRows;  // units of 64 pixel rows
   const int64_t nunits = blockIdx.x < nhalves ? (nhalves - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
+  // per-thread sums (converter threads only): hidden channel k over its 32-row half; 4 gate columns per atom
+  float hsum_acc = 0.f;
+  float acc_du[NA][4], acc_dz[NA][4], acc_z[NA][4];
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc_du[a][e] = acc_dz[a][e] = acc_z[a][e] = 0.f;
+  // this thread's 16-byte chunk inside an atom: physical chunk (tid % 8) of row (tid / 8) [+ 32]; the ATOM_32B swizzle
+  // XORs the 32-byte index with (row % 4), which is the same for both rows -> a fixed logical column group
+  const int cj = (int)(threadIdx.x & 7), crow = (int)((threadIdx.x >> 3) & 31);
+  const int cl = ((((cj >> 1) ^ (crow & 3)) << 1) | (cj & 1));  // logical 16-byte chunk: columns 4*cl .. 4*cl+3 of the atom
+
   if (warp < 8) {
-    // ------------------------------------------------------------------ converters (thread = channel k)
+    // ------------------------------------------------------------------ converters
     const int quad = warp & 3, rh = warp >> 2;  // lane quadrant (k / 32), 32-row half of the unit
     const int k = quad * 32 + lane;
     for (int64_t u = 0; u < nunits; ++u) {
       const int s = (int)(u % S), hb = (int)(u & 1);
+      const int64_t row0 = (blockIdx.x + u * gridDim.x) * L::kHalfRows;
       mbar_wait(bar_full(s), (uint32_t)((u / S) & 1));
-      const uint8_t* hs = smem + s * L::kStage + (k >> 5) * L::kSlotH;  // K-atom holding channel k
-      float hv[32];
+      uint8_t* stage = smem + s * L::kStage;
+      {  // (i) h^T -> TMEM (thread = hidden channel k)
+        const uint8_t* hs = stage + (k >> 5) * L::kSlotH;  // K-atom holding channel k
+        float hv[32];
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        const int row = rh * 32 + r;
-        hv[r] = *reinterpret_cast<const float*>(hs + sw128_off(row, (k & 31) >> 2) + ((k & 3) << 2));
-      }
-      mbar_arrive(bar_hfree(s));
-      if (u >= 2) {  // the MMAs of unit u-2 (same A half buffer) are done
-        const int64_t up = u - 2;
-        mbar_wait(bar_umma((int)(up % S)), (uint32_t)((up / S) & 1));
-        tc_fence_after_sync();
-      }
-      const uint32_t ta = tmem_base + (((uint32_t)quad * 32) << 16) + (uint32_t)(hb * 128 + rh * 32);
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        float hi[16], lo[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          hi[e] = tf32_hi(hv[g * 16 + e]);
-          lo[e] = hv[g * 16 + e] - hi[e];
+        for (int r = 0; r < 32; ++r) {
+          const int row = rh * 32 + r;
+          hv[r] = *reinterpret_cast<const float*>(hs + sw128_off(row, (k & 31) >> 2) + ((k & 3) << 2));
+          hsum_acc += hv[r];
         }
-        tmem_st16(ta + g * 16, hi);
-        if (SPLIT) tmem_st16(ta + 64 + g * 16, lo);
-      }
-      if (SPLIT) {
-        // dz arrived raw (fp32) in the MN-major atoms [0, NA): split it in place into tf32 hi (same place) and
-        // lo (atoms [NA, 2NA)).  Elementwise, so the swizzle does not matter: walk the 16-byte chunks.
-        uint8_t* dzs = smem + s * L::kStage + L::kStageH;
-#pragma unroll
-        for (int i = 0; i < NA * 2; ++i) {
-          const uint32_t o = (uint32_t)(threadIdx.x + 256 * i) * 16u;  // NA * 8 KB / 16 B = NA * 512 chunks
-          const float4 a = *reinterpret_cast<const float4*>(dzs + o);
-          const float4 hi4 = make_float4(tf32_hi(a.x), tf32_hi(a.y), tf32_hi(a.z), tf32_hi(a.w));
-          *reinterpret_cast<float4*>(dzs + o) = hi4;
-          *reinterpret_cast<float4*>(dzs + NA * L::kSlotD + o) =
-              make_float4(a.x - hi4.x, a.y - hi4.y, a.z - hi4.z, a.w - hi4.w);
+        if (u >= 2) {  // the MMAs of unit u-2 (same A half buffer) are done
+          const int64_t up = u - 2;
+          mbar_wait(bar_umma((int)(up % S)), (uint32_t)((up / S) & 1));
+          tc_fence_after_sync();
         }
-        fence_proxy_async_smem();
+        const uint32_t ta = tmem_base + (((uint32_t)quad * 32) << 16) + (uint32_t)(hb * 128 + rh * 32);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float hi[16], lo[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            hi[e] = tf32_hi(hv[g * 16 + e]);
+            lo[e] = hv[g * 16 + e] - hi[e];
+          }
+          tmem_st16(ta + g * 16, hi);
+          if (SPLIT) tmem_st16(ta + 64 + g * 16, lo);
+        }
       }
+      // (ii) dy, z, s -> ds (global) and the B operand [du_hi | zhat_hi | du_lo | zhat_lo], in place
+      uint8_t* dsm = stage + L::kStageH;
+#pragma unroll
+      for (int i = 0; i < NA * 2; ++i) {
+        const int atom = i >> 1;
+        const int row = crow + 32 * (i & 1);
+        const uint32_t o = (uint32_t)(threadIdx.x + 256 * (i & 1)) * 16u;
+        const float4 gy = *reinterpret_cast<const float4*>(dsm + (0 * NA + atom) * L::kSlotD + o);
+        const float4 zv = *reinterpret_cast<const float4*>(dsm + (1 * NA + atom) * L::kSlotD + o);
+        const float4 sv = *reinterpret_cast<const float4*>(dsm + (2 * NA + atom) * L::kSlotD + o);
+        const int col = atom * 32 + cl * 4;
+        const float4 A = *reinterpret_cast<const float4*>(s_coef + col);
+        const float4 B = *reinterpret_cast<const float4*>(s_coef + N + col);
+        const float4 mu = *reinterpret_cast<const float4*>(s_coef + 2 * N + col);
+        const float4 rs = *reinterpret_cast<const float4*>(s_coef + 3 * N + col);
+        const bool valid = row0 + row < M;  // rows past M arrive as zeros: du = ds = 0 there, zhat must be forced
+        const float gyv[4] = {gy.x, gy.y, gy.z, gy.w}, zvv[4] = {zv.x, zv.y, zv.z, zv.w}, svv[4] = {sv.x, sv.y, sv.z, sv.w};
+        const float Av[4] = {A.x, A.y, A.z, A.w}, Bv[4] = {B.x, B.y, B.z, B.w};
+        const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, rsv[4] = {rs.x, rs.y, rs.z, rs.w};
+        float dsv[4], du[4], zh[4], duh[4], zhh[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float act = sigmoidf_acc(fmaf(Av[e], zvv[e], Bv[e]));
+          dsv[e] = gyv[e] * act;
+          du[e] = gyv[e] * svv[e] * act * (1.f - act);
+          zh[e] = valid ? (zvv[e] - muv[e]) * rsv[e] : 0.f;
+          acc_du[atom][e] += du[e];
+          acc_dz[atom][e] = fmaf(du[e], zh[e], acc_dz[atom][e]);
+          acc_z[atom][e] += zh[e];
+          duh[e] = tf32_hi(du[e]);
+          zhh[e] = tf32_hi(zh[e]);
+        }
+        if (ds != nullptr && valid)
+          stg_stream(reinterpret_cast<float4*>(ds + (row0 + row) * n_total + n0 + col), make_float4(dsv[0], dsv[1], dsv[2], dsv[3]));
+        *reinterpret_cast<float4*>(dsm + (0 * NA + atom) * L::kSlotD + o) = make_float4(duh[0], duh[1], duh[2], duh[3]);
+        *reinterpret_cast<float4*>(dsm + (1 * NA + atom) * L::kSlotD + o) = make_float4(zhh[0], zhh[1], zhh[2], zhh[3]);
+        if (SPLIT) {
+          *reinterpret_cast<float4*>(dsm + (2 * NA + atom) * L::kSlotD + o) =
+              make_float4(du[0] - duh[0], du[1] - duh[1], du[2] - duh[2], du[3] - duh[3]);
+          *reinterpret_cast<float4*>(dsm + (3 * NA + atom) * L::kSlotD + o) =
+              make_float4(zh[0] - zhh[0], zh[1] - zhh[1], zh[2] - zhh[2], zh[3] - zhh[3]);
+        }
+      }
+      fence_proxy_async_smem();
       tmem_wait_st();
       tc_fence_before_sync();
       mbar_arrive(bar_aready(hb));
@@ -473,29 +503,30 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     if (lane == 0) {
       for (int64_t u = 0; u < nunits; ++u) {
         const int s = (int)(u % S);
-        if (u >= S) {  // stage reusable: converters have read h (hfree) and the unit's MMAs have read dz (umma)
-          mbar_wait(bar_hfree(s), (uint32_t)(((u / S) - 1) & 1));
-          mbar_wait(bar_umma(s), (uint32_t)(((u / S) - 1) & 1));
-        }
+        // stage reusable once the MMAs of its previous unit are done (they were issued after every converter
+        // had finished reading and rewriting the stage)
+        if (u >= S) mbar_wait(bar_umma(s), (uint32_t)(((u / S) - 1) & 1));
         const int row0 = (int)((blockIdx.x + u * gridDim.x) * L::kHalfRows);
-        mbar_expect_tx(bar_full(s), (uint32_t)(L::kStageH + L::kStageD / 2));
+        mbar_expect_tx(bar_full(s), (uint32_t)(L::kStageH + 3 * NA * L::kSlotD));
         const uint32_t dst = smem_u32(smem + s * L::kStage);
 #pragma unroll
         for (int a = 0; a < 4; ++a) tma_load_2d(dst + a * L::kSlotH, &tmap_h, a * 32, row0, bar_full(s));
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
-          tma_load_2d(dst + L::kStageH + a * L::kSlotD, &tmap_dz, n0 + a * 32, row0, bar_full(s));
+          const uint32_t d0 = dst + L::kStageH + a * L::kSlotD;
+          tma_load_2d(d0, &tmap_dy, n0 + a * 32, row0, bar_full(s));
+          tma_load_2d(d0 + NA * L::kSlotD, &tmap_z, n0 + a * 32, row0, bar_full(s));
+          tma_load_2d(d0 + 2 * NA * L::kSlotD, &tmap_s, n0 + a * 32, row0, bar_full(s));
         }
       }
     }
   } else if (warp == 17 && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_wide = idesc_tf32(KH, DC, 0, 1);  // A from TMEM (K-major form), B MN-major
-    constexpr uint32_t idesc_n = idesc_tf32(KH, N, 0, 1);
+    constexpr uint32_t idesc_n = idesc_tf32(KH, 2 * N, 0, 1);
     for (int64_t u = 0; u < nunits; ++u) {
       const int s = (int)(u % S), hb = (int)(u & 1);
       mbar_wait(bar_aready(hb), (uint32_t)((u >> 1) & 1));
-      mbar_wait(bar_full(s), (uint32_t)((u / S) & 1));  // dz operands landed (usually long ago)
       tc_fence_after_sync();
       const uint32_t bD = smem_u32(smem + s * L::kStage + L::kStageH);
 #pragma unroll
@@ -511,7 +542,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   // warps 8-15 have no per-unit work in this kernel: they only help drain the accumulator
   tc_fence_before_sync();
   __syncthreads();
-  float* out = dw_partial + ((int64_t)blockIdx.x * n_total + n0) * KH;
+  float* out = pw_partial + ((int64_t)blockIdx.x * 2 * n_total + n0) * KH;
+  const int64_t q_stride = (int64_t)n_total * KH;  // P1 -> P2
   if (nunits > 0) {
     if (warp == 17 && lane == 0) {  // wait for the last unit's MMAs
       const int64_t ul = nunits - 1;
@@ -519,29 +551,63 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
     __syncthreads();
     tc_fence_after_sync();
-    if (warp < 8) {  // thread (k = lane quadrant row) drains dW^T[k][n]; partial layout is dW[n][k]
+    if (warp < 8) {  // thread (k = lane quadrant row) drains [P1 | P2][k][n]; partial layout is [q][n][k]
       const int k = (warp & 3) * 32 + lane;
       const int col0 = (warp >> 2) * (N / 2);
       const uint32_t taddr = tmem_d + (((uint32_t)(warp & 3) * 32) << 16) + (uint32_t)col0;
 #pragma unroll
-      for (int j = 0; j < N / 2; j += 16) {
-        float t16[16], t2[16];
-        tmem_ld16(taddr + j, t16);
-        if (SPLIT) {
-          tmem_ld16(taddr + N + j, t2);
+      for (int q = 0; q < 2; ++q) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) t16[e] += t2[e];
+        for (int j = 0; j < N / 2; j += 16) {
+          float t16[16], t2[16];
+          tmem_ld16(taddr + q * N + j, t16);
+          if (SPLIT) {
+            tmem_ld16(taddr + (2 + q) * N + j, t2);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) t16[e] += t2[e];
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) out[q * q_stride + (int64_t)(col0 + j + e) * KH + k] = t16[e];
         }
-#pragma unroll
-        for (int e = 0; e < 16; ++e) out[(int64_t)(col0 + j + e) * KH + k] = t16[e];
       }
     }
   } else {
-    for (int e = threadIdx.x; e < N * KH; e += kTmaThreads) out[e] = 0.f;
+    for (int e = threadIdx.x; e < 2 * N * KH; e += kTmaThreads)
+      out[(e / (N * KH)) * q_stride + (e % (N * KH))] = 0.f;
   }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 17) tmem_dealloc(tmem_base, kTmemCols);
+  // ---- per-CTA column sums and hsum: fixed-order block reductions through shared memory (stage 0 is idle) ----
+  float* s_red = reinterpret_cast<float*>(smem);  // [256][NA][12] then [256] hsum
+  float* s_hs = s_red + 256 * NA * 12;
+  if (warp < 8) {
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        s_red[(threadIdx.x * NA + a) * 12 + e] = acc_du[a][e];
+        s_red[(threadIdx.x * NA + a) * 12 + 4 + e] = acc_dz[a][e];
+        s_red[(threadIdx.x * NA + a) * 12 + 8 + e] = acc_z[a][e];
+      }
+    s_hs[threadIdx.x] = hsum_acc;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 3 * N; o += kTmaThreads) {
+    const int q = o / N, col = o % N;
+    const int atom = col >> 5, c = (col & 31) >> 2, e = col & 3;
+    float acc = 0.f;
+    for (int t = 0; t < 256; ++t) {  // the 32 converter threads whose chunk holds this column, in thread order
+      const int tj = t & 7, tr = (t >> 3) & 31;
+      if (((((tj >> 1) ^ (tr & 3)) << 1) | (tj & 1)) == c) acc += s_red[(t * NA + atom) * 12 + q * 4 + e];
+    }
+    col_partial[((int64_t)blockIdx.x * 3 + q) * n_total + n0 + col] = acc;
+  }
+  if (n0 == 0)
+    for (int k = threadIdx.x; k < KH; k += kTmaThreads) {
+      // converter thread (quad, rh) held channel k = quad*32 + lane: tid = (rh*4 + quad)*32 + lane
+      hs_partial[(int64_t)blockIdx.x * KH + k] = s_hs[k] + s_hs[128 + k];
+    }
 }
 
 // N = 32 or any multiple of 64.  dh: one launch covers up to 256 gate columns (NCH chunks of 64 whose dh
