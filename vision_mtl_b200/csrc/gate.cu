@@ -10,10 +10,12 @@
 //   fwd  phase 1 : contraction, writes z, per-CTA column partials (sum z, sum z^2)
 //        finalize: fp64 fixed-order reduction -> mean, invstd, running-stat update, (A,B)
 //        phase 2 : y = s * sigmoid(A*z + B)                       streams z,s -> y
-//   bwd  phase A : ds = dy*a ; per-channel sum du, sum du*zhat    streams dy,s,z -> ds
-//        finalize: dbeta, dgamma (and c1 = dbeta/M, c2 = dgamma/M)
-//        phase B : dz = gamma*invstd*(du - c1 - zhat*c2) ; dh = dz W ; dW = dz^T h ; db = sum dz
-// Algorithmic bytes (train): fwd 4M(K + 4N), bwd 4M(2K + 7N)  (K = 128).
+//   bwd  pass 1  : ds = dy*a ; per-channel sum du, sum du*zhat ; P1 = du^T h, P2 = zhat^T h, hsum
+//        finalize: dbeta, dgamma, c1 = dbeta/M, c2 = dgamma/M, dW = A (P1 - c1 hsum - c2 P2), db
+//        pass 2  : dz = gamma*invstd*(du - c1 - zhat*c2) per tile in registers ; dh = dz W
+//   (the CUDA-core path keeps the direct form: phase A statistics, dz materialised, two sgemms)
+// Issued bytes (train, tensor-core path): fwd 4M(K + 4N), bwd 4M(2K + 7N) (K = 128): the backward
+// reads (dy, s, z) twice (statistics + dW pass, dh pass), h once, writes ds and dh; dz never exists in HBM.
 #include <math.h>
 
 #include "gate_internal.cuh"
@@ -214,6 +216,55 @@ __global__ void gate_bwd_stats_finalize(const float* __restrict__ partial, int n
   invstd_out[c] = invstd[c];
 }
 
+// ---- backward finalize of the tensor-core path ---------------------------------------------------
+// Per-CTA partials of pass 1 (gate_tc_bwd_tma.cuh) -> every parameter gradient, in fp64, fixed order:
+//   dbeta = sum du, dgamma = sum du zhat, c1 = dbeta/M, c2 = dgamma/M (0 in eval mode),
+//   dW[n,k] = A_n (P1[n,k] - c1_n hsum[k] - c2_n P2[n,k]),  dbias_n = A_n (sum du - M c1 - c2 sum zhat)
+// (dbias is analytically zero under batch statistics: what is left is the round-off of sum zhat).
+// Blocks [0, N*K/32): 32 consecutive k of one dW row; the rest: 32 gate columns of the per-channel outputs,
+// which also publish the folded coefficients pass 2 needs.
+__global__ void gate_bwd_tc_finalize(const float* __restrict__ pw_partial, const float* __restrict__ hs_partial,
+                                     const float* __restrict__ col_partial, int nparts, int64_t M, int N, int K,
+                                     int training, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     float* __restrict__ dW, float* __restrict__ dbias, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, float* __restrict__ c1, float* __restrict__ c2,
+                                     float* __restrict__ coefA, float* __restrict__ coefB, float* __restrict__ mean_out,
+                                     float* __restrict__ invstd_out) {
+  const int lx = threadIdx.x & 31;
+  const int nb_w = N * K / 32;
+  if ((int)blockIdx.x < nb_w) {  // block-uniform
+    const int n = (int)blockIdx.x / (K / 32), k = ((int)blockIdx.x % (K / 32)) * 32 + lx;
+    double sdu, sdz, p1, p2;
+    block_colsum2(col_partial, nparts, 3 * (int64_t)N, n, N + n, true, &sdu, &sdz);
+    const double hs = block_colsum(hs_partial, nparts, (int64_t)K, k, true);
+    block_colsum2(pw_partial, nparts, 2 * (int64_t)N * K, (int64_t)n * K + k, (int64_t)(N + n) * K + k, true, &p1, &p2);
+    if (threadIdx.x >= 32) return;
+    const double k1 = training ? sdu / (double)M : 0.0, k2 = training ? sdz / (double)M : 0.0;
+    const double a = (double)gamma[n] * (double)invstd[n];
+    dW[(int64_t)n * K + k] = (float)(a * (p1 - k1 * hs - k2 * p2));
+    return;
+  }
+  const int c = ((int)blockIdx.x - nb_w) * 32 + lx;
+  const bool ok = c < N;
+  double sdu, sdz;
+  block_colsum2(col_partial, nparts, 3 * (int64_t)N, ok ? c : 0, N + (ok ? c : 0), ok, &sdu, &sdz);
+  const double sz = block_colsum(col_partial, nparts, 3 * (int64_t)N, 2 * (int64_t)N + (ok ? c : 0), ok);
+  if (threadIdx.x >= 32 || !ok) return;
+  const double k1 = training ? sdu / (double)M : 0.0, k2 = training ? sdz / (double)M : 0.0;
+  const double a = (double)gamma[c] * (double)invstd[c];
+  dbeta[c] = (float)sdu;
+  dgamma[c] = (float)sdz;
+  dbias[c] = (float)(a * (sdu - (double)M * k1 - k2 * sz));
+  c1[c] = (float)k1;
+  c2[c] = (float)k2;
+  const float af = gamma[c] * invstd[c];  // same fp32 arithmetic as pass 1 used for the activation
+  coefA[c] = af;
+  coefB[c] = beta[c] - mean[c] * af;
+  mean_out[c] = mean[c];
+  invstd_out[c] = invstd[c];
+}
+
 // ---- backward: materialise dz (fp32 FFMA path) + db partials ------------------------------
 __global__ void __launch_bounds__(kEwThreads)
     gate_bwd_dz_kernel(const float* __restrict__ dy, const float* __restrict__ s,
@@ -248,19 +299,6 @@ __global__ void rows_sum_finalize(const float* __restrict__ partial, int nparts,
                                   float* __restrict__ out) {
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   const double s = block_colsum(partial, nparts, (int64_t)len, j < len ? j : 0, j < len);
-  if (threadIdx.x < 32 && j < len) out[j] = (float)s;
-}
-
-// two independent row sums in one launch: blocks [0, ceil(len_a / 32)) take a, the rest b
-__global__ void rows_sum_finalize2(const float* __restrict__ part_a, int nparts_a, int len_a, float* __restrict__ out_a,
-                                   const float* __restrict__ part_b, int nparts_b, int len_b, float* __restrict__ out_b) {
-  const int nb_a = (len_a + 31) / 32;
-  const bool is_a = (int)blockIdx.x < nb_a;  // block-uniform
-  const float* part = is_a ? part_a : part_b;
-  const int nparts = is_a ? nparts_a : nparts_b, len = is_a ? len_a : len_b;
-  float* out = is_a ? out_a : out_b;
-  const int j = ((int)blockIdx.x - (is_a ? 0 : nb_a)) * 32 + (threadIdx.x & 31);
-  const double s = block_colsum(part, nparts, (int64_t)len, j < len ? j : 0, j < len);
   if (threadIdx.x < 32 && j < len) out[j] = (float)s;
 }
 
@@ -441,6 +479,19 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, co
   const int C4 = N / 4;
   const int split3 = precision == VMTL_GATE_TC_3XTF32;
 
+  if (precision != VMTL_GATE_FP32_FFMA && gate_tc_supported(K, N)) {
+    // tensor-core path: pass 1 (ds + statistics + dW partials), finalize, pass 2 (dh)
+    int np1 = 0;
+    rc = gate_tc_bwd_pass1(dy, h, s, z, gamma, beta, save_mean, save_invstd, M, K, N, split3, ds, ws, &np1, st);
+    if (rc != VMTL_OK) return rc;
+    gate_bwd_tc_finalize<<<N * K / 32 + (N + 31) / 32, kFinThreads, 0, st>>>(
+        ws.gemm_partial, ws.hs_partial, ws.partial, np1, M, N, K, training, gamma, beta, save_mean, save_invstd, dW,
+        dbias, dgamma, dbeta, ws.c1, ws.c2, ws.coefA, ws.coefB, ws.mean, ws.invstd);
+    if ((rc = launch_status()) != VMTL_OK) return rc;
+    return dh ? gate_tc_bwd_dh(dy, s, z, W, ws, M, K, N, split3, dh, st) : VMTL_OK;
+  }
+
+  // CUDA-core path
   // phase A
   const int nparts = ew_grid(M, N, blocks_per_sm(gate_bwd_stats_kernel, kEwThreads, 0, 8));
   gate_bwd_stats_kernel<<<nparts, kEwThreads, 0, st>>>(dy, s, z, M, C4, gamma, beta, save_mean, save_invstd,
@@ -452,19 +503,6 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, co
   if ((rc = launch_status()) != VMTL_OK) return rc;
 
   // phase B
-  if (precision != VMTL_GATE_FP32_FFMA) {
-    int nslots = 0;
-    // db partials reuse ws.partial (phase A has been consumed by the finalize above)
-    rc = gate_tc_bwd_gemm(dy, h, s, z, W, ws, gamma, M, K, N, split3, dh, ws.gemm_partial, ws.gemm_slots,
-                          &nslots, ws.partial, st);
-    if (rc == VMTL_OK) {
-      rows_sum_finalize2<<<(N * K + 31) / 32 + (N + 31) / 32, kFinThreads, 0, st>>>(
-          ws.gemm_partial, nslots, N * K, dW, ws.partial, nslots, N, dbias);
-      return launch_status();
-    }
-    if (rc != VMTL_EUNSUPPORTED) return rc;
-    // shape not covered by the tensor-core backward: CUDA-core contraction below
-  }
   gate_bwd_dz_kernel<<<nparts, kEwThreads, 0, st>>>(dy, s, z, M, C4, ws.coefA, ws.coefB, ws.mean,
                                                     ws.invstd, ws.c1, ws.c2, ws.dz, ws.partial);
   if ((rc = launch_status()) != VMTL_OK) return rc;

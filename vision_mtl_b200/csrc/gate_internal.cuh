@@ -18,7 +18,8 @@ struct GateWs {
   int partial_rows;
   float* gemm_partial;  // [gemm_slots][N*K] split-K / per-CTA dW partials
   int gemm_slots;
-  float* dz;            // [M,N] fp32: written once by the dh kernel, read once by the dW kernel
+  float* dz;            // [M,N] fp32 dz of the CUDA-core backward (not allocated for tensor-core shapes)
+  float* hs_partial;    // [sm_count][K] per-CTA column sums of h (tensor-core backward)
   float* zbuf;          // [M,N] forward scratch for z when the caller passes no save_z and the shape is
                         // outside the tensor-core kernels (CUDA-core path, eval mode)
 };
@@ -45,8 +46,9 @@ inline size_t gate_ws_floats(int64_t M, int K, int N, int precision, int backwar
   w.partial = take((size_t)w.partial_rows * 2 * N);
   w.gemm_slots = backward ? sm_count() * 2 : 0;
   w.gemm_partial = take((size_t)w.gemm_slots * N * K);
-  w.dz = backward ? take((size_t)M * N) : nullptr;
   const bool tc = precision != VMTL_GATE_FP32_FFMA && gate_tc_supported(K, N);
+  w.dz = (backward && !tc) ? take((size_t)M * N) : nullptr;
+  w.hs_partial = (backward && tc) ? take((size_t)sm_count() * K) : nullptr;
   w.zbuf = (!backward && !tc) ? take((size_t)M * N) : nullptr;
   if (ws) *ws = w;
   return off;
@@ -62,11 +64,14 @@ int gate_tc_fwd_gemm(const float* h, const float* W, const float* bias, int64_t 
 int gate_tc_fwd_eval(const float* h, const float* s, const float* W, const float* bias,
                      const float* coefA, const float* coefB, int64_t M, int K, int N, int split3,
                      float* y, cudaStream_t st);
-// Backward phase B: dz recomputed per tile from (dy, s, z); dh = dz @ W ; dW partial per CTA;
-// db partial per CTA.
-int gate_tc_bwd_gemm(const float* dy, const float* h, const float* s, const float* z, const float* W,
-                     const GateWs& ws, const float* gamma, int64_t M, int K, int N, int split3,
-                     float* dh, float* dw_partial, int slots, int* nslots, float* db_partial,
-                     cudaStream_t st);
+// Backward pass 1 (statistics + dW partials + ds): per-CTA partials land in ws.gemm_partial
+// ([*nparts][2][N][K]: P1 = du^T h, P2 = zhat^T h), ws.hs_partial ([*nparts][K]: sum_r h) and ws.partial
+// ([*nparts][3][N]: sum du, sum du*zhat, sum zhat); gate.cu's finalize turns them into the gradients.
+int gate_tc_bwd_pass1(const float* dy, const float* h, const float* s, const float* z, const float* gamma,
+                      const float* beta, const float* mean, const float* invstd, int64_t M, int K, int N,
+                      int split3, float* ds, const GateWs& ws, int* nparts, cudaStream_t st);
+// Backward pass 2: dh = dz @ W with dz rebuilt per tile from (dy, s, z) and the finalized ws.c1 / ws.c2.
+int gate_tc_bwd_dh(const float* dy, const float* s, const float* z, const float* W, const GateWs& ws, int64_t M,
+                   int K, int N, int split3, float* dh, cudaStream_t st);
 
 }  // namespace vmtl

@@ -64,28 +64,31 @@ int gate_tc_fwd_eval(const float* h, const float* s, const float* W, const float
   return dispatch_fwd_tma<true>(h, W, bias, M, N, split3, y, nullptr, s, coefA, coefB, grid, st);
 }
 
-static int tc_grid(int64_t M) {
-  const int64_t ntiles = (M + kTileM - 1) / kTileM;
+static int tc_grid(int64_t M, int rows) {
+  const int64_t n = (M + rows - 1) / rows;
   const int sms = sm_count();
-  return (int)(ntiles < sms ? ntiles : sms);
+  return (int)(n < sms ? n : sms);
 }
 
-int gate_tc_bwd_gemm(const float* dy, const float* h, const float* s, const float* z, const float* W,
-                     const GateWs& ws, const float* gamma, int64_t M, int K, int N, int split3,
-                     float* dh, float* dw_partial, int slots, int* nslots, float* db_partial,
-                     cudaStream_t st) {
-  (void)gamma;
-  if (!gate_tc_supported(K, N) || !ws.dz) return VMTL_EUNSUPPORTED;
-  const int grid = tc_grid(M);
-  if (grid > slots || grid > ws.partial_rows) return VMTL_EWORKSPACE;
-  *nslots = grid;
-#define VMTL_BWD_TMA(NDW)                                                                                    \
-  (split3 ? launch_bwd_tma<NDW, true>(dy, h, s, z, W, ws, M, N, dh, dw_partial, db_partial, grid, st)         \
-          : launch_bwd_tma<NDW, false>(dy, h, s, z, W, ws, M, N, dh, dw_partial, db_partial, grid, st))
-  if (N == 32) return VMTL_BWD_TMA(1);
-  if (N % 128 == 0) return VMTL_BWD_TMA(4);
-  return VMTL_BWD_TMA(2);
-#undef VMTL_BWD_TMA
+int gate_tc_bwd_pass1(const float* dy, const float* h, const float* s, const float* z, const float* gamma,
+                      const float* beta, const float* mean, const float* invstd, int64_t M, int K, int N,
+                      int split3, float* ds, const GateWs& ws, int* nparts, cudaStream_t st) {
+  if (!gate_tc_supported(K, N) || !ws.hs_partial) return VMTL_EUNSUPPORTED;
+  const int grid = tc_grid(M, 64);
+  if (2 * grid > ws.gemm_slots || 3 * grid > 2 * ws.partial_rows) return VMTL_EWORKSPACE;
+  *nparts = grid;
+  return split3 ? launch_sdw_tma<true>(dy, h, s, z, gamma, beta, mean, invstd, M, N, ds, ws.gemm_partial, ws.hs_partial,
+                                       ws.partial, grid, st)
+                : launch_sdw_tma<false>(dy, h, s, z, gamma, beta, mean, invstd, M, N, ds, ws.gemm_partial,
+                                        ws.hs_partial, ws.partial, grid, st);
+}
+
+int gate_tc_bwd_dh(const float* dy, const float* s, const float* z, const float* W, const GateWs& ws, int64_t M,
+                   int K, int N, int split3, float* dh, cudaStream_t st) {
+  if (!gate_tc_supported(K, N)) return VMTL_EUNSUPPORTED;
+  const int grid = tc_grid(M, kTileM);
+  return split3 ? launch_dh_passes<true>(dy, s, z, W, ws, M, N, dh, grid, st)
+                : launch_dh_passes<false>(dy, s, z, W, ws, M, N, dh, grid, st);
 }
 
 }  // namespace vmtl

@@ -610,60 +610,72 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
 }
 
-// N = 32 or any multiple of 64.  dh: one launch covers up to 256 gate columns (NCH chunks of 64 whose dh
-// contributions accumulate in TMEM, W^T restaged per chunk); wider gates take further launches that add into
-// dh with TMA reduce-adds.  dW: passes of NA_DW*32 columns (2*NA_DW*32 accumulator columns in TMEM), each
-// pass re-reading h.
+// ------------------------------------------------------------------------------------------- host side
+// N = 32 or any multiple of 64.
+// pass 1: N = 32 -> one launch (NA = 1); otherwise one launch per 64 columns (NA = 2: 256 accumulator columns in TMEM),
+//         each re-reading h.  All launches share the grid, so every partial buffer is indexed by blockIdx.
+template <bool SPLIT>
+static int launch_sdw_tma(const float* dy, const float* h, const float* s, const float* z, const float* gamma,
+                          const float* beta, const float* mean, const float* invstd, int64_t M, int N, float* ds,
+                          float* pw_partial, float* hs_partial, float* col_partial, int grid, cudaStream_t st) {
+  CUtensorMap t_h, t_dy, t_z, t_s;
+  if (!make_tmap_2d_sw(&t_h, h, M, 128, 64, false) || !make_tmap_2d_sw(&t_dy, dy, M, N, 64, true) ||
+      !make_tmap_2d_sw(&t_z, z, M, N, 64, true) || !make_tmap_2d_sw(&t_s, s, M, N, 64, true))
+    return VMTL_ECUDA;
+  if (N == 32) {
+    auto k = gate_tc_sdw_tma_kernel<1, SPLIT>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SdwSmem<1>::kBytes) != cudaSuccess)
+      return VMTL_ECUDA;
+    k<<<grid, kTmaThreads, SdwSmem<1>::kBytes, st>>>(t_h, t_dy, t_z, t_s, gamma, beta, mean, invstd, M, ds, pw_partial,
+                                                     hs_partial, col_partial, 0, N);
+    return launch_status();
+  }
+  auto k = gate_tc_sdw_tma_kernel<2, SPLIT>;
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SdwSmem<2>::kBytes) != cudaSuccess)
+    return VMTL_ECUDA;
+  for (int n0 = 0; n0 < N; n0 += 64) {
+    k<<<grid, kTmaThreads, SdwSmem<2>::kBytes, st>>>(t_h, t_dy, t_z, t_s, gamma, beta, mean, invstd, M, ds, pw_partial,
+                                                     hs_partial, col_partial, n0, N);
+    const int rc = launch_status();
+    if (rc != VMTL_OK) return rc;
+  }
+  return VMTL_OK;
+}
+
+// pass 2: one launch covers up to 256 gate columns (NCH chunks of 64 whose dh contributions accumulate in TMEM, W^T
+// restaged per chunk); wider gates take further launches that add into dh with TMA reduce-adds.
 template <int NA_DH, int NCH, bool SPLIT>
 static int launch_dh_tma(const CUtensorMap& t_dy, const CUtensorMap& t_s, const CUtensorMap& t_z, const CUtensorMap& t_dh,
-                         const CUtensorMap& t_dz_st, const float* W, const GateWs& ws, int64_t M, int N, float* dh,
-                         float* db_partial, int n0, int grid, cudaStream_t st) {
+                         const float* W, const GateWs& ws, int64_t M, float* dh, int n0, int grid, cudaStream_t st) {
   auto k1 = gate_tc_dh_tma_kernel<NA_DH, NCH, SPLIT>;
   if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, DhTmaSmem<NA_DH>::kBytes) != cudaSuccess)
     return VMTL_ECUDA;
   k1<<<grid, kTmaThreads, DhTmaSmem<NA_DH>::kBytes, st>>>(t_dy, t_s, t_z, t_dh, W, ws.coefA, ws.coefB, ws.mean, ws.invstd,
-                                                           ws.c1, ws.c2, M, t_dz_st, dh, db_partial, n0, N, n0 != 0);
+                                                           ws.c1, ws.c2, M, dh, n0, n0 != 0);
   return launch_status();
 }
 
-template <int NA_DW, bool SPLIT>
-static int launch_bwd_tma(const float* dy, const float* h, const float* s, const float* z, const float* W,
-                          const GateWs& ws, int64_t M, int N, float* dh, float* dw_partial, float* db_partial,
-                          int grid, cudaStream_t st) {
-  float* dz = ws.dz;  // [M, N] fp32, written once by B1, read once by B2
-  CUtensorMap t_dy, t_s, t_z, t_h, t_dz, t_dh, t_dz_st;
+template <bool SPLIT>
+static int launch_dh_passes(const float* dy, const float* s, const float* z, const float* W, const GateWs& ws, int64_t M,
+                            int N, float* dh, int grid, cudaStream_t st) {
+  CUtensorMap t_dy, t_s, t_z, t_dh;
   if (!make_tmap_2d_sw(&t_dy, dy, M, N, kTileM, false) || !make_tmap_2d_sw(&t_s, s, M, N, kTileM, false) ||
-      !make_tmap_2d_sw(&t_z, z, M, N, kTileM, false) || !make_tmap_2d_sw(&t_h, h, M, 128, 64, false) ||
-      !make_tmap_2d_sw(&t_dz, dz, M, N, 64, true) ||
-      !make_tmap_2d_sw(&t_dh, dh ? dh : h, M, 128, kTileM, false) ||
-      !make_tmap_2d_sw(&t_dz_st, dz, M, N, kTileM, false))
+      !make_tmap_2d_sw(&t_z, z, M, N, kTileM, false) || !make_tmap_2d_sw(&t_dh, dh, M, 128, kTileM, false))
     return VMTL_ECUDA;
-  auto k2 = gate_tc_dw_tma_kernel<NA_DW, SPLIT>;
-  if (cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, DwTmaSmem<NA_DW>::kBytes) != cudaSuccess)
-    return VMTL_ECUDA;
-  if (N == 32) {
-    const int rc = launch_dh_tma<1, 1, SPLIT>(t_dy, t_s, t_z, t_dh, t_dz_st, W, ws, M, N, dh, db_partial, 0, grid, st);
-    if (rc != VMTL_OK) return rc;
-  } else {
-    // One launch over several chunks pays a W^T restage per (tile, chunk); it wins only where a CTA has a
-    // single tile anyway (then the alternative is one latency-bound launch per chunk).  Otherwise: one
-    // 64-column pass per launch, later passes add into dh.
-    const int cols_per_launch = (M + kTileM - 1) / kTileM <= grid ? 256 : 64;
-    for (int n0 = 0; n0 < N; n0 += cols_per_launch) {
-      const int nch = (N - n0 >= cols_per_launch ? cols_per_launch : N - n0) / 64;
-      int rc;
-      switch (nch) {
-        case 1: rc = launch_dh_tma<2, 1, SPLIT>(t_dy, t_s, t_z, t_dh, t_dz_st, W, ws, M, N, dh, db_partial, n0, grid, st); break;
-        case 2: rc = launch_dh_tma<2, 2, SPLIT>(t_dy, t_s, t_z, t_dh, t_dz_st, W, ws, M, N, dh, db_partial, n0, grid, st); break;
-        case 3: rc = launch_dh_tma<2, 3, SPLIT>(t_dy, t_s, t_z, t_dh, t_dz_st, W, ws, M, N, dh, db_partial, n0, grid, st); break;
-        default: rc = launch_dh_tma<2, 4, SPLIT>(t_dy, t_s, t_z, t_dh, t_dz_st, W, ws, M, N, dh, db_partial, n0, grid, st); break;
-      }
-      if (rc != VMTL_OK) return rc;
+  if (N == 32) return launch_dh_tma<1, 1, SPLIT>(t_dy, t_s, t_z, t_dh, W, ws, M, dh, 0, grid, st);
+  // One launch over several chunks pays a W^T restage per (tile, chunk); it wins only where a CTA has a
+  // single tile anyway (then the alternative is one latency-bound launch per chunk).  Otherwise: one
+  // 64-column pass per launch, later passes add into dh.
+  const int cols_per_launch = (M + kTileM - 1) / kTileM <= grid ? 256 : 64;
+  for (int n0 = 0; n0 < N; n0 += cols_per_launch) {
+    const int nch = (N - n0 >= cols_per_launch ? cols_per_launch : N - n0) / 64;
+    int rc;
+    switch (nch) {
+      case 1: rc = launch_dh_tma<2, 1, SPLIT>(t_dy, t_s, t_z, t_dh, W, ws, M, dh, n0, grid, st); break;
+      case 2: rc = launch_dh_tma<2, 2, SPLIT>(t_dy, t_s, t_z, t_dh, W, ws, M, dh, n0, grid, st); break;
+      case 3: rc = launch_dh_tma<2, 3, SPLIT>(t_dy, t_s, t_z, t_dh, W, ws, M, dh, n0, grid, st); break;
+      default: rc = launch_dh_tma<2, 4, SPLIT>(t_dy, t_s, t_z, t_dh, W, ws, M, dh, n0, grid, st); break;
     }
-  }
-  for (int n0 = 0; n0 < N; n0 += NA_DW * 32) {
-    k2<<<grid, kTmaThreads, DwTmaSmem<NA_DW>::kBytes, st>>>(t_h, t_dz, M, dw_partial, n0, N);
-    const int rc = launch_status();
     if (rc != VMTL_OK) return rc;
   }
   return VMTL_OK;

@@ -48,7 +48,7 @@ def enable_nvtx(on: bool = True) -> None:
 
 # kernels enqueued by one C call (for the `gpu_launches` claim in bench.py)
 _KERNELS_PER_CALL = {
-    "xstitch_fwd": 1, "xstitch_bwd": 2, "gate_fwd": 3, "gate_bwd": 5, "head_ce_fwd": 2,
+    "xstitch_fwd": 1, "xstitch_bwd": 2, "gate_fwd": 3, "gate_bwd": 3, "head_ce_fwd": 2,
     "head_ce_bwd": 2, "ce_logits_fwd": 2, "ce_logits_bwd": 1, "head_silog_fwd": 2,
     "head_silog_bwd": 2, "confusion_accum": 1, "depth_err_sums": 2, "seg_metrics": 1,
 }
@@ -214,13 +214,12 @@ def cross_stitch(xs: Sequence[torch.Tensor], alpha: torch.Tensor, mode: str = "r
 # MTAN attention gate
 # --------------------------------------------------------------------------------------
 def _gate_bwd_passes(M: int, N: int):
-    """(dh launches, dW launches) of the tensor-core backward (csrc/gate_tc_bwd_tma.cuh)."""
+    """(pass-1 launches, dh launches) of the tensor-core backward (csrc/gate_tc_bwd_tma.cuh)."""
     if N <= 64:
         return 1, 1
     one_tile = (M + 127) // 128 <= _lib.load().vmtl_sm_count()
     n_dh = -(-N // 256) if one_tile else N // 64
-    n_dw = N // 128 if N % 128 == 0 else N // 64
-    return n_dh, n_dw
+    return N // 64, n_dh
 
 
 def gate_bytes(M: int, K: int, N: int, training: bool, backward: bool, stored_z: bool = True):
@@ -229,15 +228,15 @@ def gate_bytes(M: int, K: int, N: int, training: bool, backward: bool, stored_z:
     Algorithmic = SURVEY 8(d): forward ``4M(K + 2N)`` in eval mode, ``4M(K + 2N + min(K, 2N))`` with batch
     statistics (z must be stored or recomputed for the second phase); backward
     ``4M(2K + 4N + min(K, 2N))``.  Issued = what the kernels of this library request: the forward stores and
-    re-reads z (``4M(K + 4N)``); the backward reads (dy, s, z) in the statistics pass and again in the dh
-    pass, round-trips dz in fp32 and re-reads h / re-adds dh once per column pass."""
+    re-reads z (``4M(K + 4N)``); the backward reads (dy, s, z) in the statistics + dW pass and again in the dh
+    pass (``4M(2K + 7N)``; wide gates re-read h / re-add dh once per 64-column pass)."""
     if not backward:
         algo = 4 * M * (K + 2 * N + (min(K, 2 * N) if training else 0))
         issued = 4 * M * (K + (4 * N if training or stored_z else 2 * N))
         return algo, issued
-    n_dh, n_dw = _gate_bwd_passes(M, N) if K == 128 else (1, 1)
+    n_p1, n_dh = _gate_bwd_passes(M, N) if K == 128 else (1, 1)
     algo = 4 * M * (2 * K + 4 * N + min(K, 2 * N))
-    issued = 4 * M * (9 * N + K * (n_dh + n_dw))
+    issued = 4 * M * (7 * N + K * (n_p1 + n_dh))
     return algo, issued
 
 
@@ -293,10 +292,10 @@ class GateFunction(torch.autograd.Function):
               _p(dh), _p(ds), _p(dW), _p(dbias), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream(),
               issued=issued)
         if ctx.precision != 0 and N > 64 and K == 128 and N % 64 == 0:
-            # wider gates run extra column launches: dh per 64 columns, or per 256 when every CTA owns a
-            # single 128-row tile; dW per 128 (64) columns
-            n_dh, n_dw = _gate_bwd_passes(M, N)
-            _Prof.launches += (n_dh - 1) + (n_dw - 1)
+            # wider gates run extra column launches: pass 1 per 64 columns; dh per 64 columns, or per 256
+            # when every CTA owns a single 128-row tile
+            n_p1, n_dh = _gate_bwd_passes(M, N)
+            _Prof.launches += (n_p1 - 1) + (n_dh - 1)
         return (dh, ds, dW.reshape(ctx.wshape), dbias, dgamma, dbeta, None, None, None, None, None, None)
 
 
