@@ -221,48 +221,116 @@ __global__ void gate_bwd_stats_finalize(const float* __restrict__ partial, int n
 //   dbeta = sum du, dgamma = sum du zhat, c1 = dbeta/M, c2 = dgamma/M (0 in eval mode),
 //   dW[n,k] = A_n (P1[n,k] - c1_n hsum[k] - c2_n P2[n,k]),  dbias_n = A_n (sum du - M c1 - c2 sum zhat)
 // (dbias is analytically zero under batch statistics: what is left is the round-off of sum zhat).
-// Blocks [0, N*K/32): 32 consecutive k of one dW row; the rest: 32 gate columns of the per-channel outputs,
-// which also publish the folded coefficients pass 2 needs.
-__global__ void gate_bwd_tc_finalize(const float* __restrict__ pw_partial, const float* __restrict__ hs_partial,
-                                     const float* __restrict__ col_partial, int nparts, int64_t M, int N, int K,
-                                     int training, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     const float* __restrict__ mean, const float* __restrict__ invstd,
-                                     float* __restrict__ dW, float* __restrict__ dbias, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta, float* __restrict__ c1, float* __restrict__ c2,
-                                     float* __restrict__ coefA, float* __restrict__ coefB, float* __restrict__ mean_out,
-                                     float* __restrict__ invstd_out) {
-  const int lx = threadIdx.x & 31;
-  const int nb_w = N * K / 32;
+// CTA b of pass 1 owned the column chunk b % nch: the partials of chunk c are rows c, c + nch, ... of each buffer.
+//
+// Blocks [0, N/4 * K/32): one [4 rows n x 32 k] patch of dW each.  1024 threads = 32 k-lanes x (4 rows x 8 part groups): every thread sums its share
+// of the partial rows (a handful of independent loads in flight), the 8 groups are combined in a fixed order.
+// The last ceil(N/32) blocks produce the per-channel outputs and the folded coefficients pass 2 needs.
+constexpr int kFinRows = 4, kFinGroups = 8;
+__global__ void __launch_bounds__(kFinThreads)
+    gate_bwd_tc_finalize(const float* __restrict__ pw_partial, const float* __restrict__ hs_partial,
+                         const float* __restrict__ col_partial, int nparts, int nch, int64_t M, int N, int K,
+                         int training, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ dW,
+                         float* __restrict__ dbias, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                         float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ coefA,
+                         float* __restrict__ coefB, float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int Nc = N / nch, per_chunk = nparts / nch;
+  const int kslabs = K / 32;
+  const int nb_w = (N / kFinRows) * kslabs;
+  __shared__ double s_acc[4][32][33];
   if ((int)blockIdx.x < nb_w) {  // block-uniform
-    const int n = (int)blockIdx.x / (K / 32), k = ((int)blockIdx.x % (K / 32)) * 32 + lx;
-    double sdu, sdz, p1, p2;
-    block_colsum2(col_partial, nparts, 3 * (int64_t)N, n, N + n, true, &sdu, &sdz);
-    const double hs = block_colsum(hs_partial, nparts, (int64_t)K, k, true);
-    block_colsum2(pw_partial, nparts, 2 * (int64_t)N * K, (int64_t)n * K + k, (int64_t)(N + n) * K + k, true, &p1, &p2);
-    if (threadIdx.x >= 32) return;
+    const int r = ly % kFinRows, pg = ly / kFinRows;
+    const int n = ((int)blockIdx.x / kslabs) * kFinRows + r, k = ((int)blockIdx.x % kslabs) * 32 + lx;
+    const int c = n / Nc, nl = n % Nc;  // the 4 rows of a patch share their chunk (Nc is a multiple of 4)
+    const float* pw = pw_partial + (int64_t)c * 2 * Nc * K;
+    const int64_t pw_stride = (int64_t)nch * 2 * Nc * K;
+    const float* hp = hs_partial + (int64_t)c * K;  // any chunk's CTAs cover every unit exactly once: use this one's
+    const float* cp = col_partial + (int64_t)c * 3 * Nc;
+    double a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
+    // the kernel is one dependent-latency chain per thread: keep 4 partial rows (up to 16 loads) in flight
+    int p = pg;
+    for (; p + 3 * kFinGroups < per_chunk; p += 4 * kFinGroups) {
+      float v1[4], v2[4], v3[4], v4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int pp = p + q * kFinGroups;
+        v1[q] = pw[pp * pw_stride + (int64_t)nl * K + k];
+        v2[q] = pw[pp * pw_stride + (int64_t)(Nc + nl) * K + k];
+        v3[q] = r == 0 ? hp[(int64_t)pp * nch * K + k] : 0.f;
+        v4[q] = lx < 2 ? cp[(int64_t)pp * nch * 3 * Nc + lx * Nc + nl] : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a1 += (double)v1[q];
+        a2 += (double)v2[q];
+        a3 += (double)v3[q];
+        a4 += (double)v4[q];
+      }
+    }
+    for (; p < per_chunk; p += kFinGroups) {
+      a1 += (double)pw[p * pw_stride + (int64_t)nl * K + k];
+      a2 += (double)pw[p * pw_stride + (int64_t)(Nc + nl) * K + k];
+      if (r == 0) a3 += (double)hp[(int64_t)p * nch * K + k];
+      if (lx < 2) a4 += (double)cp[(int64_t)p * nch * 3 * Nc + lx * Nc + nl];
+    }
+    s_acc[0][ly][lx] = a1;
+    s_acc[1][ly][lx] = a2;
+    s_acc[2][ly][lx] = a3;
+    s_acc[3][ly][lx] = a4;
+    __syncthreads();
+    if (pg != 0) return;
+    double p1 = 0.0, p2 = 0.0, hs = 0.0, sdu = 0.0, sdz = 0.0;
+#pragma unroll
+    for (int g = 0; g < kFinGroups; ++g) {
+      p1 += s_acc[0][g * kFinRows + r][lx];
+      p2 += s_acc[1][g * kFinRows + r][lx];
+      hs += s_acc[2][g * kFinRows][lx];
+      sdu += s_acc[3][g * kFinRows + r][0];
+      sdz += s_acc[3][g * kFinRows + r][1];
+    }
     const double k1 = training ? sdu / (double)M : 0.0, k2 = training ? sdz / (double)M : 0.0;
     const double a = (double)gamma[n] * (double)invstd[n];
     dW[(int64_t)n * K + k] = (float)(a * (p1 - k1 * hs - k2 * p2));
     return;
   }
-  const int c = ((int)blockIdx.x - nb_w) * 32 + lx;
-  const bool ok = c < N;
-  double sdu, sdz;
-  block_colsum2(col_partial, nparts, 3 * (int64_t)N, ok ? c : 0, N + (ok ? c : 0), ok, &sdu, &sdz);
-  const double sz = block_colsum(col_partial, nparts, 3 * (int64_t)N, 2 * (int64_t)N + (ok ? c : 0), ok);
-  if (threadIdx.x >= 32 || !ok) return;
+  const int col = ((int)blockIdx.x - nb_w) * 32 + lx;  // 32 consecutive columns never straddle a chunk (Nc = 32 or 64)
+  const bool ok = col < N;
+  const int c = (ok ? col : 0) / Nc, nl = (ok ? col : 0) % Nc;
+  const float* cp = col_partial + (int64_t)c * 3 * Nc;
+  double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (ok)
+    for (int p = ly; p < per_chunk; p += 32) {
+      const float* row = cp + (int64_t)p * nch * 3 * Nc;
+      a1 += (double)row[nl];
+      a2 += (double)row[Nc + nl];
+      a3 += (double)row[2 * Nc + nl];
+    }
+  s_acc[0][ly][lx] = a1;
+  s_acc[1][ly][lx] = a2;
+  s_acc[2][ly][lx] = a3;
+  __syncthreads();
+  if (ly != 0 || !ok) return;
+  double sdu = 0.0, sdz = 0.0, sz = 0.0;
+#pragma unroll
+  for (int g = 0; g < 32; ++g) {
+    sdu += s_acc[0][g][lx];
+    sdz += s_acc[1][g][lx];
+    sz += s_acc[2][g][lx];
+  }
   const double k1 = training ? sdu / (double)M : 0.0, k2 = training ? sdz / (double)M : 0.0;
-  const double a = (double)gamma[c] * (double)invstd[c];
-  dbeta[c] = (float)sdu;
-  dgamma[c] = (float)sdz;
-  dbias[c] = (float)(a * (sdu - (double)M * k1 - k2 * sz));
-  c1[c] = (float)k1;
-  c2[c] = (float)k2;
-  const float af = gamma[c] * invstd[c];  // same fp32 arithmetic as pass 1 used for the activation
-  coefA[c] = af;
-  coefB[c] = beta[c] - mean[c] * af;
-  mean_out[c] = mean[c];
-  invstd_out[c] = invstd[c];
+  const double a = (double)gamma[col] * (double)invstd[col];
+  dbeta[col] = (float)sdu;
+  dgamma[col] = (float)sdz;
+  dbias[col] = (float)(a * (sdu - (double)M * k1 - k2 * sz));
+  c1[col] = (float)k1;
+  c2[col] = (float)k2;
+  const float af = gamma[col] * invstd[col];  // same fp32 arithmetic as pass 1 used for the activation
+  coefA[col] = af;
+  coefB[col] = beta[col] - mean[col] * af;
+  mean_out[col] = mean[col];
+  invstd_out[col] = invstd[col];
 }
 
 // ---- backward: materialise dz (fp32 FFMA path) + db partials ------------------------------
@@ -484,8 +552,8 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, co
     int np1 = 0;
     rc = gate_tc_bwd_pass1(dy, h, s, z, gamma, beta, save_mean, save_invstd, M, K, N, split3, ds, ws, &np1, st);
     if (rc != VMTL_OK) return rc;
-    gate_bwd_tc_finalize<<<N * K / 32 + (N + 31) / 32, kFinThreads, 0, st>>>(
-        ws.gemm_partial, ws.hs_partial, ws.partial, np1, M, N, K, training, gamma, beta, save_mean, save_invstd, dW,
+    gate_bwd_tc_finalize<<<(N / kFinRows) * (K / 32) + (N + 31) / 32, kFinThreads, 0, st>>>(
+        ws.gemm_partial, ws.hs_partial, ws.partial, np1, N <= 64 ? 1 : N / 64, M, N, K, training, gamma, beta, save_mean, save_invstd, dW,
         dbias, dgamma, dbeta, ws.c1, ws.c2, ws.coefA, ws.coefB, ws.mean, ws.invstd);
     if ((rc = launch_status()) != VMTL_OK) return rc;
     return dh ? gate_tc_bwd_dh(dy, s, z, W, ws, M, K, N, split3, dh, st) : VMTL_OK;

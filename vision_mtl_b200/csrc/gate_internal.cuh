@@ -19,7 +19,8 @@ struct GateWs {
   float* gemm_partial;  // [gemm_slots][N*K] split-K / per-CTA dW partials
   int gemm_slots;
   float* dz;            // [M,N] fp32 dz of the CUDA-core backward (not allocated for tensor-core shapes)
-  float* hs_partial;    // [sm_count][K] per-CTA column sums of h (tensor-core backward)
+  float* hs_partial;    // [hs_rows][K] per-CTA column sums of h (tensor-core backward)
+  int hs_rows;
   float* zbuf;          // [M,N] forward scratch for z when the caller passes no save_z and the shape is
                         // outside the tensor-core kernels (CUDA-core path, eval mode)
 };
@@ -48,7 +49,8 @@ inline size_t gate_ws_floats(int64_t M, int K, int N, int precision, int backwar
   w.gemm_partial = take((size_t)w.gemm_slots * N * K);
   const bool tc = precision != VMTL_GATE_FP32_FFMA && gate_tc_supported(K, N);
   w.dz = (backward && !tc) ? take((size_t)M * N) : nullptr;
-  w.hs_partial = (backward && tc) ? take((size_t)sm_count() * K) : nullptr;
+  w.hs_rows = sm_count() + 16;  // grid of pass 1: <= sm_count, or the chunk count (<= 16) on a tiny device
+  w.hs_partial = (backward && tc) ? take((size_t)w.hs_rows * K) : nullptr;
   w.zbuf = (!backward && !tc) ? take((size_t)M * N) : nullptr;
   if (ws) *ws = w;
   return off;
@@ -64,9 +66,10 @@ int gate_tc_fwd_gemm(const float* h, const float* W, const float* bias, int64_t 
 int gate_tc_fwd_eval(const float* h, const float* s, const float* W, const float* bias,
                      const float* coefA, const float* coefB, int64_t M, int K, int N, int split3,
                      float* y, cudaStream_t st);
-// Backward pass 1 (statistics + dW partials + ds): per-CTA partials land in ws.gemm_partial
-// ([*nparts][2][N][K]: P1 = du^T h, P2 = zhat^T h), ws.hs_partial ([*nparts][K]: sum_r h) and ws.partial
-// ([*nparts][3][N]: sum du, sum du*zhat, sum zhat); gate.cu's finalize turns them into the gradients.
+// Backward pass 1 (statistics + dW partials + ds).  CTA b of the *nparts CTAs owns the column chunk b % nch
+// (nch = N <= 64 ? 1 : N / 64, chunk width Nc = N / nch); its partials land in ws.gemm_partial ([b][2][Nc][K]:
+// P1 = du^T h, P2 = zhat^T h), ws.hs_partial ([b][K]: sum_r h over its units) and ws.partial ([b][3][Nc]: sum du,
+// sum du*zhat, sum zhat); gate.cu's finalize turns them into the gradients.
 int gate_tc_bwd_pass1(const float* dy, const float* h, const float* s, const float* z, const float* gamma,
                       const float* beta, const float* mean, const float* invstd, int64_t M, int K, int N,
                       int split3, float* ds, const GateWs& ws, int* nparts, cudaStream_t st);

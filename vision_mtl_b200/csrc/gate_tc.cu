@@ -74,13 +74,22 @@ int gate_tc_bwd_pass1(const float* dy, const float* h, const float* s, const flo
                       const float* beta, const float* mean, const float* invstd, int64_t M, int K, int N,
                       int split3, float* ds, const GateWs& ws, int* nparts, cudaStream_t st) {
   if (!gate_tc_supported(K, N) || !ws.hs_partial) return VMTL_EUNSUPPORTED;
-  const int grid = tc_grid(M, 64);
-  if (2 * grid > ws.gemm_slots || 3 * grid > 2 * ws.partial_rows) return VMTL_EWORKSPACE;
+  // (64-row unit, column chunk) items over the SMs; the grid is a multiple of the chunk count
+  const int nch = N <= 64 ? 1 : N / 64;
+  const int64_t items = ((M + 63) / 64) * nch;
+  int grid = (int)(items < sm_count() ? items : sm_count());
+  grid = grid / nch * nch;
+  if (grid < nch) grid = nch;
+  // per-CTA partials: [2][Nc][K] in ws.gemm_partial (2 sm_count slots of N*K), [3][Nc] in ws.partial, [K] in ws.hs_partial
+  const int Nc = N <= 64 ? N : 64;
+  if ((int64_t)grid * 2 * Nc > (int64_t)ws.gemm_slots * N || (int64_t)grid * 3 * Nc > (int64_t)ws.partial_rows * 2 * N ||
+      grid > ws.hs_rows)
+    return VMTL_EWORKSPACE;
   *nparts = grid;
   return split3 ? launch_sdw_tma<true>(dy, h, s, z, gamma, beta, mean, invstd, M, N, ds, ws.gemm_partial, ws.hs_partial,
-                                       ws.partial, grid, st)
+                                       ws.partial, grid, nch, st)
                 : launch_sdw_tma<false>(dy, h, s, z, gamma, beta, mean, invstd, M, N, ds, ws.gemm_partial,
-                                        ws.hs_partial, ws.partial, grid, st);
+                                        ws.hs_partial, ws.partial, grid, nch, st);
 }
 
 int gate_tc_bwd_dh(const float* dy, const float* s, const float* z, const float* W, const GateWs& ws, int64_t M,

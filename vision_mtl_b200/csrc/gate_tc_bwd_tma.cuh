@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
               k2 = __ldg(reinterpret_cast<const float4*>(c2 + col));
             }
             auto dz1 = [](float g, float sv, float zv, float A_, float B_, float mu_, float r_, float k1_, float k2_) {
-              const float act = sigmoidf_acc(fmaf(A_, zv, B_));
+              const float act = sigmoidf_fast(fmaf(A_, zv, B_));
               return A_ * (g * sv * act * (1.f - act) - k1_ - (zv - mu_) * r_ * k2_);
             };
             d[4 * j] = dz1(vdy[j].x, vs[j].x, vz[j].x, A.x, B.x, mu.x, rs.x, k1.x, k2.x);
@@ -349,10 +349,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
                            const float* __restrict__ gamma, const float* __restrict__ beta,
                            const float* __restrict__ mean, const float* __restrict__ invstd, int64_t M,
                            float* __restrict__ ds /* [M, n_total] or nullptr */,
-                           float* __restrict__ pw_partial /* [grid][2][n_total][128]: P1, P2 */,
-                           float* __restrict__ hs_partial /* [grid][128] (written by the n0 == 0 launch) */,
-                           float* __restrict__ col_partial /* [grid][3][n_total]: sum du, sum du zhat, sum zhat */,
-                           int n0, int n_total) {
+                           float* __restrict__ pw_partial /* [grid][2][N][128]: P1, P2 of the CTA's column chunk */,
+                           float* __restrict__ hs_partial /* [grid][128] */,
+                           float* __restrict__ col_partial /* [grid][3][N]: sum du, sum du zhat, sum zhat */,
+                           int nch, int n_total) {
   using namespace tc;
   using L = SdwSmem<NA>;
   constexpr int S = L::kStages;
@@ -367,6 +367,11 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L::kMisc + 192);
   float* s_coef = reinterpret_cast<float*>(smem + L::kMisc + 256);  // [4][N]: A, B, mean, invstd
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // n_total = N * nch gate columns: column chunks of N are spread over the CTAs of ONE launch (chunk = blockIdx.x %
+  // nch, fixed per CTA); the CTAs of a chunk share its 64-row units.  h is re-read once per chunk -- from L2, the
+  // chunk-mates work on the same units at the same time.
+  const int chunk = (int)blockIdx.x % nch, cslot = (int)blockIdx.x / nch, cgrid = (int)gridDim.x / nch;
+  const int n0 = chunk * N;
   const uint32_t bar0 = smem_u32(s_bar);
   auto bar_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
   auto bar_aready = [&](int b) { return bar0 + 64u + 8u * (uint32_t)b; };
@@ -376,7 +381,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       mbar_init(bar_full(s), 1);
       mbar_init(bar_umma(s), 1);
     }
-    for (int i = 0; i < 2; ++i) mbar_init(bar_aready(i), 256);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_aready(i), 512);
     fence_mbar_init();
   }
   if (warp == 17) tmem_alloc(smem_u32(s_tmem), kTmemCols);
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   const uint32_t tmem_d = tmem_base + kACols;
 
   const int64_t nhalves = (M + L::kHalfRows - 1) / L::kHalfRows;  // units of 64 pixel rows
-  const int64_t nunits = blockIdx.x < nhalves ? (nhalves - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t nunits = cslot < nhalves ? (nhalves - cslot + cgrid - 1) / cgrid : 0;
 
   // per-thread sums (converter threads only): hidden channel k over its 32-row half; 4 gate columns per atom
   float hsum_acc = 0.f;
@@ -409,18 +414,68 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   for (int a = 0; a < NA; ++a)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc_du[a][e] = acc_dz[a][e] = acc_z[a][e] = 0.f;
-  // this thread's 16-byte chunk inside an atom: physical chunk (tid % 8) of row (tid / 8) [+ 32]; the ATOM_32B swizzle
-  // XORs the 32-byte index with (row % 4), which is the same for both rows -> a fixed logical column group
-  const int cj = (int)(threadIdx.x & 7), crow = (int)((threadIdx.x >> 3) & 31);
+  // A thread's 16-byte chunk inside an atom: physical chunk (t % 8) of row (t / 8) [+ 32], t = tid % 256; the ATOM_32B
+  // swizzle XORs the 32-byte index with (row % 4), which is the same for both rows -> a fixed logical column group
+  const int t256 = (int)(threadIdx.x & 255);
+  const int cj = t256 & 7, crow = t256 >> 3;
   const int cl = ((((cj >> 1) ^ (crow & 3)) << 1) | (cj & 1));  // logical 16-byte chunk: columns 4*cl .. 4*cl+3 of the atom
+  // The elementwise pass over (dy, z, s) is split between the two groups of 8 warps: group B (warps 8-15, which have
+  // no other per-unit work) takes chunks [0, kChunksB), group A (warps 0-7, after the h transposition) the rest.
+  constexpr int kChunks = NA * 2, kChunksB = NA == 1 ? 2 : 3;
+
+  // (ii) dy, z, s -> ds (global) and the B operand [du_hi | zhat_hi | du_lo | zhat_lo], in place
+  auto elementwise = [&](uint8_t* dsm, int64_t row0, int i_begin, int i_end) {
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) {
+      if (i < i_begin || i >= i_end) continue;
+      const int atom = i >> 1;
+      const int row = crow + 32 * (i & 1);
+      const uint32_t o = (uint32_t)(t256 + 256 * (i & 1)) * 16u;
+      const float4 gy = *reinterpret_cast<const float4*>(dsm + (0 * NA + atom) * L::kSlotD + o);
+      const float4 zv = *reinterpret_cast<const float4*>(dsm + (1 * NA + atom) * L::kSlotD + o);
+      const float4 sv = *reinterpret_cast<const float4*>(dsm + (2 * NA + atom) * L::kSlotD + o);
+      const int col = atom * 32 + cl * 4;
+      const float4 A = *reinterpret_cast<const float4*>(s_coef + col);
+      const float4 B = *reinterpret_cast<const float4*>(s_coef + N + col);
+      const float4 mu = *reinterpret_cast<const float4*>(s_coef + 2 * N + col);
+      const float4 rs = *reinterpret_cast<const float4*>(s_coef + 3 * N + col);
+      const bool valid = row0 + row < M;  // rows past M arrive as zeros: du = ds = 0 there, zhat must be forced
+      const float gyv[4] = {gy.x, gy.y, gy.z, gy.w}, zvv[4] = {zv.x, zv.y, zv.z, zv.w}, svv[4] = {sv.x, sv.y, sv.z, sv.w};
+      const float Av[4] = {A.x, A.y, A.z, A.w}, Bv[4] = {B.x, B.y, B.z, B.w};
+      const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, rsv[4] = {rs.x, rs.y, rs.z, rs.w};
+      float dsv[4], du[4], zh[4], duh[4], zhh[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float act = sigmoidf_fast(fmaf(Av[e], zvv[e], Bv[e]));
+        dsv[e] = gyv[e] * act;
+        du[e] = gyv[e] * svv[e] * act * (1.f - act);
+        zh[e] = valid ? (zvv[e] - muv[e]) * rsv[e] : 0.f;
+        acc_du[atom][e] += du[e];
+        acc_dz[atom][e] = fmaf(du[e], zh[e], acc_dz[atom][e]);
+        acc_z[atom][e] += zh[e];
+        duh[e] = tf32_hi(du[e]);
+        zhh[e] = tf32_hi(zh[e]);
+      }
+      if (ds != nullptr && valid)
+        stg_stream(reinterpret_cast<float4*>(ds + (row0 + row) * n_total + n0 + col), make_float4(dsv[0], dsv[1], dsv[2], dsv[3]));
+      *reinterpret_cast<float4*>(dsm + (0 * NA + atom) * L::kSlotD + o) = make_float4(duh[0], duh[1], duh[2], duh[3]);
+      *reinterpret_cast<float4*>(dsm + (1 * NA + atom) * L::kSlotD + o) = make_float4(zhh[0], zhh[1], zhh[2], zhh[3]);
+      if (SPLIT) {
+        *reinterpret_cast<float4*>(dsm + (2 * NA + atom) * L::kSlotD + o) =
+            make_float4(du[0] - duh[0], du[1] - duh[1], du[2] - duh[2], du[3] - duh[3]);
+        *reinterpret_cast<float4*>(dsm + (3 * NA + atom) * L::kSlotD + o) =
+            make_float4(zh[0] - zhh[0], zh[1] - zhh[1], zh[2] - zhh[2], zh[3] - zhh[3]);
+      }
+    }
+  };
 
   if (warp < 8) {
-    // ------------------------------------------------------------------ converters
+    // ------------------------------------------------------------------ converters A: h^T -> TMEM, then their chunks
     const int quad = warp & 3, rh = warp >> 2;  // lane quadrant (k / 32), 32-row half of the unit
     const int k = quad * 32 + lane;
     for (int64_t u = 0; u < nunits; ++u) {
       const int s = (int)(u % S), hb = (int)(u & 1);
-      const int64_t row0 = (blockIdx.x + u * gridDim.x) * L::kHalfRows;
+      const int64_t row0 = (cslot + u * cgrid) * L::kHalfRows;
       mbar_wait(bar_full(s), (uint32_t)((u / S) & 1));
       uint8_t* stage = smem + s * L::kStage;
       {  // (i) h^T -> TMEM (thread = hidden channel k)
@@ -450,52 +505,20 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
           if (SPLIT) tmem_st16(ta + 64 + g * 16, lo);
         }
       }
-      // (ii) dy, z, s -> ds (global) and the B operand [du_hi | zhat_hi | du_lo | zhat_lo], in place
-      uint8_t* dsm = stage + L::kStageH;
-#pragma unroll
-      for (int i = 0; i < NA * 2; ++i) {
-        const int atom = i >> 1;
-        const int row = crow + 32 * (i & 1);
-        const uint32_t o = (uint32_t)(threadIdx.x + 256 * (i & 1)) * 16u;
-        const float4 gy = *reinterpret_cast<const float4*>(dsm + (0 * NA + atom) * L::kSlotD + o);
-        const float4 zv = *reinterpret_cast<const float4*>(dsm + (1 * NA + atom) * L::kSlotD + o);
-        const float4 sv = *reinterpret_cast<const float4*>(dsm + (2 * NA + atom) * L::kSlotD + o);
-        const int col = atom * 32 + cl * 4;
-        const float4 A = *reinterpret_cast<const float4*>(s_coef + col);
-        const float4 B = *reinterpret_cast<const float4*>(s_coef + N + col);
-        const float4 mu = *reinterpret_cast<const float4*>(s_coef + 2 * N + col);
-        const float4 rs = *reinterpret_cast<const float4*>(s_coef + 3 * N + col);
-        const bool valid = row0 + row < M;  // rows past M arrive as zeros: du = ds = 0 there, zhat must be forced
-        const float gyv[4] = {gy.x, gy.y, gy.z, gy.w}, zvv[4] = {zv.x, zv.y, zv.z, zv.w}, svv[4] = {sv.x, sv.y, sv.z, sv.w};
-        const float Av[4] = {A.x, A.y, A.z, A.w}, Bv[4] = {B.x, B.y, B.z, B.w};
-        const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, rsv[4] = {rs.x, rs.y, rs.z, rs.w};
-        float dsv[4], du[4], zh[4], duh[4], zhh[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float act = sigmoidf_acc(fmaf(Av[e], zvv[e], Bv[e]));
-          dsv[e] = gyv[e] * act;
-          du[e] = gyv[e] * svv[e] * act * (1.f - act);
-          zh[e] = valid ? (zvv[e] - muv[e]) * rsv[e] : 0.f;
-          acc_du[atom][e] += du[e];
-          acc_dz[atom][e] = fmaf(du[e], zh[e], acc_dz[atom][e]);
-          acc_z[atom][e] += zh[e];
-          duh[e] = tf32_hi(du[e]);
-          zhh[e] = tf32_hi(zh[e]);
-        }
-        if (ds != nullptr && valid)
-          stg_stream(reinterpret_cast<float4*>(ds + (row0 + row) * n_total + n0 + col), make_float4(dsv[0], dsv[1], dsv[2], dsv[3]));
-        *reinterpret_cast<float4*>(dsm + (0 * NA + atom) * L::kSlotD + o) = make_float4(duh[0], duh[1], duh[2], duh[3]);
-        *reinterpret_cast<float4*>(dsm + (1 * NA + atom) * L::kSlotD + o) = make_float4(zhh[0], zhh[1], zhh[2], zhh[3]);
-        if (SPLIT) {
-          *reinterpret_cast<float4*>(dsm + (2 * NA + atom) * L::kSlotD + o) =
-              make_float4(du[0] - duh[0], du[1] - duh[1], du[2] - duh[2], du[3] - duh[3]);
-          *reinterpret_cast<float4*>(dsm + (3 * NA + atom) * L::kSlotD + o) =
-              make_float4(zh[0] - zhh[0], zh[1] - zhh[1], zh[2] - zhh[2], zh[3] - zhh[3]);
-        }
-      }
+      elementwise(stage + L::kStageH, row0, kChunksB, kChunks);
       fence_proxy_async_smem();
       tmem_wait_st();
       tc_fence_before_sync();
+      mbar_arrive(bar_aready(hb));
+    }
+  } else if (warp < 16) {
+    // ------------------------------------------------------------------ converters B: elementwise only
+    for (int64_t u = 0; u < nunits; ++u) {
+      const int s = (int)(u % S), hb = (int)(u & 1);
+      const int64_t row0 = (cslot + u * cgrid) * L::kHalfRows;
+      mbar_wait(bar_full(s), (uint32_t)((u / S) & 1));
+      elementwise(smem + s * L::kStage + L::kStageH, row0, 0, kChunksB);
+      fence_proxy_async_smem();
       mbar_arrive(bar_aready(hb));
     }
   } else if (warp == 16) {
@@ -506,7 +529,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         // stage reusable once the MMAs of its previous unit are done (they were issued after every converter
         // had finished reading and rewriting the stage)
         if (u >= S) mbar_wait(bar_umma(s), (uint32_t)(((u / S) - 1) & 1));
-        const int row0 = (int)((blockIdx.x + u * gridDim.x) * L::kHalfRows);
+        const int row0 = (int)((cslot + u * cgrid) * L::kHalfRows);
         mbar_expect_tx(bar_full(s), (uint32_t)(L::kStageH + 3 * NA * L::kSlotD));
         const uint32_t dst = smem_u32(smem + s * L::kStage);
 #pragma unroll
@@ -539,11 +562,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       mma_commit(bar_umma(s));
     }
   }
-  // warps 8-15 have no per-unit work in this kernel: they only help drain the accumulator
   tc_fence_before_sync();
   __syncthreads();
-  float* out = pw_partial + ((int64_t)blockIdx.x * 2 * n_total + n0) * KH;
-  const int64_t q_stride = (int64_t)n_total * KH;  // P1 -> P2
+  float* out = pw_partial + (int64_t)blockIdx.x * 2 * N * KH;
+  const int64_t q_stride = (int64_t)N * KH;  // P1 -> P2
   if (nunits > 0) {
     if (warp == 17 && lane == 0) {  // wait for the last unit's MMAs
       const int64_t ul = nunits - 1;
@@ -579,9 +601,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   __syncthreads();
   if (warp == 17) tmem_dealloc(tmem_base, kTmemCols);
   // ---- per-CTA column sums and hsum: fixed-order block reductions through shared memory (stage 0 is idle) ----
-  float* s_red = reinterpret_cast<float*>(smem);  // [256][NA][12] then [256] hsum
-  float* s_hs = s_red + 256 * NA * 12;
-  if (warp < 8) {
+  float* s_red = reinterpret_cast<float*>(smem);  // [512][NA][12] then [256] hsum
+  float* s_hs = s_red + 512 * NA * 12;
+  if (warp < 16) {
 #pragma unroll
     for (int a = 0; a < NA; ++a)
 #pragma unroll
@@ -590,34 +612,33 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         s_red[(threadIdx.x * NA + a) * 12 + 4 + e] = acc_dz[a][e];
         s_red[(threadIdx.x * NA + a) * 12 + 8 + e] = acc_z[a][e];
       }
-    s_hs[threadIdx.x] = hsum_acc;
+    if (warp < 8) s_hs[threadIdx.x] = hsum_acc;
   }
   __syncthreads();
   for (int o = threadIdx.x; o < 3 * N; o += kTmaThreads) {
     const int q = o / N, col = o % N;
     const int atom = col >> 5, c = (col & 31) >> 2, e = col & 3;
     float acc = 0.f;
-    for (int t = 0; t < 256; ++t) {  // the 32 converter threads whose chunk holds this column, in thread order
+    for (int t = 0; t < 512; ++t) {  // the 64 converter threads (both groups) whose chunk holds this column, in thread order
       const int tj = t & 7, tr = (t >> 3) & 31;
       if (((((tj >> 1) ^ (tr & 3)) << 1) | (tj & 1)) == c) acc += s_red[(t * NA + atom) * 12 + q * 4 + e];
     }
-    col_partial[((int64_t)blockIdx.x * 3 + q) * n_total + n0 + col] = acc;
+    col_partial[((int64_t)blockIdx.x * 3 + q) * N + col] = acc;
   }
-  if (n0 == 0)
-    for (int k = threadIdx.x; k < KH; k += kTmaThreads) {
-      // converter thread (quad, rh) held channel k = quad*32 + lane: tid = (rh*4 + quad)*32 + lane
-      hs_partial[(int64_t)blockIdx.x * KH + k] = s_hs[k] + s_hs[128 + k];
-    }
+  for (int k = threadIdx.x; k < KH; k += kTmaThreads) {
+    // converter thread (quad, rh) held channel k = quad*32 + lane: tid = (rh*4 + quad)*32 + lane
+    hs_partial[(int64_t)blockIdx.x * KH + k] = s_hs[k] + s_hs[128 + k];
+  }
 }
 
 // ------------------------------------------------------------------------------------------- host side
 // N = 32 or any multiple of 64.
-// pass 1: N = 32 -> one launch (NA = 1); otherwise one launch per 64 columns (NA = 2: 256 accumulator columns in TMEM),
-//         each re-reading h.  All launches share the grid, so every partial buffer is indexed by blockIdx.
+// pass 1: ONE launch.  N = 32: NA = 1; otherwise 64-column chunks (NA = 2: 256 accumulator columns in TMEM) spread
+//         over the CTAs of the launch, grid a multiple of the chunk count.
 template <bool SPLIT>
 static int launch_sdw_tma(const float* dy, const float* h, const float* s, const float* z, const float* gamma,
                           const float* beta, const float* mean, const float* invstd, int64_t M, int N, float* ds,
-                          float* pw_partial, float* hs_partial, float* col_partial, int grid, cudaStream_t st) {
+                          float* pw_partial, float* hs_partial, float* col_partial, int grid, int nch, cudaStream_t st) {
   CUtensorMap t_h, t_dy, t_z, t_s;
   if (!make_tmap_2d_sw(&t_h, h, M, 128, 64, false) || !make_tmap_2d_sw(&t_dy, dy, M, N, 64, true) ||
       !make_tmap_2d_sw(&t_z, z, M, N, 64, true) || !make_tmap_2d_sw(&t_s, s, M, N, 64, true))
@@ -627,19 +648,15 @@ static int launch_sdw_tma(const float* dy, const float* h, const float* s, const
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SdwSmem<1>::kBytes) != cudaSuccess)
       return VMTL_ECUDA;
     k<<<grid, kTmaThreads, SdwSmem<1>::kBytes, st>>>(t_h, t_dy, t_z, t_s, gamma, beta, mean, invstd, M, ds, pw_partial,
-                                                     hs_partial, col_partial, 0, N);
+                                                     hs_partial, col_partial, 1, N);
     return launch_status();
   }
   auto k = gate_tc_sdw_tma_kernel<2, SPLIT>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SdwSmem<2>::kBytes) != cudaSuccess)
     return VMTL_ECUDA;
-  for (int n0 = 0; n0 < N; n0 += 64) {
-    k<<<grid, kTmaThreads, SdwSmem<2>::kBytes, st>>>(t_h, t_dy, t_z, t_s, gamma, beta, mean, invstd, M, ds, pw_partial,
-                                                     hs_partial, col_partial, n0, N);
-    const int rc = launch_status();
-    if (rc != VMTL_OK) return rc;
-  }
-  return VMTL_OK;
+  k<<<grid, kTmaThreads, SdwSmem<2>::kBytes, st>>>(t_h, t_dy, t_z, t_s, gamma, beta, mean, invstd, M, ds, pw_partial,
+                                                   hs_partial, col_partial, nch, N);
+  return launch_status();
 }
 
 // pass 2: one launch covers up to 256 gate columns (NCH chunks of 64 whose dh contributions accumulate in TMEM, W^T

@@ -167,6 +167,14 @@ __device__ __forceinline__ float fast_lg2(float x) {
   return r;
 }
 
+// MUFU sigmoid: ex2.approx + rcp.approx, ~3e-7 relative error on the value (the gate BACKWARD kernels: both passes
+// use it, so du of the statistics pass and dz of the dh pass see the same activation)
+__device__ __forceinline__ float sigmoidf_fast(float u) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + fast_ex2(-u * kLog2e)));
+  return r;
+}
+
 __device__ __forceinline__ float sigmoidf_acc(float u) {
   // 1/(1+exp(-u)) with the accurate expf: the parity bar is 1e-4 relative on gradients.
   return 1.0f / (1.0f + expf(-u));

@@ -214,7 +214,8 @@ def cross_stitch(xs: Sequence[torch.Tensor], alpha: torch.Tensor, mode: str = "r
 # MTAN attention gate
 # --------------------------------------------------------------------------------------
 def _gate_bwd_passes(M: int, N: int):
-    """(pass-1 launches, dh launches) of the tensor-core backward (csrc/gate_tc_bwd_tma.cuh)."""
+    """(reads of h in pass 1, dh launches) of the tensor-core backward (csrc/gate_tc_bwd_tma.cuh): pass 1 is one
+    launch whose CTAs split wide gates into 64-column chunks, each chunk reading h once (from L2 after the first)."""
     if N <= 64:
         return 1, 1
     one_tile = (M + 127) // 128 <= _lib.load().vmtl_sm_count()
@@ -292,10 +293,8 @@ class GateFunction(torch.autograd.Function):
               _p(dh), _p(ds), _p(dW), _p(dbias), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream(),
               issued=issued)
         if ctx.precision != 0 and N > 64 and K == 128 and N % 64 == 0:
-            # wider gates run extra column launches: pass 1 per 64 columns; dh per 64 columns, or per 256
-            # when every CTA owns a single 128-row tile
-            n_p1, n_dh = _gate_bwd_passes(M, N)
-            _Prof.launches += (n_p1 - 1) + (n_dh - 1)
+            # wider gates run extra dh launches: per 64 columns, or per 256 when every CTA owns a single 128-row tile
+            _Prof.launches += _gate_bwd_passes(M, N)[1] - 1
         return (dh, ds, dW.reshape(ctx.wshape), dbias, dgamma, dbeta, None, None, None, None, None, None)
 
 
