@@ -195,36 +195,6 @@ def gen_mtan_full(ref, out):
         print(f"{name}: loss {losses[0].item():.6f} (fp64 {losses64[0].item():.6f}), near-tie pixels {int(tie.sum())}")
 
 
-def _act_margin(net, img):
-    """Smallest distance of any activation input of the task networks from a kink of its activation
-    (ReLU: 0; Hardswish: -3 and +3)."""
-    margins = []
-
-    def relu_hook(_m, inp, _out):
-        margins.append(float(inp[0].detach().abs().min()))
-
-    def hsw_hook(_m, inp, _out):
-        x = inp[0].detach()
-        margins.append(float(torch.minimum((x + 3).abs(), (x - 3).abs()).min()))
-
-    hooks = []
-    for m in net.modules():
-        if isinstance(m, nn.ReLU):
-            m.inplace = False
-            hooks.append(m.register_forward_hook(relu_hook))
-        elif isinstance(m, nn.Hardswish):
-            m.inplace = False
-            hooks.append(m.register_forward_hook(hsw_hook))
-    with torch.no_grad():
-        net(img)
-    for h in hooks:
-        h.remove()
-    return min(margins)
-
-
-CSNET_SMALL = ("csnet_small", 2, 64, 64, 19)  # flip-free fixture (searched over the salt): gradients at 1e-4
-
-
 def gen_csnet(ref, out):
     """Reference CSNet class over the stand-in backbone (smp/timm are not installable)."""
     from vision_mtl_b200.utils.model_utils import get_model_with_dense_preds
@@ -277,9 +247,10 @@ def _csnet_step(ref, net, batch, dtype):
 
 
 def _gen_csnet_extra(ref, out):
-    """(a) fp64 runs of the two 64x64 cases: the yardstick for gradient comparisons at sizes where ReLU /
-    Hardswish near-flips are unavoidable; (b) a small flip-free case whose gradients are reproducible to
-    fp32 round-off between two correct implementations."""
+    """fp64 runs of the two 64x64 cases: the yardstick for gradient comparisons at sizes where ReLU /
+    Hardswish near-flips are unavoidable.  (A fixture searched to be flip-free IN THE REFERENCE'S RUN was tried
+    and dropped: through ~190 layers the product's activations drift by more than any margin the search can
+    find, and selecting on the reference's run biases the comparison in its favour.)"""
     for name, cw in (("csnet_cw", True), ("csnet_lw", False)):
         torch.manual_seed(0)
         net = ref["CSNet"](_csnet_models(19), channel_wise_stitching=cw)
@@ -289,41 +260,6 @@ def _gen_csnet_extra(ref, out):
         for k, p_ in net.named_parameters():
             if p_.grad is not None:
                 out[f"{name}/grad64/{k}"] = FX.summarize(p_.grad)
-    name, B, H, W, C = CSNET_SMALL
-    for salt in range(5000):
-        torch.manual_seed(0)
-        net = ref["CSNet"](_csnet_models(C), channel_wise_stitching=True)
-        net.load_state_dict(FX.fill_state_dict(net.state_dict(), salt=salt))
-        batch = FX.image_batch(B, H, W, C, f"{name}/{salt}")
-        margin = _act_margin(net.train(), batch["img"])
-        if margin > FLIP_MARGIN:
-            break
-    else:
-        raise RuntimeError("no flip-free csnet fixture found")
-    print(f"{name}: salt {salt}, activation margin {margin:.2e}")
-    # the margin pass ran a training-mode forward: rebuild so the running statistics start from the fixture
-    torch.manual_seed(0)
-    net = ref["CSNet"](_csnet_models(C), channel_wise_stitching=True)
-    net.load_state_dict(FX.fill_state_dict(net.state_dict(), salt=salt))
-    raw, losses = _csnet_step(ref, net, batch, torch.float32)
-    out[f"{name}/salt"] = np.array([salt], dtype=np.int64)
-    out[f"{name}/margin"] = np.array([margin])
-    out[f"{name}/segm_logits"] = _np(raw["segm"]).astype(np.float32)
-    out[f"{name}/depth_logits"] = _np(raw["depth"]).astype(np.float32)
-    out[f"{name}/losses"] = np.array([v.item() for v in losses])
-    for k, p_ in net.named_parameters():
-        if p_.grad is not None:
-            out[f"{name}/grad/{k}"] = FX.summarize(p_.grad)
-    for k, b_ in net.named_buffers():
-        out[f"{name}/buf/{k}"] = FX.summarize(b_.float())
-    # fp64 run of the same fixture: tells analytically-zero gradients (noise in fp32) from real ones
-    torch.manual_seed(0)
-    net = ref["CSNet"](_csnet_models(C), channel_wise_stitching=True)
-    net.load_state_dict(FX.fill_state_dict(net.state_dict(), salt=salt))
-    _csnet_step(ref, net, batch, torch.float64)
-    for k, p_ in net.named_parameters():
-        if p_.grad is not None:
-            out[f"{name}/grad64/{k}"] = FX.summarize(p_.grad)
 
 
 def gen_epoch_summary(ref, out):
