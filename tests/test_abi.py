@@ -33,7 +33,10 @@ def test_library_exports_every_declared_symbol():
     assert typed.vmtl_strerror(0).decode() == "ok"
     # sizing helpers are host-only and must work without a GPU
     assert typed.vmtl_xstitch_bwd_workspace_bytes(2, 1 << 20, 32, 1) > 0
-    assert typed.vmtl_gate_workspace_bytes(1 << 20, 128, 32, 1, 1) > 4 * (1 << 20) * 32
+    # the tensor-core backward never materialises dz: its workspace holds per-CTA partials only; the CUDA-core
+    # backward (precision 0) stages dz [M,N]
+    assert 0 < typed.vmtl_gate_workspace_bytes(1 << 20, 128, 32, 1, 1) < 4 * (1 << 20) * 32
+    assert typed.vmtl_gate_workspace_bytes(1 << 20, 128, 32, 0, 1) > 4 * (1 << 20) * 32
     assert typed.vmtl_gate_workspace_bytes(1 << 20, 100, 32, 1, 1) > 0   # any K: CUDA-core contraction
     assert typed.vmtl_gate_workspace_bytes(1 << 20, 128, 30, 1, 1) == 0  # N must be a multiple of 4
     assert typed.vmtl_loss_workspace_bytes(1 << 20) > 0
