@@ -111,6 +111,42 @@ int vmtl_gate_bwd(const float* dy, const float* h, const float* s, const float* 
                   float* dbeta, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * BatchNorm2d (+ ReLU, + 2x2 max-pool) on NHWC maps, batch or running statistics.
+ * Replaces the batch_norm / relu / max_pool2d ATen kernels behind every conv -> BN -> ReLU chain of the
+ * MTAN network: DoubleConv (vision_mtl/utils/model_utils.py:61-80), the attention modules' conv1/bn1/relu
+ * (mtan_model.py:65-69, :152-156), conv3/bn3/relu(/maxpool) (mtan_model.py:77-81, :141-142) and
+ * conv_out/bn_out/relu (mtan_model.py:165-167).
+ *   x [M,C] (C % 4 == 0, C <= 1024), gamma/beta/running_* [C]
+ *   training != 0: batch statistics (running_* updated with `momentum`, may be NULL); else running statistics
+ *   relu != 0: y = max(bn(x), 0)
+ *   y == NULL: statistics only -- save_mean / save_invstd / coef are produced, nothing is applied (the gate
+ *              kernels consume x and fold max(A x + B, 0) into their operand conversion: vmtl_gate_*_pre)
+ *   coef [2][C]: A = gamma*invstd, B = beta - mean*A, the fp32 coefficients every consumer folds
+ * pool variants: x [B,H,W,C] -> y [B,H/2,W/2,C], nn.MaxPool2d(2) after the ReLU.
+ * Backward: dx [M,C] (NULL to skip), dgamma, dbeta [C]; dy has the shape of y.
+ * ---------------------------------------------------------------------------------- */
+size_t vmtl_bnrelu_workspace_bytes(int64_t M, int C);
+
+int vmtl_bnrelu_fwd(const float* x, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float momentum, float eps, int training, int relu, int64_t M, int C,
+                    float* y, float* save_mean, float* save_invstd, float* coef, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+int vmtl_bnrelu_bwd(const float* dy, const float* x, const float* coef, const float* save_mean,
+                    const float* save_invstd, int training, int relu, int64_t M, int C, float* dx,
+                    float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream);
+
+int vmtl_bnrelu_pool_fwd(const float* x, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, float momentum, float eps, int training, int relu, int B, int H,
+                         int W, int C, float* y, float* save_mean, float* save_invstd, float* coef,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+int vmtl_bnrelu_pool_bwd(const float* dy, const float* x, const float* coef, const float* save_mean,
+                         const float* save_invstd, int training, int relu, int B, int H, int W, int C,
+                         float* dx, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Segmentation head fused with cross-entropy, argmax and the confusion matrix.
  * Replaces nn.Conv2d(32,C,1) (mtan_model.py:367-376,401-404), F.softmax + argmax
  * (lit_module.py:137-138), nn.CrossEntropyLoss (lit_module.py:31,123) and the

@@ -108,3 +108,19 @@ def depth_abs_rel(pred: torch.Tensor, target: torch.Tensor, min_depth: float = 1
     north_star ("depth abs/rel error sums")."""
     m = target > min_depth
     return ((pred[m] - target[m]).abs() / target[m]).sum() / m.sum()
+
+
+# --------------------------------------------------------------------------
+# conv -> BatchNorm2d -> ReLU (-> MaxPool2d(2)) tails
+# (vision_mtl/utils/model_utils.py:61-80; vision_mtl/models/mtan_model.py:65-69, :77-81, :141-142, :165-167)
+# --------------------------------------------------------------------------
+def bn_relu(x, gamma, beta, running_mean, running_var, training: bool, relu: bool = True, pool: bool = False,
+            momentum: float = 0.1, eps: float = 1e-5) -> torch.Tensor:
+    """``nn.BatchNorm2d`` then (optionally) ``nn.ReLU`` then (optionally) ``nn.MaxPool2d(2)``, as the
+    reference sequences the ATen ops."""
+    y = F.batch_norm(x, running_mean, running_var, gamma, beta, training, momentum, eps)
+    if relu:
+        y = F.relu(y)
+    if pool:
+        y = F.max_pool2d(y, 2)
+    return y

@@ -325,3 +325,49 @@ def test_gate_fwd_bwd(B, N, H, W, training, precision):
         with torch.no_grad():  # inference: the tensor-core path fuses the whole gate into one pass
             y2 = ops.attention_gate(hd, sd, p[0], p[1], p[2], p[3], rmd, rvd, False, 0.1, 1e-5, precision)
         assert_rel(y2, yr, what="y (no_grad eval)")
+
+
+# ----------------------------------------------------------------------------- BatchNorm (+ReLU, +max-pool)
+BN_SHAPES = [(2, 32, 16, 24), (1, 64, 9, 13), (3, 128, 20, 24), (2, 256, 12, 10), (1, 512, 4, 8), (2, 4, 8, 8),
+             (4, 32, 64, 64), (2, 128, 128, 256)]
+
+
+@pytest.mark.parametrize("B,C,H,W", BN_SHAPES)
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("relu,pool", [(True, False), (False, False), (True, True)])
+def test_bn_relu_pool_fwd_bwd(B, C, H, W, training, relu, pool):
+    from vision_mtl_b200 import ops
+
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, C, H, W, generator=g) * 1.5 + 0.3
+    bn = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5, generator=g)
+        bn.bias.uniform_(-0.5, 0.5, generator=g)
+        bn.running_mean.uniform_(-0.2, 0.6, generator=g)
+        bn.running_var.uniform_(1.5, 3.0, generator=g)
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    dy = torch.randn(B, C, Ho, Wo, generator=g)
+    xr = x.clone().requires_grad_(True)
+    gr, br = bn.weight.detach().clone().requires_grad_(True), bn.bias.detach().clone().requires_grad_(True)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    yr = K.bn_relu(xr, gr, br, rm, rv, training, relu, pool)
+    yr.backward(dy)
+
+    bnd = torch.nn.BatchNorm2d(C).to(dev())
+    bnd.load_state_dict(bn.state_dict())
+    bnd.train(training)
+    xd = to_cl(x).requires_grad_(True)
+    assert ops.bn_supported(bnd, xd)
+    y = ops.batch_norm_relu(xd, bnd, relu=relu, pool=pool)
+    y.backward(to_cl(dy))
+    assert_rel(y, yr, what="y")
+    assert_rel(xd.grad, xr.grad, what="dx")
+    assert_rel(bnd.weight.grad, gr.grad, what="dgamma")
+    assert_rel(bnd.bias.grad, br.grad, what="dbeta")
+    if training:
+        assert_rel(bnd.running_mean, rm, what="running_mean")
+        assert_rel(bnd.running_var, rv, what="running_var")
+        assert int(bnd.num_batches_tracked) == 1
+    else:
+        assert torch.equal(bnd.running_mean.cpu(), bn.running_mean) and int(bnd.num_batches_tracked) == 0

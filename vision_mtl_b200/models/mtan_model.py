@@ -35,8 +35,16 @@ class _GatedAttention(nn.Module):
         self.bn2 = nn.BatchNorm2d(gated_channels)
         self.sigmoid = nn.Sigmoid()
 
+    @staticmethod
+    def _bn_relu(x: torch.Tensor, bn: nn.BatchNorm2d, act: nn.Module, pool: t.Optional[nn.Module] = None) -> torch.Tensor:
+        """``[pool(] act(bn(x)) [)]`` through the fused BatchNorm kernels where they apply."""
+        if ops.bn_supported(bn, x) and isinstance(act, nn.ReLU):
+            return ops.batch_norm_relu(x, bn, relu=True, pool=pool is not None)
+        y = act(bn(x))
+        return y if pool is None else pool(y)
+
     def _gate(self, merged: torch.Tensor, shared: torch.Tensor) -> torch.Tensor:
-        hidden = self.relu1(self.bn1(self.conv1(merged)))
+        hidden = self._bn_relu(self.conv1(merged), self.bn1, self.relu1)
         bn = self.bn2
         use_batch_stats = bn.training or bn.running_mean is None
         if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
@@ -80,7 +88,7 @@ class AttentionModuleEncoder(_GatedAttention):
                 raise ValueError("prev_layer_outs must be provided for a non-first AttentionModuleEncoder")
             merged = torch.cat((conv1_shared, prev_layer_outs), dim=1)
         gated = self._gate(merged, conv2_shared)
-        return self.maxpool(self.relu2(self.bn3(self.conv3(gated))))
+        return self._bn_relu(self.conv3(gated), self.bn3, self.relu2, self.maxpool)
 
 
 class AttentionModuleDecoder(_GatedAttention):
@@ -110,13 +118,13 @@ class AttentionModuleDecoder(_GatedAttention):
         self.relu_out = nn.ReLU()
 
     def forward(self, conv1_shared, prev_layer_outs, conv2_shared):
-        prev = self.relu2(self.bn3(self.conv3(prev_layer_outs)))
+        prev = self._bn_relu(self.conv3(prev_layer_outs), self.bn3, self.relu2)
         if conv1_shared.shape[2:] != prev.shape[2:]:
             prev = self.up(prev)
         if conv1_shared.shape[2:] != conv2_shared.shape[2:]:
             raise ValueError("conv1_shared and conv2_shared must share their spatial size")
         gated = self._gate(torch.cat((conv1_shared, prev), dim=1), conv2_shared)
-        return self.relu_out(self.bn_out(self.conv_out(gated)))
+        return self._bn_relu(self.conv_out(gated), self.bn_out, self.relu_out)
 
 
 class MTANDown(nn.Module):

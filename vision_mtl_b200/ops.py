@@ -51,6 +51,7 @@ _KERNELS_PER_CALL = {
     "xstitch_fwd": 1, "xstitch_bwd": 2, "gate_fwd": 3, "gate_bwd": 3, "head_ce_fwd": 2,
     "head_ce_bwd": 2, "ce_logits_fwd": 2, "ce_logits_bwd": 1, "head_silog_fwd": 2,
     "head_silog_bwd": 2, "confusion_accum": 1, "depth_err_sums": 2, "seg_metrics": 1,
+    "bnrelu_fwd": 3, "bnrelu_bwd": 3, "bnrelu_pool_fwd": 3, "bnrelu_pool_bwd": 3,
 }
 
 
@@ -208,6 +209,84 @@ class CrossStitchFunction(torch.autograd.Function):
 
 def cross_stitch(xs: Sequence[torch.Tensor], alpha: torch.Tensor, mode: str = "reference_diag"):
     return list(CrossStitchFunction.apply(alpha, _XS_MODES[mode], *xs))
+
+
+# --------------------------------------------------------------------------------------
+# BatchNorm2d (+ ReLU, + 2x2 max-pool)
+# --------------------------------------------------------------------------------------
+class BNReLUFunction(torch.autograd.Function):
+    """``[maxpool2(] relu( batch_norm(x) ) [)]`` in NHWC: statistics pass + apply pass (+ their backward)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, pool):
+        x = _nhwc(x)
+        _need_cuda(x, gamma, beta)
+        B, C, H, W = x.shape
+        M = B * H * W
+        dev = x.device
+        if pool:
+            y = torch.empty((B, C, H // 2, W // 2), dtype=torch.float32, device=dev).contiguous(
+                memory_format=torch.channels_last)
+        else:
+            y = torch.empty_like(x)
+        stats = torch.empty((4, C), dtype=torch.float32, device=dev)  # save_mean, save_invstd, A, B
+        ws = _workspace(_lib.load().vmtl_bnrelu_workspace_bytes(M, C), dev)
+        nbytes = 4 * C * ((2 * M if training else M) + y.numel() // C)
+        if pool:
+            _call("bnrelu_pool_fwd", nbytes, _p(x), _p(gamma.detach()), _p(beta.detach()), _p(running_mean),
+                  _p(running_var), float(momentum), float(eps), 1 if training else 0, 1 if relu else 0, B, H, W, C,
+                  _p(y), _p(stats[0]), _p(stats[1]), _p(stats[2:]), _p(ws), ws.numel(), _stream())
+        else:
+            _call("bnrelu_fwd", nbytes, _p(x), _p(gamma.detach()), _p(beta.detach()), _p(running_mean),
+                  _p(running_var), float(momentum), float(eps), 1 if training else 0, 1 if relu else 0, M, C,
+                  _p(y), _p(stats[0]), _p(stats[1]), _p(stats[2:]), _p(ws), ws.numel(), _stream())
+        if not training:
+            _Prof.launches -= 1  # no statistics pass on running statistics
+        ctx.cfg = (bool(training), bool(relu), bool(pool))
+        ctx.save_for_backward(x, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats = ctx.saved_tensors
+        training, relu, pool = ctx.cfg
+        dy = _nhwc(dy)
+        B, C, H, W = x.shape
+        M = B * H * W
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dgb = torch.empty((2, C), dtype=torch.float32, device=x.device)
+        ws = _workspace(_lib.load().vmtl_bnrelu_workspace_bytes(M, C), x.device)
+        nbytes = 4 * C * (2 * (M + dy.numel() // C) + (M if dx is not None else 0))
+        if pool:
+            _call("bnrelu_pool_bwd", nbytes, _p(dy), _p(x), _p(stats[2:]), _p(stats[0]), _p(stats[1]),
+                  1 if training else 0, 1 if relu else 0, B, H, W, C, _p(dx), _p(dgb[0]), _p(dgb[1]), _p(ws),
+                  ws.numel(), _stream())
+        else:
+            _call("bnrelu_bwd", nbytes, _p(dy), _p(x), _p(stats[2:]), _p(stats[0]), _p(stats[1]),
+                  1 if training else 0, 1 if relu else 0, M, C, _p(dx), _p(dgb[0]), _p(dgb[1]), _p(ws), ws.numel(),
+                  _stream())
+        return dx, dgb[0], dgb[1], None, None, None, None, None, None, None
+
+
+def bn_supported(bn: torch.nn.Module, x: torch.Tensor) -> bool:
+    """Shapes / configurations the fused BatchNorm kernels cover (anything else stays on ATen)."""
+    return (isinstance(bn, torch.nn.BatchNorm2d) and bn.affine and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+            and x.shape[1] % 4 == 0 and 4 <= x.shape[1] <= 1024 and (bn.training or bn.running_mean is not None))
+
+
+def batch_norm_relu(x: torch.Tensor, bn: torch.nn.BatchNorm2d, relu: bool = True, pool: bool = False) -> torch.Tensor:
+    """``maxpool2(relu(bn(x)))`` (each optional) with ``bn``'s parameters, mode and running statistics
+    (updated in place like ``nn.BatchNorm2d.forward``)."""
+    use_batch_stats = bn.training or bn.running_mean is None
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    if bn.momentum is None:  # cumulative moving average
+        momentum = 1.0 / float(bn.num_batches_tracked) if bn.training and bn.track_running_stats else 0.0
+    else:
+        momentum = bn.momentum
+    return BNReLUFunction.apply(x, bn.weight, bn.bias, bn.running_mean if bn.track_running_stats else None,
+                                bn.running_var if bn.track_running_stats else None, use_batch_stats, momentum,
+                                bn.eps, relu, pool)
 
 
 # --------------------------------------------------------------------------------------

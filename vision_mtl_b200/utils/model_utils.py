@@ -14,6 +14,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .. import ops
 from .standin_backbone import StandinUnet
 
 try:  # pragma: no cover - not installable offline
@@ -106,7 +107,13 @@ class DoubleConv(nn.Module):
         self.double_conv = nn.Sequential(*stages)
 
     def forward(self, x):
-        return self.double_conv(x)
+        dc = self.double_conv
+        for conv, bn, act in ((dc[0], dc[1], dc[2]), (dc[3], dc[4], dc[5])):
+            x = conv(x)
+            # BN (batch or running statistics) + ReLU as one statistics pass + one apply pass of the library;
+            # shapes / devices the kernels do not cover keep the ATen modules
+            x = ops.batch_norm_relu(x, bn) if ops.bn_supported(bn, x) else act(bn(x))
+        return x
 
 
 def _is_stitch_level(parts: t.List[str]) -> bool:
