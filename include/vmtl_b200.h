@@ -90,11 +90,20 @@ int vmtl_xstitch_bwd(const float* const* dy_host, const float* const* x_host,
  *   (mean, invstd) to save_mean/save_invstd for the backward.  running_* may be NULL.
  * training == 0: running statistics, save_* may be NULL (save_z == NULL: single fused pass on the
  *   tensor-core path, z is never stored).
+ * h_coef (forward and backward): NULL, or [A1 | B1] ([2][K]) -- then `h` holds the PRE-activation c of the
+ *   hidden layer (conv1's output, mtan_model.py:65-69 / :152-156) and the kernels rebuild
+ *   h = max(A1 c + B1, 0), the folded bn1 + ReLU (coef of vmtl_bnrelu_fwd with y == NULL), while they convert
+ *   their operand: the [M,K] hidden tensor is never written to or read from HBM.  Tensor-core shapes only
+ *   (vmtl_gate_tc_supported); the backward's dh is then the gradient w.r.t. h (feed it, with c, to
+ *   vmtl_bnrelu_bwd).
  * ---------------------------------------------------------------------------------- */
+/* 1 when the tcgen05 kernels cover (K, N) */
+int vmtl_gate_tc_supported(int K, int N);
+
 /* backward != 0: size for vmtl_gate_bwd, else for vmtl_gate_fwd */
 size_t vmtl_gate_workspace_bytes(int64_t M, int K, int N, int precision, int backward);
 
-int vmtl_gate_fwd(const float* h, const float* s, const float* W, const float* bias,
+int vmtl_gate_fwd(const float* h, const float* h_coef, const float* s, const float* W, const float* bias,
                   const float* gamma, const float* beta, float* running_mean,
                   float* running_var, float momentum, float eps, int training, int precision,
                   int64_t M, int K, int N, float* y, float* save_z, float* save_mean,
@@ -104,7 +113,7 @@ int vmtl_gate_fwd(const float* h, const float* s, const float* W, const float* b
  * Inputs: dy, h, s, saved z/mean/invstd.  Outputs: dh [M,K], ds [M,N], dW [N,K],
  * dbias/dgamma/dbeta [N].  dh or ds may be NULL to skip them.  training == 0 uses
  * running statistics passed in save_mean/save_invstd (dz = gamma*invstd*du). */
-int vmtl_gate_bwd(const float* dy, const float* h, const float* s, const float* z,
+int vmtl_gate_bwd(const float* dy, const float* h, const float* h_coef, const float* s, const float* z,
                   const float* W, const float* gamma, const float* beta, const float* save_mean,
                   const float* save_invstd, int training, int precision, int64_t M, int K,
                   int N, float* dh, float* ds, float* dW, float* dbias, float* dgamma,

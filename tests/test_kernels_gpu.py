@@ -371,3 +371,51 @@ def test_bn_relu_pool_fwd_bwd(B, C, H, W, training, relu, pool):
         assert int(bnd.num_batches_tracked) == 1
     else:
         assert torch.equal(bnd.running_mean.cpu(), bn.running_mean) and int(bnd.num_batches_tracked) == 0
+
+
+# ----------------------------------------------------------------------------- gate with the folded hidden layer
+@pytest.mark.parametrize("B,N,H,W", [(2, 32, 16, 24), (1, 64, 9, 13), (2, 128, 8, 8), (1, 256, 4, 8), (2, 32, 128, 256),
+                                     (1, 128, 160, 256)])
+@pytest.mark.parametrize("training", [True, False])
+def test_gate_folded_hidden_layer(B, N, H, W, training):
+    """relu(bn1(c)) is folded into the gate kernels: against conv1-output -> bn1 -> relu -> gate
+    sequenced with ATen ops, forward, every gradient and both BatchNorms' running statistics."""
+    from vision_mtl_b200 import ops
+
+    g = torch.Generator().manual_seed(23)
+    c = torch.randn(B, 128, H, W, generator=g) * 1.3 + 0.2
+    s = torch.relu(torch.randn(B, N, H, W, generator=g))
+    dy = torch.randn(B, N, H, W, generator=g)
+    bn1, conv2, bn2 = torch.nn.BatchNorm2d(128), torch.nn.Conv2d(128, N, 1), torch.nn.BatchNorm2d(N)
+    with torch.no_grad():
+        for bn in (bn1, bn2):
+            bn.weight.uniform_(0.5, 1.5, generator=g)
+            bn.bias.uniform_(-0.5, 0.5, generator=g)
+            bn.running_mean.uniform_(-0.2, 0.2, generator=g)
+            bn.running_var.uniform_(0.5, 1.5, generator=g)
+    mods = torch.nn.ModuleList([bn1, conv2, bn2])
+    ref = type(mods)([type(m)(*a) for m, a in ((bn1, (128,)), (conv2, (128, N, 1)), (bn2, (N,)))])
+    ref.load_state_dict(mods.state_dict())
+    ref.train(training)
+    cr, sr = c.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    yr = sr * torch.sigmoid(ref[2](ref[1](torch.relu(ref[0](cr)))))
+    yr.backward(dy)
+
+    mods.to(dev()).train(training)
+    cd, sd = to_cl(c).requires_grad_(True), to_cl(s).requires_grad_(True)
+    assert ops.folded_gate_supported(cd, sd, mods[0], mods[2])
+    y = ops.attention_gate_folded(cd, mods[0], sd, mods[1], mods[2])
+    y.backward(to_cl(dy))
+    assert_rel(y, yr, what="y")
+    assert_rel(sd.grad, sr.grad, what="ds")
+    assert_rel(cd.grad, cr.grad, what="dc")
+    for (k, p), (_, q) in zip(mods.named_parameters(), ref.named_parameters()):
+        if k == "1.bias" and training:  # analytically zero under batch statistics
+            assert p.grad.abs().max().item() <= 1e-4 * max(ref[2].bias.grad.abs().max().item(), 1e-30) + 1e-6
+        else:
+            assert_rel(p.grad, q.grad, what=k)
+    for (k, b), (_, q) in zip(mods.named_buffers(), ref.named_buffers()):
+        if "num_batches" in k:
+            assert int(b) == int(q), k
+        else:
+            assert_rel(b, q, what=k)

@@ -463,7 +463,9 @@ extern "C" size_t vmtl_gate_workspace_bytes(int64_t M, int K, int N, int precisi
   return gate_ws_floats(M, K, N, precision, backward, nullptr, nullptr) * sizeof(float) + 256;
 }
 
-extern "C" int vmtl_gate_fwd(const float* h, const float* s, const float* W, const float* bias,
+extern "C" int vmtl_gate_tc_supported(int K, int N) { return gate_tc_supported(K, N) ? 1 : 0; }
+
+extern "C" int vmtl_gate_fwd(const float* h, const float* h_coef, const float* s, const float* W, const float* bias,
                              const float* gamma, const float* beta, float* running_mean,
                              float* running_var, float momentum, float eps, int training, int precision,
                              int64_t M, int K, int N, float* y, float* save_z, float* save_mean,
@@ -471,6 +473,7 @@ extern "C" int vmtl_gate_fwd(const float* h, const float* s, const float* W, con
   int rc = gate_check(M, K, N, precision);
   if (rc != VMTL_OK) return rc;
   if (!h || !s || !W || !bias || !gamma || !beta || !y || !workspace) return VMTL_EINVAL;
+  if (h_coef && (precision == VMTL_GATE_FP32_FFMA || !gate_tc_supported(K, N))) return VMTL_EUNSUPPORTED;
   if (training && !save_z) return VMTL_EINVAL;
   if (!training && (!running_mean || !running_var)) return VMTL_EINVAL;
   if (!aligned16(h) || !aligned16(s) || !aligned16(W) || !aligned16(y) || !aligned16(workspace) ||
@@ -491,12 +494,12 @@ extern "C" int vmtl_gate_fwd(const float* h, const float* s, const float* W, con
     if ((rc = launch_status()) != VMTL_OK) return rc;
     const bool tc = precision != VMTL_GATE_FP32_FFMA && gate_tc_supported(K, N);
     if (tc && !save_z)  // inference: single fused pass, z never stored
-      return gate_tc_fwd_eval(h, s, W, bias, ws.coefA, ws.coefB, M, K, N, split3, y, st);
+      return gate_tc_fwd_eval(h, h_coef, s, W, bias, ws.coefA, ws.coefB, M, K, N, split3, y, st);
     float* zbuf = save_z ? save_z : ws.zbuf;  // the CUDA-core path stages z (workspace when not saved)
     if (!zbuf) return VMTL_EWORKSPACE;
     if (tc) {
       int unused = 0;  // a backward will follow: keep z (batch partials are computed but unused)
-      rc = gate_tc_fwd_gemm(h, W, bias, M, K, N, split3, zbuf, ws.partial, ws.partial_rows, &unused, st);
+      rc = gate_tc_fwd_gemm(h, h_coef, W, bias, M, K, N, split3, zbuf, ws.partial, ws.partial_rows, &unused, st);
     } else {
       rc = sgemm64(h, W, zbuf, bias, M, N, K, K, 1, 1, K, N, 1, 0, st);
     }
@@ -507,7 +510,7 @@ extern "C" int vmtl_gate_fwd(const float* h, const float* s, const float* W, con
 
   int nparts = 0;
   if (precision != VMTL_GATE_FP32_FFMA && gate_tc_supported(K, N)) {
-    rc = gate_tc_fwd_gemm(h, W, bias, M, K, N, split3, save_z, ws.partial, ws.partial_rows, &nparts, st);
+    rc = gate_tc_fwd_gemm(h, h_coef, W, bias, M, K, N, split3, save_z, ws.partial, ws.partial_rows, &nparts, st);
     if (rc != VMTL_OK) return rc;
   } else {
     rc = sgemm64(h, W, save_z, bias, M, N, K, K, 1, 1, K, N, 1, 0, st);
@@ -526,7 +529,7 @@ extern "C" int vmtl_gate_fwd(const float* h, const float* s, const float* W, con
 }
 
 // coefA/B from saved statistics (backward re-derives them instead of trusting workspace reuse)
-extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, const float* z,
+extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* h_coef, const float* s, const float* z,
                              const float* W, const float* gamma, const float* beta,
                              const float* save_mean, const float* save_invstd, int training,
                              int precision, int64_t M, int K, int N, float* dh, float* ds, float* dW,
@@ -537,6 +540,7 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, co
   if (!dy || !h || !s || !z || !W || !gamma || !beta || !save_mean || !save_invstd || !dW || !dbias ||
       !dgamma || !dbeta || !workspace)
     return VMTL_EINVAL;
+  if (h_coef && (precision == VMTL_GATE_FP32_FFMA || !gate_tc_supported(K, N))) return VMTL_EUNSUPPORTED;
   if (!aligned16(dy) || !aligned16(h) || !aligned16(s) || !aligned16(z) || !aligned16(W) ||
       !aligned16(workspace) || (dh && !aligned16(dh)) || (ds && !aligned16(ds)))
     return VMTL_EALIGN;
@@ -550,7 +554,7 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* s, co
   if (precision != VMTL_GATE_FP32_FFMA && gate_tc_supported(K, N)) {
     // tensor-core path: pass 1 (ds + statistics + dW partials), finalize, pass 2 (dh)
     int np1 = 0;
-    rc = gate_tc_bwd_pass1(dy, h, s, z, gamma, beta, save_mean, save_invstd, M, K, N, split3, ds, ws, &np1, st);
+    rc = gate_tc_bwd_pass1(dy, h, h_coef, s, z, gamma, beta, save_mean, save_invstd, M, K, N, split3, ds, ws, &np1, st);
     if (rc != VMTL_OK) return rc;
     gate_bwd_tc_finalize<<<(N / kFinRows) * (K / 32) + (N + 31) / 32, kFinThreads, 0, st>>>(
         ws.gemm_partial, ws.hs_partial, ws.partial, np1, N <= 64 ? 1 : N / 64, M, N, K, training, gamma, beta, save_mean, save_invstd, dW,

@@ -60,17 +60,19 @@ inline size_t gate_ws_floats(int64_t M, int K, int N, int precision, int backwar
 // Forward phase 1: z = h @ W^T + bias -> save_z, per-CTA column partials (sum, sumsq) into
 // ws.partial rows [0, *nparts).  EVAL variant applies the folded BN + sigmoid + product
 // directly and writes y.
-int gate_tc_fwd_gemm(const float* h, const float* W, const float* bias, int64_t M, int K, int N,
+// h_coef (everywhere below): nullptr, or [A1 | B1] ([2][K]) -- then `h` is the hidden layer's PRE-activation and the
+// kernels rebuild h = max(A1 c + B1, 0) while they convert the operand.
+int gate_tc_fwd_gemm(const float* h, const float* h_coef, const float* W, const float* bias, int64_t M, int K, int N,
                      int split3, float* z_out, float* partial, int partial_rows, int* nparts,
                      cudaStream_t st);
-int gate_tc_fwd_eval(const float* h, const float* s, const float* W, const float* bias,
+int gate_tc_fwd_eval(const float* h, const float* h_coef, const float* s, const float* W, const float* bias,
                      const float* coefA, const float* coefB, int64_t M, int K, int N, int split3,
                      float* y, cudaStream_t st);
 // Backward pass 1 (statistics + dW partials + ds).  CTA b of the *nparts CTAs owns the column chunk b % nch
 // (nch = N <= 64 ? 1 : N / 64, chunk width Nc = N / nch); its partials land in ws.gemm_partial ([b][2][Nc][K]:
 // P1 = du^T h, P2 = zhat^T h), ws.hs_partial ([b][K]: sum_r h over its units) and ws.partial ([b][3][Nc]: sum du,
 // sum du*zhat, sum zhat); gate.cu's finalize turns them into the gradients.
-int gate_tc_bwd_pass1(const float* dy, const float* h, const float* s, const float* z, const float* gamma,
+int gate_tc_bwd_pass1(const float* dy, const float* h, const float* h_coef, const float* s, const float* z, const float* gamma,
                       const float* beta, const float* mean, const float* invstd, int64_t M, int K, int N,
                       int split3, float* ds, const GateWs& ws, int* nparts, cudaStream_t st);
 // Backward pass 2: dh = dz @ W with dz rebuilt per tile from (dy, s, z) and the finalized ws.c1 / ws.c2.

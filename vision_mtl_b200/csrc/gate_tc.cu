@@ -46,22 +46,22 @@ namespace vmtl {
 
 bool gate_tc_supported(int K, int N) { return K == 128 && (N == 32 || (N % 64 == 0 && N >= 64 && N <= 1024)); }
 
-int gate_tc_fwd_gemm(const float* h, const float* W, const float* bias, int64_t M, int K, int N,
+int gate_tc_fwd_gemm(const float* h, const float* h_coef, const float* W, const float* bias, int64_t M, int K, int N,
                      int split3, float* z_out, float* partial, int partial_rows, int* nparts,
                      cudaStream_t st) {
   if (!gate_tc_supported(K, N)) return VMTL_EUNSUPPORTED;
   const int grid = fwd_tma_grid(M, N <= 64 ? 1 : N / 64);
   if (grid > partial_rows) return VMTL_EWORKSPACE;
   *nparts = grid;
-  return dispatch_fwd_tma<false>(h, W, bias, M, N, split3, z_out, partial, nullptr, nullptr, nullptr, grid, st);
+  return dispatch_fwd_tma<false>(h, h_coef, W, bias, M, N, split3, z_out, partial, nullptr, nullptr, nullptr, grid, st);
 }
 
-int gate_tc_fwd_eval(const float* h, const float* s, const float* W, const float* bias,
+int gate_tc_fwd_eval(const float* h, const float* h_coef, const float* s, const float* W, const float* bias,
                      const float* coefA, const float* coefB, int64_t M, int K, int N, int split3,
                      float* y, cudaStream_t st) {
   if (!gate_tc_supported(K, N)) return VMTL_EUNSUPPORTED;
   const int grid = fwd_tma_grid(M, N <= 64 ? 1 : N / 64);
-  return dispatch_fwd_tma<true>(h, W, bias, M, N, split3, y, nullptr, s, coefA, coefB, grid, st);
+  return dispatch_fwd_tma<true>(h, h_coef, W, bias, M, N, split3, y, nullptr, s, coefA, coefB, grid, st);
 }
 
 static int tc_grid(int64_t M, int rows) {
@@ -70,7 +70,7 @@ static int tc_grid(int64_t M, int rows) {
   return (int)(n < sms ? n : sms);
 }
 
-int gate_tc_bwd_pass1(const float* dy, const float* h, const float* s, const float* z, const float* gamma,
+int gate_tc_bwd_pass1(const float* dy, const float* h, const float* h_coef, const float* s, const float* z, const float* gamma,
                       const float* beta, const float* mean, const float* invstd, int64_t M, int K, int N,
                       int split3, float* ds, const GateWs& ws, int* nparts, cudaStream_t st) {
   if (!gate_tc_supported(K, N) || !ws.hs_partial) return VMTL_EUNSUPPORTED;
@@ -86,9 +86,9 @@ int gate_tc_bwd_pass1(const float* dy, const float* h, const float* s, const flo
       grid > ws.hs_rows)
     return VMTL_EWORKSPACE;
   *nparts = grid;
-  return split3 ? launch_sdw_tma<true>(dy, h, s, z, gamma, beta, mean, invstd, M, N, ds, ws.gemm_partial, ws.hs_partial,
-                                       ws.partial, grid, nch, st)
-                : launch_sdw_tma<false>(dy, h, s, z, gamma, beta, mean, invstd, M, N, ds, ws.gemm_partial,
+  return split3 ? launch_sdw_tma<true>(dy, h, h_coef, s, z, gamma, beta, mean, invstd, M, N, ds, ws.gemm_partial,
+                                       ws.hs_partial, ws.partial, grid, nch, st)
+                : launch_sdw_tma<false>(dy, h, h_coef, s, z, gamma, beta, mean, invstd, M, N, ds, ws.gemm_partial,
                                         ws.hs_partial, ws.partial, grid, nch, st);
 }
 

@@ -346,6 +346,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     gate_tc_sdw_tma_kernel(const __grid_constant__ CUtensorMap tmap_h /* box [32 x 64], SW128 */,
                            const __grid_constant__ CUtensorMap tmap_dy /* box [32 x 64], SW128_ATOM_32B */,
                            const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_s,
+                           const float* __restrict__ h_coef /* nullptr, or [A1 | B1]: the h operand is the hidden
+                              layer's pre-activation c and h = max(A1 c + B1, 0) is rebuilt here */,
                            const float* __restrict__ gamma, const float* __restrict__ beta,
                            const float* __restrict__ mean, const float* __restrict__ invstd, int64_t M,
                            float* __restrict__ ds /* [M, n_total] or nullptr */,
@@ -473,6 +475,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     // ------------------------------------------------------------------ converters A: h^T -> TMEM, then their chunks
     const int quad = warp & 3, rh = warp >> 2;  // lane quadrant (k / 32), 32-row half of the unit
     const int k = quad * 32 + lane;
+    const bool pre = h_coef != nullptr;
+    const float a1 = pre ? h_coef[k] : 1.f, b1 = pre ? h_coef[KH + k] : 0.f;
     for (int64_t u = 0; u < nunits; ++u) {
       const int s = (int)(u % S), hb = (int)(u & 1);
       const int64_t row0 = (cslot + u * cgrid) * L::kHalfRows;
@@ -485,6 +489,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         for (int r = 0; r < 32; ++r) {
           const int row = rh * 32 + r;
           hv[r] = *reinterpret_cast<const float*>(hs + sw128_off(row, (k & 31) >> 2) + ((k & 3) << 2));
+          // folded BatchNorm + ReLU of the hidden layer; rows past M arrive as zeros and must stay zeros
+          if (pre) hv[r] = row0 + row < M ? fmaxf(fmaf(a1, hv[r], b1), 0.f) : 0.f;
           hsum_acc += hv[r];
         }
         if (u >= 2) {  // the MMAs of unit u-2 (same A half buffer) are done
@@ -636,7 +642,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 // pass 1: ONE launch.  N = 32: NA = 1; otherwise 64-column chunks (NA = 2: 256 accumulator columns in TMEM) spread
 //         over the CTAs of the launch, grid a multiple of the chunk count.
 template <bool SPLIT>
-static int launch_sdw_tma(const float* dy, const float* h, const float* s, const float* z, const float* gamma,
+static int launch_sdw_tma(const float* dy, const float* h, const float* h_coef, const float* s, const float* z, const float* gamma,
                           const float* beta, const float* mean, const float* invstd, int64_t M, int N, float* ds,
                           float* pw_partial, float* hs_partial, float* col_partial, int grid, int nch, cudaStream_t st) {
   CUtensorMap t_h, t_dy, t_z, t_s;
@@ -647,14 +653,14 @@ static int launch_sdw_tma(const float* dy, const float* h, const float* s, const
     auto k = gate_tc_sdw_tma_kernel<1, SPLIT>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SdwSmem<1>::kBytes) != cudaSuccess)
       return VMTL_ECUDA;
-    k<<<grid, kTmaThreads, SdwSmem<1>::kBytes, st>>>(t_h, t_dy, t_z, t_s, gamma, beta, mean, invstd, M, ds, pw_partial,
+    k<<<grid, kTmaThreads, SdwSmem<1>::kBytes, st>>>(t_h, t_dy, t_z, t_s, h_coef, gamma, beta, mean, invstd, M, ds, pw_partial,
                                                      hs_partial, col_partial, 1, N);
     return launch_status();
   }
   auto k = gate_tc_sdw_tma_kernel<2, SPLIT>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SdwSmem<2>::kBytes) != cudaSuccess)
     return VMTL_ECUDA;
-  k<<<grid, kTmaThreads, SdwSmem<2>::kBytes, st>>>(t_h, t_dy, t_z, t_s, gamma, beta, mean, invstd, M, ds, pw_partial,
+  k<<<grid, kTmaThreads, SdwSmem<2>::kBytes, st>>>(t_h, t_dy, t_z, t_s, h_coef, gamma, beta, mean, invstd, M, ds, pw_partial,
                                                    hs_partial, col_partial, nch, N);
   return launch_status();
 }

@@ -34,14 +34,17 @@ struct TmaSmem {
   static constexpr int kAtomB = 2 * NC * 128;              // rows [0,NC) = W_hi, [NC,2NC) = W_lo
   static constexpr int kB = kStages * kStage;
   static constexpr int kMisc = kB + 4 * kAtomB;
-  static constexpr int kBytes = kMisc + 256 + 3 * 64 * 4 + 1024;
+  static constexpr int kBytes = kMisc + 256 + 3 * 64 * 4 + 2 * 128 * 4 + 1024;
 };
 
 // N = NC * nch.  nch > 1: column chunks of NC are spread over CTAs (chunk = blockIdx.x % nch, fixed per CTA so
 // its W operand is staged once); gridDim.x is a multiple of nch.
-template <int NC, bool SPLIT, bool EVAL>
+// PRE: the operand is the PRE-activation c of the hidden layer and the converters fold the BatchNorm + ReLU in front
+// of the gate into the conversion, h = max(A1 c + B1, 0) (h_coef = [A1 | B1], [2][128]): h is never materialised.
+template <int NC, bool SPLIT, bool EVAL, bool PRE>
 __global__ void __launch_bounds__(kTmaThreads, 1)
-    gate_tc_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_h, const float* __restrict__ W,
+    gate_tc_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_h, const float* __restrict__ h_coef,
+                           const float* __restrict__ W,
                            const float* __restrict__ bias, int64_t M, int nch,
                            float* __restrict__ out /* TRAIN: z ; EVAL: y */,
                            float* __restrict__ partial /* TRAIN: [gridDim.x][2][N] */,
@@ -63,6 +66,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   float* s_bias = reinterpret_cast<float*>(smem + L::kMisc + 256);
   float* s_cA = s_bias + 64;
   float* s_cB = s_cA + 64;
+  float* s_hc = s_cB + 64;  // PRE: [A1 | B1] of the hidden layer's BatchNorm, 2 x 128
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x % nch;          // this CTA's column chunk (fixed: W staged once)
@@ -91,6 +95,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   }
   if (warp == 17) tmem_alloc(smem_u32(s_tmem), kTmemCols);
   if (warp == 16 && lane == 0) tma_prefetch_desc(&tmap_h);
+  if (PRE)
+    for (int i = threadIdx.x; i < 256; i += kTmaThreads) s_hc[i] = h_coef[i];
   for (int i = threadIdx.x; i < NC; i += kTmaThreads) {
     s_bias[i] = bias[chunk * NC + i];
     if (EVAL) {
@@ -142,6 +148,17 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         float4 c[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) c[j] = *reinterpret_cast<const float4*>(atom + sw128_off(row, j));
+        if (PRE) {  // h = max(A1 c + B1, 0); all lanes read the same coefficients (shared-memory broadcast)
+          const float* hc = s_hc + (kh * 2 + a2) * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 A1 = *reinterpret_cast<const float4*>(hc + 4 * j), B1 = *reinterpret_cast<const float4*>(hc + 128 + 4 * j);
+            c[j].x = fmaxf(fmaf(A1.x, c[j].x, B1.x), 0.f);
+            c[j].y = fmaxf(fmaf(A1.y, c[j].y, B1.y), 0.f);
+            c[j].z = fmaxf(fmaf(A1.z, c[j].z, B1.z), 0.f);
+            c[j].w = fmaxf(fmaf(A1.w, c[j].w, B1.w), 0.f);
+          }
+        }
         if (it > 0) {  // MMAs that read this A half for the previous tile are done
           mbar_wait(bar_amma(kh), (uint32_t)((it - 1) & 1));
           tc_fence_after_sync();
@@ -295,18 +312,26 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   }
 }
 
-template <int NC, bool SPLIT, bool EVAL>
-static int launch_fwd_tma(const float* h, const float* W, const float* bias, int64_t M, int nch, float* out,
-                          float* partial, const float* s_in, const float* coefA, const float* coefB, int grid,
-                          cudaStream_t st) {
+template <int NC, bool SPLIT, bool EVAL, bool PRE>
+static int launch_fwd_tma1(const CUtensorMap& tmap, const float* h_coef, const float* W, const float* bias, int64_t M,
+                           int nch, float* out, float* partial, const float* s_in, const float* coefA,
+                           const float* coefB, int grid, cudaStream_t st) {
   using L = TmaSmem<NC>;
-  CUtensorMap tmap;
-  if (!make_tmap_2d(&tmap, h, M, 128, kTileM)) return VMTL_ECUDA;
-  auto kern = gate_tc_fwd_tma_kernel<NC, SPLIT, EVAL>;
+  auto kern = gate_tc_fwd_tma_kernel<NC, SPLIT, EVAL, PRE>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes) != cudaSuccess)
     return VMTL_ECUDA;
-  kern<<<grid, kTmaThreads, L::kBytes, st>>>(tmap, W, bias, M, nch, out, partial, s_in, coefA, coefB);
+  kern<<<grid, kTmaThreads, L::kBytes, st>>>(tmap, h_coef, W, bias, M, nch, out, partial, s_in, coefA, coefB);
   return launch_status();
+}
+
+template <int NC, bool SPLIT, bool EVAL>
+static int launch_fwd_tma(const float* h, const float* h_coef, const float* W, const float* bias, int64_t M, int nch,
+                          float* out, float* partial, const float* s_in, const float* coefA, const float* coefB,
+                          int grid, cudaStream_t st) {
+  CUtensorMap tmap;
+  if (!make_tmap_2d(&tmap, h, M, 128, kTileM)) return VMTL_ECUDA;
+  return h_coef ? launch_fwd_tma1<NC, SPLIT, EVAL, true>(tmap, h_coef, W, bias, M, nch, out, partial, s_in, coefA, coefB, grid, st)
+                : launch_fwd_tma1<NC, SPLIT, EVAL, false>(tmap, h_coef, W, bias, M, nch, out, partial, s_in, coefA, coefB, grid, st);
 }
 
 // grid of the forward: (row tile, column chunk) items over the SMs, a multiple of nch
@@ -318,15 +343,15 @@ static int fwd_tma_grid(int64_t M, int nch) {
 }
 
 template <bool EVAL>
-static int dispatch_fwd_tma(const float* h, const float* W, const float* bias, int64_t M, int N, int split3,
-                            float* out, float* partial, const float* s_in, const float* coefA, const float* coefB,
-                            int grid, cudaStream_t st) {
+static int dispatch_fwd_tma(const float* h, const float* h_coef, const float* W, const float* bias, int64_t M, int N,
+                            int split3, float* out, float* partial, const float* s_in, const float* coefA,
+                            const float* coefB, int grid, cudaStream_t st) {
   const int nch = N <= 64 ? 1 : N / 64;
   if (N == 32)
-    return split3 ? launch_fwd_tma<32, true, EVAL>(h, W, bias, M, 1, out, partial, s_in, coefA, coefB, grid, st)
-                  : launch_fwd_tma<32, false, EVAL>(h, W, bias, M, 1, out, partial, s_in, coefA, coefB, grid, st);
-  return split3 ? launch_fwd_tma<64, true, EVAL>(h, W, bias, M, nch, out, partial, s_in, coefA, coefB, grid, st)
-                : launch_fwd_tma<64, false, EVAL>(h, W, bias, M, nch, out, partial, s_in, coefA, coefB, grid, st);
+    return split3 ? launch_fwd_tma<32, true, EVAL>(h, h_coef, W, bias, M, 1, out, partial, s_in, coefA, coefB, grid, st)
+                  : launch_fwd_tma<32, false, EVAL>(h, h_coef, W, bias, M, 1, out, partial, s_in, coefA, coefB, grid, st);
+  return split3 ? launch_fwd_tma<64, true, EVAL>(h, h_coef, W, bias, M, nch, out, partial, s_in, coefA, coefB, grid, st)
+                : launch_fwd_tma<64, false, EVAL>(h, h_coef, W, bias, M, nch, out, partial, s_in, coefA, coefB, grid, st);
 }
 
 }  // namespace vmtl

@@ -44,7 +44,11 @@ class _GatedAttention(nn.Module):
         return y if pool is None else pool(y)
 
     def _gate(self, merged: torch.Tensor, shared: torch.Tensor) -> torch.Tensor:
-        hidden = self._bn_relu(self.conv1(merged), self.bn1, self.relu1)
+        squeezed = self.conv1(merged)
+        if isinstance(self.relu1, nn.ReLU) and ops.folded_gate_supported(squeezed, shared, self.bn1, self.bn2, self.gate_precision):
+            # bn1 + relu1 are folded into the gate kernels: the hidden activation never reaches HBM
+            return ops.attention_gate_folded(squeezed, self.bn1, shared, self.conv2, self.bn2, self.gate_precision)
+        hidden = self._bn_relu(squeezed, self.bn1, self.relu1)
         bn = self.bn2
         use_batch_stats = bn.training or bn.running_mean is None
         if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:

@@ -323,7 +323,10 @@ def gate_bytes(M: int, K: int, N: int, training: bool, backward: bool, stored_z:
 class GateFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, s, weight, bias, gamma, beta, running_mean, running_var, training, momentum,
-                eps, precision):
+                eps, precision, h_coef=None):
+        """``h_coef`` ([2,K], no gradient): ``h`` is then the hidden layer's pre-activation and the kernels fold
+        ``max(A1 h + B1, 0)`` into their operand conversion; the backward's first gradient is w.r.t. that
+        activation (``FoldedGateFunction`` chains the BatchNorm backward behind it)."""
         h = _nhwc(h)
         s = _nhwc(s)
         _need_cuda(h, s, weight)
@@ -341,7 +344,7 @@ class GateFunction(torch.autograd.Function):
         lib = _lib.load()
         ws = _workspace(lib.vmtl_gate_workspace_bytes(M, K, N, precision, 0), h.device)
         algo, issued = gate_bytes(M, K, N, training, backward=False, stored_z=z is not None)
-        _call("gate_fwd", algo, _p(h), _p(s), _p(w2), _p(bias.detach()), _p(gamma.detach()),
+        _call("gate_fwd", algo, _p(h), _p(h_coef), _p(s), _p(w2), _p(bias.detach()), _p(gamma.detach()),
               _p(beta.detach()), _p(running_mean), _p(running_var), float(momentum), float(eps),
               1 if training else 0, precision, M, K, N, _p(y), _p(z), _p(mean), _p(invstd), _p(ws),
               ws.numel(), _stream(), issued=issued)
@@ -349,12 +352,14 @@ class GateFunction(torch.autograd.Function):
         ctx.precision = precision
         ctx.dims = (M, K, N)
         ctx.wshape = weight.shape
-        ctx.save_for_backward(h, s, z, w2, gamma, beta, mean, invstd)
+        ctx.has_pre = h_coef is not None
+        ctx.save_for_backward(h, s, z, w2, gamma, beta, mean, invstd, *([h_coef] if h_coef is not None else []))
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        h, s, z, w2, gamma, beta, mean, invstd = ctx.saved_tensors
+        h, s, z, w2, gamma, beta, mean, invstd, *pre = ctx.saved_tensors
+        h_coef = pre[0] if pre else None
         M, K, N = ctx.dims
         dy = _nhwc(dy)
         need_dh, need_ds = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
@@ -367,14 +372,114 @@ class GateFunction(torch.autograd.Function):
         lib = _lib.load()
         ws = _workspace(lib.vmtl_gate_workspace_bytes(M, K, N, ctx.precision, 1), h.device)
         algo, issued = gate_bytes(M, K, N, ctx.training, backward=True)
-        _call("gate_bwd", algo, _p(dy), _p(h), _p(s), _p(z), _p(w2), _p(gamma.detach()),
+        _call("gate_bwd", algo, _p(dy), _p(h), _p(h_coef), _p(s), _p(z), _p(w2), _p(gamma.detach()),
               _p(beta.detach()), _p(mean), _p(invstd), 1 if ctx.training else 0, ctx.precision, M, K, N,
               _p(dh), _p(ds), _p(dW), _p(dbias), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream(),
               issued=issued)
         if ctx.precision != 0 and N > 64 and K == 128 and N % 64 == 0:
             # wider gates run extra dh launches: per 64 columns, or per 256 when every CTA owns a single 128-row tile
             _Prof.launches += _gate_bwd_passes(M, N)[1] - 1
-        return (dh, ds, dW.reshape(ctx.wshape), dbias, dgamma, dbeta, None, None, None, None, None, None)
+        return (dh, ds, dW.reshape(ctx.wshape), dbias, dgamma, dbeta, None, None, None, None, None, None, None)
+
+
+class FoldedGateFunction(torch.autograd.Function):
+    """``s * sigmoid(bn2(conv2( relu(bn1(c)) )))`` with the hidden activation ``relu(bn1(c))`` never written to
+    HBM: one statistics pass over ``c`` (the 1x1 squeeze's output) produces bn1's folded
+    coefficients, the gate kernels apply them while converting their operand, and the backward chains the gate
+    backward (gradient w.r.t. the activation) into the fused BatchNorm + ReLU backward over ``c``."""
+
+    @staticmethod
+    def forward(ctx, c, g1, b1, rm1, rv1, train1, mom1, eps1, s, weight, bias, g2, b2, rm2, rv2, train2, mom2, eps2,
+                precision):
+        c = _nhwc(c)
+        s = _nhwc(s)
+        _need_cuda(c, s, weight)
+        B, K, H, W = c.shape
+        N = s.shape[1]
+        M = B * H * W
+        dev = c.device
+        lib = _lib.load()
+        stats1 = torch.empty((4, K), dtype=torch.float32, device=dev)  # mean1, invstd1, A1, B1
+        ws1 = _workspace(lib.vmtl_bnrelu_workspace_bytes(M, K), dev)
+        _call("bnrelu_fwd", 4 * K * M if train1 else 0, _p(c), _p(g1.detach()), _p(b1.detach()), _p(rm1), _p(rv1),
+              float(mom1), float(eps1), 1 if train1 else 0, 1, M, K, _p(None), _p(stats1[0]), _p(stats1[1]),
+              _p(stats1[2:]), _p(ws1), ws1.numel(), _stream())
+        _Prof.launches -= 1 if train1 else 2  # statistics (+ finalize) only: nothing is applied
+        w2 = weight.detach().reshape(N, K).contiguous()
+        y = torch.empty_like(s)
+        need_z = train2 or any(ctx.needs_input_grad)
+        z = torch.empty_like(s) if need_z else None
+        st2 = torch.empty((2, N), dtype=torch.float32, device=dev)
+        ws = _workspace(lib.vmtl_gate_workspace_bytes(M, K, N, precision, 0), dev)
+        algo, issued = gate_bytes(M, K, N, train2, backward=False, stored_z=z is not None)
+        _call("gate_fwd", algo, _p(c), _p(stats1[2:]), _p(s), _p(w2), _p(bias.detach()), _p(g2.detach()),
+              _p(b2.detach()), _p(rm2), _p(rv2), float(mom2), float(eps2), 1 if train2 else 0, precision, M, K, N,
+              _p(y), _p(z), _p(st2[0]), _p(st2[1]), _p(ws), ws.numel(), _stream(), issued=issued)
+        ctx.cfg = (bool(train1), bool(train2), precision, (M, K, N), weight.shape)
+        ctx.save_for_backward(c, stats1, s, z, w2, g2, b2, st2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        c, stats1, s, z, w2, g2, b2, st2 = ctx.saved_tensors
+        train1, train2, precision, (M, K, N), wshape = ctx.cfg
+        dy = _nhwc(dy)
+        dev = c.device
+        lib = _lib.load()
+        need_dc = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dh = torch.empty_like(c) if need_dc else None
+        ds = torch.empty_like(s) if ctx.needs_input_grad[8] else None
+        dW = torch.empty_like(w2)
+        small = torch.empty((3, N), dtype=torch.float32, device=dev)  # dbias, dgamma2, dbeta2
+        ws = _workspace(lib.vmtl_gate_workspace_bytes(M, K, N, precision, 1), dev)
+        algo, issued = gate_bytes(M, K, N, train2, backward=True)
+        _call("gate_bwd", algo, _p(dy), _p(c), _p(stats1[2:]), _p(s), _p(z), _p(w2), _p(g2.detach()),
+              _p(b2.detach()), _p(st2[0]), _p(st2[1]), 1 if train2 else 0, precision, M, K, N, _p(dh), _p(ds), _p(dW),
+              _p(small[0]), _p(small[1]), _p(small[2]), _p(ws), ws.numel(), _stream(), issued=issued)
+        if N > 64:
+            _Prof.launches += _gate_bwd_passes(M, N)[1] - 1
+        dc = dg1 = db1 = None
+        if need_dc:  # relu + bn1 backward over (dh, c): statistics pass, finalize, apply pass
+            dc = torch.empty_like(c) if ctx.needs_input_grad[0] else None
+            dgb = torch.empty((2, K), dtype=torch.float32, device=dev)
+            ws1 = _workspace(lib.vmtl_bnrelu_workspace_bytes(M, K), dev)
+            _call("bnrelu_bwd", 4 * K * M * (5 if dc is not None else 2), _p(dh), _p(c), _p(stats1[2:]),
+                  _p(stats1[0]), _p(stats1[1]), 1 if train1 else 0, 1, M, K, _p(dc), _p(dgb[0]), _p(dgb[1]), _p(ws1),
+                  ws1.numel(), _stream())
+            dg1, db1 = dgb[0], dgb[1]
+        return (dc, dg1, db1, None, None, None, None, None, ds, dW.reshape(wshape), small[0], small[1], small[2],
+                None, None, None, None, None, None)
+
+
+def _bn_mode(bn):
+    """(use batch statistics, momentum) of an ``nn.BatchNorm2d`` call; bumps ``num_batches_tracked``."""
+    use_batch_stats = bn.training or bn.running_mean is None
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    if bn.momentum is None:
+        momentum = 1.0 / float(bn.num_batches_tracked) if bn.training and bn.track_running_stats else 0.0
+    else:
+        momentum = bn.momentum
+    return use_batch_stats, momentum
+
+
+def folded_gate_supported(c: torch.Tensor, s: torch.Tensor, bn1, bn2, precision: Optional[str] = None) -> bool:
+    prec = _GATE_PRECISIONS[precision or default_gate_precision]
+    return (prec != GATE_FP32_FFMA and c.is_cuda and bn_supported(bn1, c) and bn2.affine
+            and (bn2.training or bn2.running_mean is not None)
+            and bool(_lib.load().vmtl_gate_tc_supported(c.shape[1], s.shape[1])))
+
+
+def attention_gate_folded(c, bn1, s, conv2, bn2, precision: Optional[str] = None):
+    """The whole tail of an MTAN attention module after its 1x1 squeeze ``c = conv1(merged)``:
+    ``s * sigmoid(bn2(conv2(relu(bn1(c)))))`` (mtan_model.py:66-75 / :153-162)."""
+    t1, m1 = _bn_mode(bn1)
+    t2, m2 = _bn_mode(bn2)
+    rs = lambda bn, name: getattr(bn, name) if bn.track_running_stats else None  # noqa: E731
+    return FoldedGateFunction.apply(c, bn1.weight, bn1.bias, rs(bn1, "running_mean"), rs(bn1, "running_var"), t1, m1,
+                                    bn1.eps, s, conv2.weight, conv2.bias, bn2.weight, bn2.bias, rs(bn2, "running_mean"),
+                                    rs(bn2, "running_var"), t2, m2, bn2.eps,
+                                    _GATE_PRECISIONS[precision or default_gate_precision])
 
 
 def attention_gate(h, s, weight, bias, gamma, beta, running_mean, running_var, training: bool,
