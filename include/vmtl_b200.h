@@ -76,6 +76,26 @@ int vmtl_xstitch_bwd(const float* const* dy_host, const float* const* x_host,
                      int64_t npix, int C, int channel_wise, int mode, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* Cross-stitch unit fused with the tensor assembly in front of it at CSNet's decoder sites
+ * (vision_mtl/models/cross_stitch_model.py:121-156, utils/model_utils.py:46-58): per task, the stitched map is
+ *   up2 == 0 : cat([skip, zero_pad(x)], channel)   skip [B,Ho,Wo,Cs] (Cs may be 0), x [B,Hi,Wi,Cx] centred in
+ *              the [Ho,Wo] frame (Ho >= Hi, Wo >= Wi), C = Cs + Cx
+ *   up2 != 0 : nearest x2 up-sampling of x          (Cs == 0, Ho == 2 Hi, Wo == 2 Wi)
+ * The kernels gather from (skip, x) and write y [B,Ho,Wo,C] per task; the concatenated / up-sampled tensor
+ * never exists.  alpha is [T,T] or [T,T,C].  Backward: dskip / dx (entries may be NULL), dalpha. */
+int vmtl_xstitch_cat_fwd(const float* const* skip_host, const float* const* x_host, float* const* y_host,
+                         const float* alpha, int T, int B, int Ho, int Wo, int Cs, int Hi, int Wi, int Cx,
+                         int up2, int channel_wise, int mode, void* stream);
+
+size_t vmtl_xstitch_cat_bwd_workspace_bytes(int T, int B, int Ho, int Wo, int Cs, int Hi, int Wi, int Cx,
+                                            int up2, int channel_wise);
+
+int vmtl_xstitch_cat_bwd(const float* const* dy_host, const float* const* skip_host,
+                         const float* const* x_host, float* const* dskip_host, float* const* dx_host,
+                         const float* alpha, float* dalpha, int T, int B, int Ho, int Wo, int Cs, int Hi,
+                         int Wi, int Cx, int up2, int channel_wise, int mode, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * MTAN attention gate:  y = s * sigmoid(BN(h @ W^T + bias)).
  * Replaces conv2 -> bn2 -> sigmoid -> mul at vision_mtl/models/mtan_model.py:71-75

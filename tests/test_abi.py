@@ -110,5 +110,7 @@ def test_csnet_plan_and_state_dict_keys():
     assert "cross_stitch_layers.0_decoder_blocks_4.weights" in keys
     assert any(k.startswith("models.segm.0.encoder.model.conv_stem") for k in keys)
     ops_ = [op for op, _ in net._plan]
-    assert ops_.count("stitch") == 11 and ops_.count("save_skip") == 4 and ops_.count("cat_skip") == 4
-    assert ops_.count("upsample2") == 1
+    # 11 stitch sites: 6 encoder sites, 4 decoder sites fused with their zero-pad + cat, and the last
+    # decoder site fused with its nearest x2 up-sampling
+    assert ops_.count("stitch") == 6 and ops_.count("cat_stitch") == 4 and ops_.count("up_stitch") == 1
+    assert ops_.count("save_skip") == 4 and ops_.count("cat_skip") == 0 and ops_.count("upsample2") == 0

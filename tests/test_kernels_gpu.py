@@ -419,3 +419,61 @@ def test_gate_folded_hidden_layer(B, N, H, W, training):
             assert int(b) == int(q), k
         else:
             assert_rel(b, q, what=k)
+
+
+# ----------------------------------------------------------------------------- pad + cat + stitch / upsample + stitch
+CAT_CASES = [  # (T, B, Cs, Ho, Wo, Cx, Hi, Wi, up2)
+    (2, 2, 112, 8, 16, 960, 4, 8, False),   # decoder block 0 of the csnet config (1072 channels, x zero-padded)
+    (2, 2, 40, 16, 32, 256, 8, 16, False),
+    (2, 1, 24, 12, 20, 128, 6, 10, False),
+    (2, 2, 16, 9, 13, 64, 5, 6, False),     # odd sizes: asymmetric centred padding
+    (3, 1, 8, 6, 6, 12, 6, 6, False),       # same size: pure cat
+    (2, 2, 0, 16, 24, 32, 8, 12, True),     # last decoder block: nearest x2
+    (3, 1, 0, 8, 8, 16, 4, 4, True),
+]
+
+
+@pytest.mark.parametrize("T,B,Cs,Ho,Wo,Cx,Hi,Wi,up2", CAT_CASES)
+@pytest.mark.parametrize("cw", [True, False])
+@pytest.mark.parametrize("mode", ["reference_diag", "full_mix"])
+def test_xstitch_cat_fwd_bwd(T, B, Cs, Ho, Wo, Cx, Hi, Wi, up2, cw, mode):
+    """The gather-stitch kernels against the reference's op sequence (F.pad + torch.cat / nearest interpolate, then
+    the stitch oracle): outputs, input gradients and alpha gradients."""
+    from vision_mtl_b200 import ops
+
+    g = torch.Generator().manual_seed(29)
+    C = Cs + Cx
+    xs = [torch.randn(B, Cx, Hi, Wi, generator=g) for _ in range(T)]
+    skips = [torch.randn(B, Cs, Ho, Wo, generator=g) for _ in range(T)] if Cs else []
+    alpha = torch.rand(T, T, C, generator=g) if cw else torch.rand(T, T, generator=g)
+    dys = [torch.randn(B, C, Ho, Wo, generator=g) for _ in range(T)]
+    xr = [x.clone().requires_grad_(True) for x in xs]
+    sr = [s.clone().requires_grad_(True) for s in skips]
+    ar = alpha.clone().requires_grad_(True)
+    if up2:
+        feats = [torch.nn.functional.interpolate(x, scale_factor=2, mode="nearest") for x in xr]
+    else:
+        dh, dw = Ho - Hi, Wo - Wi
+        feats = [torch.cat([s, torch.nn.functional.pad(x, [dw // 2, dw - dw // 2, dh // 2, dh - dh // 2])], dim=1)
+                 for x, s in zip(xr, sr)]
+    stacked = torch.stack(feats)
+    yr = K.xstitch_reference_diag(ar, stacked) if mode == "reference_diag" else K.xstitch_full_mix(ar, stacked)
+    yr.backward(torch.stack(dys))
+
+    xd = [to_cl(x).requires_grad_(True) for x in xs]
+    sd = [to_cl(s).requires_grad_(True) for s in skips]
+    ad = alpha.to(dev()).requires_grad_(True)
+    ys = ops.cross_stitch_cat(sd, xd, ad, mode, up2=up2)
+    torch.autograd.backward(ys, [to_cl(d) for d in dys])
+    for t in range(T):
+        if mode == "reference_diag":
+            assert torch.equal(ys[t].cpu(), yr[t].detach()), "one multiply per element: bit-exact"
+        else:
+            assert_rel(ys[t], yr[t], what=f"y[{t}]")
+        assert_rel(xd[t].grad, xr[t].grad, what=f"dx[{t}]")
+        if Cs:
+            assert_rel(sd[t].grad, sr[t].grad, what=f"dskip[{t}]")
+    assert_rel(ad.grad, ar.grad, what="dalpha")
+    if mode == "reference_diag":
+        off = ~torch.eye(T, dtype=torch.bool)
+        assert float(ad.grad.cpu()[off].abs().max()) == 0.0

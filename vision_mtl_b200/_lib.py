@@ -20,6 +20,12 @@ SIGNATURES = {
     "vmtl_xstitch_fwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int, c_int, _P]),
     "vmtl_xstitch_bwd_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int]),
     "vmtl_xstitch_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "vmtl_xstitch_cat_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, _P]),
+    "vmtl_xstitch_cat_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                        c_int]),
+    "vmtl_xstitch_cat_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "vmtl_gate_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int, c_int]),
     "vmtl_gate_tc_supported": (c_int, [c_int, c_int]),
     "vmtl_gate_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_float, c_float, c_int, c_int, c_int64,

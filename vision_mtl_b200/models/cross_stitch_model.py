@@ -109,7 +109,16 @@ class CSNet(nn.Module):
                 plan.append(("leaf", name))
             if name in stitch_after:
                 plan.append(("stitch", name.replace(".", "_")))
-        return plan
+        # decoder sites: the tensor assembly in front of the stitch (zero-pad + cat with the skip, or nearest x2
+        # up-sampling) is folded into the stitch kernel -- the assembled tensor is never materialised
+        fused = []
+        for step in plan:
+            if step[0] == "stitch" and fused and fused[-1][0] in ("cat_skip", "upsample2"):
+                prev = fused.pop()
+                fused.append(("cat_stitch", (prev[1], step[1])) if prev[0] == "cat_skip" else ("up_stitch", step[1]))
+            else:
+                fused.append(step)
+        return fused
 
     def forward(self, x: torch.Tensor) -> dict:
         """Returns task name -> output tensor."""
@@ -128,6 +137,19 @@ class CSNet(nn.Module):
             elif op == "save_skip":
                 for s, f in zip(skips, feats):
                     s.append(f)
+            elif op == "cat_stitch":
+                idx, site = arg
+                layer = self.cross_stitch_layers[site]
+                if x.is_cuda:
+                    feats = ops.cross_stitch_cat([s[-idx - 1] for s in skips], feats, layer.weights, layer.mode)
+                else:
+                    feats = layer([concat_slightly_diff_sized_tensors(f, s[-idx - 1]) for f, s in zip(feats, skips)])
+            elif op == "up_stitch":
+                layer = self.cross_stitch_layers[arg]
+                if x.is_cuda:
+                    feats = ops.cross_stitch_cat(None, feats, layer.weights, layer.mode, up2=True)
+                else:
+                    feats = layer([F.interpolate(f, scale_factor=2, mode="nearest") for f in feats])
             elif op == "cat_skip":
                 feats = [concat_slightly_diff_sized_tensors(f, s[-arg - 1]) for f, s in zip(feats, skips)]
             else:  # upsample2

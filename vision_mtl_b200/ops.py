@@ -51,6 +51,7 @@ _KERNELS_PER_CALL = {
     "xstitch_fwd": 1, "xstitch_bwd": 2, "gate_fwd": 3, "gate_bwd": 3, "head_ce_fwd": 2,
     "head_ce_bwd": 2, "ce_logits_fwd": 2, "ce_logits_bwd": 1, "head_silog_fwd": 2,
     "head_silog_bwd": 2, "confusion_accum": 1, "depth_err_sums": 2, "seg_metrics": 1,
+    "xstitch_cat_fwd": 1, "xstitch_cat_bwd": 2,
     "bnrelu_fwd": 3, "bnrelu_bwd": 3, "bnrelu_pool_fwd": 3, "bnrelu_pool_bwd": 3,
 }
 
@@ -209,6 +210,69 @@ class CrossStitchFunction(torch.autograd.Function):
 
 def cross_stitch(xs: Sequence[torch.Tensor], alpha: torch.Tensor, mode: str = "reference_diag"):
     return list(CrossStitchFunction.apply(alpha, _XS_MODES[mode], *xs))
+
+
+class CrossStitchCatFunction(torch.autograd.Function):
+    """Cross-stitch over ``cat([skip, zero_pad(x)], 1)`` (``up2=False``) or over the nearest x2 up-sampling of
+    ``x`` (``up2=True``) per task, gathered by the kernel: the assembled tensor is never materialised."""
+
+    @staticmethod
+    def forward(ctx, alpha, mode, up2, n_skip, *tensors):
+        skips = [_nhwc(t) for t in tensors[:n_skip]]
+        xs = [_nhwc(t) for t in tensors[n_skip:]]
+        T = len(xs)
+        _need_cuda(alpha, *xs, *skips)
+        B, Cx, Hi, Wi = xs[0].shape
+        if skips:
+            _, Cs, Ho, Wo = skips[0].shape
+        else:
+            Cs, Ho, Wo = 0, (2 * Hi if up2 else Hi), (2 * Wi if up2 else Wi)
+        C = Cs + Cx
+        ys = [torch.empty((B, C, Ho, Wo), dtype=torch.float32, device=xs[0].device).contiguous(
+            memory_format=torch.channels_last) for _ in range(T)]
+        cw = 1 if alpha.dim() == 3 else 0
+        a = alpha.detach().contiguous()
+        geom = (T, B, Ho, Wo, Cs, Hi, Wi, Cx, 1 if up2 else 0, cw, mode)
+        nbytes = 4 * T * (B * Ho * Wo * (C + Cs) + B * Hi * Wi * Cx)
+        _call("xstitch_cat_fwd", nbytes, _ptr_array(skips) if skips else None, _ptr_array(xs), _ptr_array(ys), _p(a),
+              *geom, _stream())
+        ctx.geom = geom
+        ctx.n_skip = n_skip
+        ctx.save_for_backward(alpha, *skips, *xs)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        alpha, *rest = ctx.saved_tensors
+        n_skip = ctx.n_skip
+        skips, xs = rest[:n_skip], rest[n_skip:]
+        T, B, Ho, Wo, Cs, Hi, Wi, Cx, up2, cw, mode = ctx.geom
+        dev = xs[0].device
+        dys = [torch.zeros((B, Cs + Cx, Ho, Wo), device=dev).contiguous(memory_format=torch.channels_last)
+               if d is None else _nhwc(d) for d in dys]
+        a = alpha.detach().contiguous()
+        dalpha = torch.empty_like(a)
+        need = ctx.needs_input_grad[4:]
+        dskips = [torch.empty_like(t) if need[i] else None for i, t in enumerate(skips)]
+        dxs = [torch.empty_like(t) if need[n_skip + i] else None for i, t in enumerate(xs)]
+        lib = _lib.load()
+        ws = _workspace(lib.vmtl_xstitch_cat_bwd_workspace_bytes(T, B, Ho, Wo, Cs, Hi, Wi, Cx, up2, cw), dev)
+
+        def ptrs(ts):
+            return (ctypes.c_void_p * len(ts))(*[0 if t is None else t.data_ptr() for t in ts])
+
+        nbytes = 4 * T * (B * Ho * Wo * (Cs + Cx) + 2 * (B * Ho * Wo * Cs + B * Hi * Wi * Cx))  # R dy, R + W (skip, x)
+        _call("xstitch_cat_bwd", nbytes, _ptr_array(dys), _ptr_array(skips) if skips else None, _ptr_array(xs),
+              ptrs(dskips) if skips else None, ptrs(dxs), _p(a), _p(dalpha), T, B, Ho, Wo, Cs, Hi, Wi, Cx, up2, cw, mode,
+              _p(ws), ws.numel(), _stream())
+        return (dalpha, None, None, None, *dskips, *dxs)
+
+
+def cross_stitch_cat(skips: Sequence[torch.Tensor], xs: Sequence[torch.Tensor], alpha: torch.Tensor,
+                     mode: str = "reference_diag", up2: bool = False):
+    """``stitch([cat([skip_t, zero_pad(x_t)], 1) for t])`` / ``stitch([upsample2(x_t) for t])`` in one kernel."""
+    skips = list(skips or [])
+    return list(CrossStitchCatFunction.apply(alpha, _XS_MODES[mode], bool(up2), len(skips), *skips, *xs))
 
 
 # --------------------------------------------------------------------------------------
