@@ -10,6 +10,10 @@ the graph and (optionally) reads back the packed step scalars -- one launch, one
 All hand-written kernels are capture-safe: they only enqueue work on the current stream, their
 workspaces come from torch's (graph-pool aware) caching allocator and TMA descriptors are by-value
 kernel parameters over static addresses.
+
+The optimizer must be ``capturable`` and its learning rate a DEVICE tensor (``make_optimizer``):
+a Python-float lr would be baked into the graph and a later ``ReduceLROnPlateau`` step would be
+silently ignored on replay.
 """
 from __future__ import annotations
 
@@ -17,24 +21,43 @@ import typing as t
 
 import torch
 
-from .lit_module import MTLModule
+from .lit_module import STEP_KEYS, MTLModule
+
+
+def make_optimizer(params, lr: float, device) -> torch.optim.Adam:
+    """Adam as the reference builds it (training_lit.py:56), capture-safe: fused + capturable, with the
+    learning rate held in a device tensor so schedulers (which ``fill_`` it) act on graph replays."""
+    return torch.optim.Adam(params, lr=torch.tensor(float(lr), dtype=torch.float32, device=device),
+                            fused=True, capturable=True)
 
 
 class GraphedTrainStep:
     def __init__(self, module: MTLModule, optimizer: torch.optim.Optimizer, example_batch: dict,
                  warmup: int = 3, after_backward: t.Optional[t.Callable[[], None]] = None,
-                 profile: bool = False):
+                 profile: bool = False, preserve_state: bool = False, record_step_outputs: bool = False):
         """``example_batch`` fixes shapes/dtypes; ``after_backward`` (e.g. a metric all-reduce) is
         captured between backward and the optimizer step.  ``profile=True`` captures a pair of external
         CUDA events around every library call, so ``kernel_stats()`` reports per-op device time of the
-        last replay (an instrumented copy for measurement; the event nodes cost a little step time)."""
+        last replay (an instrumented copy for measurement; the event nodes cost a little step time).
+        ``preserve_state=True`` (training loops): parameters, buffers and optimizer state are restored
+        in place after the eager warm-up steps, so building the graph does not train.
+        ``record_step_outputs=True``: every replay appends its five scalars to
+        ``module.step_outputs["train"]`` like an eager ``training_step``."""
         self.module, self.optimizer = module, optimizer
+        for group in optimizer.param_groups:
+            if not group.get("capturable", False):
+                raise ValueError("GraphedTrainStep needs a capturable optimizer (graph_step.make_optimizer)")
+            if preserve_state and not isinstance(group["lr"], torch.Tensor):
+                raise ValueError("GraphedTrainStep in a training loop needs the learning rate in a device tensor "
+                                 "(graph_step.make_optimizer): a float lr is baked into the graph")
         dev = example_batch["img"].device
         self.static = {k: torch.empty_like(v) for k, v in example_batch.items()}
         for k, v in example_batch.items():
             self.static[k].copy_(v)
         self._after_backward = after_backward
+        self._record = record_step_outputs
         self._keep = {k: len(v) for k, v in module.step_outputs["train"].items()}
+        snapshot = self._snapshot() if preserve_state else None
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):  # eager warm-up on a side stream (allocator, cuDNN autotune, DDP buckets)
@@ -55,11 +78,31 @@ class GraphedTrainStep:
             with torch.cuda.graph(self.graph):
                 self._capture()
         self._trim_step_outputs()
+        if snapshot is not None:
+            self._restore(snapshot)
+
+    # -- state kept across the warm-up steps (addresses stay: the graph holds them) -------------------
+    def _state_tensors(self) -> t.List[torch.Tensor]:
+        ts = [p for p in self.module.model.parameters()] + [b for b in self.module.model.buffers()]
+        return ts
+
+    def _snapshot(self):
+        return [x.detach().clone() for x in self._state_tensors()]
+
+    def _restore(self, snapshot) -> None:
+        with torch.no_grad():
+            for x, saved in zip(self._state_tensors(), snapshot):
+                x.copy_(saved)
+            for st in self.optimizer.state.values():  # Adam moments and step counters created by the warm-up
+                for v in st.values():
+                    if isinstance(v, torch.Tensor):
+                        v.zero_()
 
     def _capture(self) -> None:
         self.loss = self._eager_step()
         self.scalars = self.module.last_step_scalars
         self.confusion = self.module.last_confusion
+        self.global_stats = getattr(self.module, "last_global_stats", None)
 
     def kernel_stats(self) -> dict:
         """name -> {calls, ms, bytes, gbps} of the last replay (``profile=True``; synchronise first)."""
@@ -92,4 +135,11 @@ class GraphedTrainStep:
         self.graph.replay()
         self.module.last_step_scalars = self.scalars
         self.module.last_confusion = self.confusion
+        if self.global_stats is not None:
+            self.module.last_global_stats = self.global_stats
+        if self._record:  # the static scalars are overwritten by the next replay: keep this step's copy
+            vals = self.scalars.clone()
+            rec = self.module.step_outputs["train"]
+            for i, k in enumerate(STEP_KEYS):
+                rec[k].append(vals[i])
         return self.loss
