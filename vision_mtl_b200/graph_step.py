@@ -45,7 +45,9 @@ class GraphedTrainStep:
         ``module.step_outputs["train"]`` like an eager ``training_step``."""
         self.module, self.optimizer = module, optimizer
         for group in optimizer.param_groups:
-            if not group.get("capturable", False):
+            # optimizers with a host-side step counter (Adam & co.) expose `capturable`; SGD-like ones have no
+            # such state and capture as they are
+            if "capturable" in optimizer.defaults and not group.get("capturable", False):
                 raise ValueError("GraphedTrainStep needs a capturable optimizer (graph_step.make_optimizer)")
             if preserve_state and not isinstance(group["lr"], torch.Tensor):
                 raise ValueError("GraphedTrainStep in a training loop needs the learning rate in a device tensor "
