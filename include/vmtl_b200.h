@@ -234,6 +234,68 @@ int vmtl_head_silog_bwd(const float* feat, const float* w, const float* b, const
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Global-batch statistics for data-parallel training.
+ * The reference is single-process: BatchNorm (mtan_model.py:72, model_utils.py:66-72) and SILog
+ * (losses.py:32-36) reduce over the whole batch.  With the batch sharded over GPUs, every op above that has a
+ * batch reduction in its middle is also exported as its two halves, so the caller can all-reduce (SUM, NCCL,
+ * same stream) the fp64 moments between them; an N-GPU step then equals the single-GPU step on the
+ * concatenated batch.  M_global = rows of all replicas.  Parameter gradients (dgamma, dbeta, dW, dbias) stay
+ * this replica's contributions: the data-parallel wrapper averages them like every other gradient.
+ *
+ *   moments (double [2][C]):
+ *     forward   (sum x, sum x^2)            backward  (sum g, sum g*xhat)   [= this replica's dbeta, dgamma]
+ *
+ * BatchNorm (+ReLU, +2x2 max-pool; pool != 0 needs y / the pooled dy as in vmtl_bnrelu_pool_*): x is [B,H,W,C].
+ * ---------------------------------------------------------------------------------- */
+int vmtl_bn_moments(const float* x, int64_t M, int C, double* moments, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* finalize from the all-reduced moments (running statistics updated with the global mean / unbiased variance)
+ * + apply pass; y == NULL: coefficients only (folded hidden layer of the gate) */
+int vmtl_bnrelu_fwd_global(const float* x, const float* gamma, const float* beta, float* running_mean,
+                           float* running_var, float momentum, float eps, int relu, int pool, int B, int H, int W,
+                           int C, const double* moments, int64_t M_global, float* y, float* save_mean,
+                           float* save_invstd, float* coef, void* workspace, size_t workspace_bytes, void* stream);
+
+int vmtl_bnrelu_bwd_moments(const float* dy, const float* x, const float* coef, const float* save_mean,
+                            const float* save_invstd, int relu, int pool, int B, int H, int W, int C,
+                            double* moments, void* workspace, size_t workspace_bytes, void* stream);
+
+int vmtl_bnrelu_bwd_global(const float* dy, const float* x, const float* coef, const float* save_mean,
+                           const float* save_invstd, int relu, int pool, int B, int H, int W, int C,
+                           const double* moments, int64_t M_global, float* dx, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* Gate forward, first half: contraction -> save_z, moments (sum z, sum z^2) [2][N]. */
+int vmtl_gate_fwd_moments(const float* h, const float* h_coef, const float* W, const float* bias, int precision,
+                          int64_t M, int K, int N, float* save_z, double* moments, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* second half: statistics from the all-reduced moments, y = s * sigmoid(BN(z)) */
+int vmtl_gate_fwd_global(const float* s, const float* z, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, float momentum, float eps, int precision, int64_t M, int K, int N,
+                         const double* moments, int64_t M_global, float* y, float* save_mean, float* save_invstd,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gate backward, first half: ds, this replica's sums -> moments (sum du, sum du*zhat) [2][N]; the workspace keeps
+ * the dW pieces and must reach vmtl_gate_bwd_global untouched. */
+int vmtl_gate_bwd_moments(const float* dy, const float* h, const float* h_coef, const float* s, const float* z,
+                          const float* W, const float* gamma, const float* beta, const float* save_mean,
+                          const float* save_invstd, int precision, int64_t M, int K, int N, float* ds,
+                          double* moments, void* workspace, size_t workspace_bytes, void* stream);
+
+int vmtl_gate_bwd_global(const float* dy, const float* h, const float* h_coef, const float* s, const float* z,
+                         const float* W, const float* gamma, const float* beta, const float* save_mean,
+                         const float* save_invstd, int precision, int64_t M, int K, int N, const double* moments,
+                         int64_t M_global, float* dh, float* dW, float* dbias, float* dgamma, float* dbeta,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* SILog: `out` of vmtl_head_silog_fwd with out[0..4] and out[7] all-reduced -> out[5] (mean g), out[6] (D) and
+ * the three scalars of the GLOBAL batch; feed that `out` to vmtl_head_silog_bwd with gscale multiplied by the
+ * number of replicas (their gradients are averaged afterwards). */
+int vmtl_silog_finalize(double* out, float* scalars, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Validation reductions (torchmetrics call sites lit_module.py:106-118).
  * ---------------------------------------------------------------------------------- */
 /* conf[target, pred] += 1 for every pixel with 0 <= target,pred < C and target != ignore_index.

@@ -54,6 +54,22 @@ SIGNATURES = {
     "vmtl_confusion_accum": (c_int, [_P, c_int, _P, c_int64, c_int, c_int64, _P, _P]),
     "vmtl_depth_err_sums": (c_int, [_P, _P, c_int64, c_float, _P, _P, c_size_t, _P]),
     "vmtl_seg_metrics": (c_int, [_P, c_int, _P, _P]),
+    # global-batch statistics: the two halves of every op with a batch reduction in its middle
+    "vmtl_bn_moments": (c_int, [_P, c_int64, c_int, _P, _P, c_size_t, _P]),
+    "vmtl_bnrelu_fwd_global": (c_int, [_P, _P, _P, _P, _P, c_float, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       _P, c_int64, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "vmtl_bnrelu_bwd_moments": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t,
+                                        _P]),
+    "vmtl_bnrelu_bwd_global": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P,
+                                       _P, c_size_t, _P]),
+    "vmtl_gate_fwd_moments": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "vmtl_gate_fwd_global": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_float, c_int, c_int64, c_int, c_int, _P,
+                                     c_int64, _P, _P, _P, _P, c_size_t, _P]),
+    "vmtl_gate_bwd_moments": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, _P, _P,
+                                      _P, c_size_t, _P]),
+    "vmtl_gate_bwd_global": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, _P,
+                                     c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "vmtl_silog_finalize": (c_int, [_P, _P, _P]),
 }
 
 

@@ -103,12 +103,17 @@ __global__ void bn_fwd_finalize(const float* __restrict__ partial, int nparts, i
                                 float momentum, int training, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float* __restrict__ running_mean,
                                 float* __restrict__ running_var, float* __restrict__ save_mean,
-                                float* __restrict__ save_invstd, float* __restrict__ coef /* [2][C] */) {
+                                float* __restrict__ save_invstd, float* __restrict__ coef /* [2][C] */,
+                                const double* __restrict__ gmoments /* NULL, or global [2][C] over M rows */) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double s = 0.0, q = 0.0;
-  if (training)  // block-uniform branch: the reduction synchronises
+  if (training && !gmoments)  // block-uniform branch: the reduction synchronises
     block_colsum2(partial, nparts, 2 * (int64_t)C, c < C ? c : 0, C + (c < C ? c : 0), c < C, &s, &q);
   if (threadIdx.x >= 32 || c >= C) return;
+  if (training && gmoments) {
+    s = gmoments[c];
+    q = gmoments[C + c];
+  }
   double mean, var;
   if (training) {
     mean = s / (double)M;
@@ -278,17 +283,35 @@ __global__ void __launch_bounds__(kBnThreads)
   bn_block_reduce<2>(acc, m, C4, partial + (int64_t)blockIdx.x * 8 * C4);
 }
 
-// partial [nparts][2][C] -> dbeta, dgamma, c1 = dbeta/Mnorm, c2 = dgamma/Mnorm (0 in eval mode)
+// partial [nparts][2][C] -> dbeta, dgamma, c1 = dbeta/Mnorm, c2 = dgamma/Mnorm (0 in eval mode).
+// gmoments != NULL (global-batch statistics): the two sums come from there (all ranks, Mnorm = global rows) and
+// only c1 / c2 are produced -- dbeta / dgamma are the caller's LOCAL moments.
 __global__ void bn_bwd_finalize(const float* __restrict__ partial, int nparts, int64_t Mnorm, int C, int training,
-                                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c12) {
+                                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c12,
+                                const double* __restrict__ gmoments) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  double sb, sg;
-  block_colsum2(partial, nparts, 2 * (int64_t)C, c < C ? c : 0, C + (c < C ? c : 0), c < C, &sb, &sg);
+  double sb = 0.0, sg = 0.0;
+  if (!gmoments) block_colsum2(partial, nparts, 2 * (int64_t)C, c < C ? c : 0, C + (c < C ? c : 0), c < C, &sb, &sg);
   if (threadIdx.x >= 32 || c >= C) return;
-  dbeta[c] = (float)sb;
-  dgamma[c] = (float)sg;
+  if (gmoments) {
+    sb = gmoments[c];
+    sg = gmoments[C + c];
+  } else {
+    dbeta[c] = (float)sb;
+    dgamma[c] = (float)sg;
+  }
   c12[c] = training ? (float)(sb / (double)Mnorm) : 0.f;
   c12[C + c] = training ? (float)(sg / (double)Mnorm) : 0.f;
+}
+
+// partial [nparts][2][C] -> fp64 moments [2][C] (fixed-order second stage), what a data-parallel caller all-reduces
+__global__ void bn_moments_finalize(const float* __restrict__ partial, int nparts, int C, double* __restrict__ moments) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  double a, b;
+  block_colsum2(partial, nparts, 2 * (int64_t)C, c < C ? c : 0, C + (c < C ? c : 0), c < C, &a, &b);
+  if (threadIdx.x >= 32 || c >= C) return;
+  moments[c] = a;
+  moments[C + c] = b;
 }
 
 template <bool RELU>
@@ -380,12 +403,29 @@ extern "C" size_t vmtl_bnrelu_workspace_bytes(int64_t M, int C) {
   return ((size_t)bn_max_blocks() * 2 * C + 2 * (size_t)C) * sizeof(float) + 256;
 }
 
+// phase 0: the whole op on local statistics.  Global-batch statistics split it around the caller's
+// all-reduce: phase 1 = statistics pass -> fp64 `moments` [2][C]; phase 2 = finalize from the (all-reduced) moments
+// over `Mstat` rows + apply pass.
 static int bnrelu_fwd_impl(const float* x, const float* gamma, const float* beta, float* running_mean,
                            float* running_var, float momentum, float eps, int training, int relu, int64_t M, int C,
                            int B, int H, int W, int pool, float* y, float* save_mean, float* save_invstd, float* coef,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+                           void* workspace, size_t workspace_bytes, void* stream, int phase = 0,
+                           double* moments = nullptr, int64_t Mstat = 0) {
   int rc = bn_check(M, C);
   if (rc != VMTL_OK) return rc;
+  if (phase == 1) {
+    if (!x || !moments || !workspace) return VMTL_EINVAL;
+    if (!aligned16(x) || !aligned16(workspace)) return VMTL_EALIGN;
+    if (workspace_bytes < vmtl_bnrelu_workspace_bytes(M, C)) return VMTL_EWORKSPACE;
+    cudaStream_t st1 = static_cast<cudaStream_t>(stream);
+    float* part = static_cast<float*>(workspace);
+    const int np = bn_grid(M, C, blocks_per_sm(bn_stats_kernel, kBnThreads, 0, 8));
+    bn_stats_kernel<<<np, kBnThreads, 0, st1>>>(x, M, C / 4, part);
+    if ((rc = launch_status()) != VMTL_OK) return rc;
+    bn_moments_finalize<<<(C + 31) / 32, kFinThreads, 0, st1>>>(part, np, C, moments);
+    return launch_status();
+  }
+  if (phase == 2 && (!moments || Mstat < 1 || !training)) return VMTL_EINVAL;
   if (!x || !gamma || !beta || !save_mean || !save_invstd || !coef || !workspace) return VMTL_EINVAL;
   if (!training && (!running_mean || !running_var)) return VMTL_EINVAL;
   if (!aligned16(x) || (y && !aligned16(y)) || !aligned16(coef) || !aligned16(workspace)) return VMTL_EALIGN;
@@ -394,13 +434,14 @@ static int bnrelu_fwd_impl(const float* x, const float* gamma, const float* beta
   const int C4 = C / 4;
   float* partial = static_cast<float*>(workspace);
   int nparts = 0;
-  if (training) {
+  if (training && phase == 0) {
     nparts = bn_grid(M, C, blocks_per_sm(bn_stats_kernel, kBnThreads, 0, 8));
     bn_stats_kernel<<<nparts, kBnThreads, 0, st>>>(x, M, C4, partial);
     if ((rc = launch_status()) != VMTL_OK) return rc;
   }
-  bn_fwd_finalize<<<(C + 31) / 32, kFinThreads, 0, st>>>(partial, nparts, M, C, eps, momentum, training, gamma, beta,
-                                                         running_mean, running_var, save_mean, save_invstd, coef);
+  bn_fwd_finalize<<<(C + 31) / 32, kFinThreads, 0, st>>>(partial, nparts, phase == 2 ? Mstat : M, C, eps, momentum,
+                                                         training, gamma, beta, running_mean, running_var, save_mean,
+                                                         save_invstd, coef, phase == 2 ? moments : nullptr);
   if ((rc = launch_status()) != VMTL_OK) return rc;
   if (!y) return VMTL_OK;
   if (pool) {
@@ -442,13 +483,18 @@ extern "C" int vmtl_bnrelu_pool_fwd(const float* x, const float* gamma, const fl
                          C, B, H, W, 1, y, save_mean, save_invstd, coef, workspace, workspace_bytes, stream);
 }
 
+// phase 0: whole op; phase 1: statistics pass -> LOCAL fp64 moments [2][C] = (sum g, sum g xhat) (also the
+// caller's dbeta / dgamma); phase 2: c1 / c2 from the all-reduced moments over `Mstat` rows + apply pass.
 static int bnrelu_bwd_impl(const float* dy, const float* x, const float* coef, const float* save_mean,
                            const float* save_invstd, int training, int relu, int64_t M, int C, int B, int H, int W,
                            int pool, float* dx, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+                           void* stream, int phase = 0, double* moments = nullptr, int64_t Mstat = 0) {
   int rc = bn_check(M, C);
   if (rc != VMTL_OK) return rc;
-  if (!dy || !x || !coef || !save_mean || !save_invstd || !dgamma || !dbeta || !workspace) return VMTL_EINVAL;
+  if (phase != 0 && !moments) return VMTL_EINVAL;
+  if (phase == 2 && (!dx || Mstat < 1)) return VMTL_EINVAL;
+  if (!dy || !x || !coef || !save_mean || !save_invstd || (phase == 0 && (!dgamma || !dbeta)) || !workspace)
+    return VMTL_EINVAL;
   if (!aligned16(dy) || !aligned16(x) || (dx && !aligned16(dx)) || !aligned16(coef) || !aligned16(workspace))
     return VMTL_EALIGN;
   if (workspace_bytes < vmtl_bnrelu_workspace_bytes(M, C)) return VMTL_EWORKSPACE;
@@ -457,21 +503,30 @@ static int bnrelu_bwd_impl(const float* dy, const float* x, const float* coef, c
   float* partial = static_cast<float*>(workspace);
   float* c12 = partial + (size_t)bn_max_blocks() * 2 * C;
   int nparts;
+  (void)nparts;
 #define VMTL_BN_LAUNCH(KERN, ROWS, ...)                                                    \
   do {                                                                                     \
     nparts = bn_grid(ROWS, C, blocks_per_sm(KERN, kBnThreads, 0, 8));                      \
     KERN<<<nparts, kBnThreads, 0, st>>>(__VA_ARGS__);                                      \
   } while (0)
-  if (pool) {
-    const int64_t Mo = (int64_t)B * (H / 2) * (W / 2);
-    if (relu) VMTL_BN_LAUNCH(bn_pool_bwd_stats_kernel<true>, Mo, dy, x, B, H, W, C4, coef, save_mean, save_invstd, partial);
-    else VMTL_BN_LAUNCH(bn_pool_bwd_stats_kernel<false>, Mo, dy, x, B, H, W, C4, coef, save_mean, save_invstd, partial);
-  } else {
-    if (relu) VMTL_BN_LAUNCH(bn_bwd_stats_kernel<true>, M, dy, x, M, C4, coef, save_mean, save_invstd, partial);
-    else VMTL_BN_LAUNCH(bn_bwd_stats_kernel<false>, M, dy, x, M, C4, coef, save_mean, save_invstd, partial);
+  nparts = 0;
+  if (phase != 2) {
+    if (pool) {
+      const int64_t Mo = (int64_t)B * (H / 2) * (W / 2);
+      if (relu) VMTL_BN_LAUNCH(bn_pool_bwd_stats_kernel<true>, Mo, dy, x, B, H, W, C4, coef, save_mean, save_invstd, partial);
+      else VMTL_BN_LAUNCH(bn_pool_bwd_stats_kernel<false>, Mo, dy, x, B, H, W, C4, coef, save_mean, save_invstd, partial);
+    } else {
+      if (relu) VMTL_BN_LAUNCH(bn_bwd_stats_kernel<true>, M, dy, x, M, C4, coef, save_mean, save_invstd, partial);
+      else VMTL_BN_LAUNCH(bn_bwd_stats_kernel<false>, M, dy, x, M, C4, coef, save_mean, save_invstd, partial);
+    }
+    if ((rc = launch_status()) != VMTL_OK) return rc;
   }
-  if ((rc = launch_status()) != VMTL_OK) return rc;
-  bn_bwd_finalize<<<(C + 31) / 32, kFinThreads, 0, st>>>(partial, nparts, M, C, training, dgamma, dbeta, c12);
+  if (phase == 1) {
+    bn_moments_finalize<<<(C + 31) / 32, kFinThreads, 0, st>>>(partial, nparts, C, moments);
+    return launch_status();
+  }
+  bn_bwd_finalize<<<(C + 31) / 32, kFinThreads, 0, st>>>(partial, nparts, phase == 2 ? Mstat : M, C, training, dgamma,
+                                                         dbeta, c12, phase == 2 ? moments : nullptr);
   if ((rc = launch_status()) != VMTL_OK) return rc;
   if (!dx) return VMTL_OK;
   int unused;
@@ -502,4 +557,39 @@ extern "C" int vmtl_bnrelu_pool_bwd(const float* dy, const float* x, const float
   if (B < 1 || H < 2 || W < 2) return VMTL_EINVAL;
   return bnrelu_bwd_impl(dy, x, coef, save_mean, save_invstd, training, relu, (int64_t)B * H * W, C, B, H, W, 1, dx,
                          dgamma, dbeta, workspace, workspace_bytes, stream);
+}
+
+// ---- global-batch statistics: the two halves of each op around the caller's all-reduce -------------
+extern "C" int vmtl_bn_moments(const float* x, int64_t M, int C, double* moments, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  return bnrelu_fwd_impl(x, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, 1, 0, M, C, 0, 0, 0, 0, nullptr, nullptr,
+                         nullptr, nullptr, workspace, workspace_bytes, stream, 1, moments, 0);
+}
+
+extern "C" int vmtl_bnrelu_fwd_global(const float* x, const float* gamma, const float* beta, float* running_mean,
+                                      float* running_var, float momentum, float eps, int relu, int pool, int B, int H,
+                                      int W, int C, const double* moments, int64_t M_global, float* y,
+                                      float* save_mean, float* save_invstd, float* coef, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  if (B < 1 || H < 1 || W < 1 || (pool && (H < 2 || W < 2 || !y))) return VMTL_EINVAL;
+  return bnrelu_fwd_impl(x, gamma, beta, running_mean, running_var, momentum, eps, 1, relu, (int64_t)B * H * W, C, B, H,
+                         W, pool, y, save_mean, save_invstd, coef, workspace, workspace_bytes, stream, 2,
+                         const_cast<double*>(moments), M_global);
+}
+
+extern "C" int vmtl_bnrelu_bwd_moments(const float* dy, const float* x, const float* coef, const float* save_mean,
+                                       const float* save_invstd, int relu, int pool, int B, int H, int W, int C,
+                                       double* moments, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 1 || H < 1 || W < 1 || (pool && (H < 2 || W < 2))) return VMTL_EINVAL;
+  return bnrelu_bwd_impl(dy, x, coef, save_mean, save_invstd, 1, relu, (int64_t)B * H * W, C, B, H, W, pool, nullptr,
+                         nullptr, nullptr, workspace, workspace_bytes, stream, 1, moments, 0);
+}
+
+extern "C" int vmtl_bnrelu_bwd_global(const float* dy, const float* x, const float* coef, const float* save_mean,
+                                      const float* save_invstd, int relu, int pool, int B, int H, int W, int C,
+                                      const double* moments, int64_t M_global, float* dx, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  if (B < 1 || H < 1 || W < 1 || (pool && (H < 2 || W < 2))) return VMTL_EINVAL;
+  return bnrelu_bwd_impl(dy, x, coef, save_mean, save_invstd, 1, relu, (int64_t)B * H * W, C, B, H, W, pool, dx, nullptr,
+                         nullptr, workspace, workspace_bytes, stream, 2, const_cast<double*>(moments), M_global);
 }

@@ -100,13 +100,18 @@ __global__ void gate_fwd_stats_finalize(const float* __restrict__ partial, int n
                                         float* __restrict__ running_mean, float* __restrict__ running_var,
                                         float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                         float* __restrict__ coefA, float* __restrict__ coefB,
-                                        float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+                                        float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                        const double* __restrict__ gmoments /* NULL, or global [2][N] over M rows */) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double s = 0.0, q = 0.0;
-  if (training) {  // block-uniform branch: the reduction synchronises
+  if (training && !gmoments) {  // block-uniform branch: the reduction synchronises
     block_colsum2(partial, nparts, 2 * (int64_t)N, c < N ? c : 0, N + (c < N ? c : 0), c < N, &s, &q);
   }
   if (threadIdx.x >= 32 || c >= N) return;
+  if (training && gmoments) {
+    s = gmoments[c];
+    q = gmoments[N + c];
+  }
   double mean, var;
   if (training) {
     mean = s / (double)M;
@@ -129,6 +134,16 @@ __global__ void gate_fwd_stats_finalize(const float* __restrict__ partial, int n
   coefB[c] = (float)((double)beta[c] - mean * a);
   if (save_mean) save_mean[c] = (float)mean;
   if (save_invstd) save_invstd[c] = (float)inv;
+}
+
+// partial [nparts][2][N] -> fp64 moments [2][N]: what a data-parallel caller all-reduces between the two phases
+__global__ void gate_moments_finalize(const float* __restrict__ partial, int nparts, int N, double* __restrict__ moments) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  double a, b;
+  block_colsum2(partial, nparts, 2 * (int64_t)N, c < N ? c : 0, N + (c < N ? c : 0), c < N, &a, &b);
+  if (threadIdx.x >= 32 || c >= N) return;
+  moments[c] = a;
+  moments[N + c] = b;
 }
 
 // ---- forward phase 2: y = s * sigmoid(A*z + B) ------------------------------------------
@@ -200,13 +215,20 @@ __global__ void gate_bwd_stats_finalize(const float* __restrict__ partial, int n
                                         const float* __restrict__ beta, const float* __restrict__ mean,
                                         const float* __restrict__ invstd, float* __restrict__ coefA,
                                         float* __restrict__ coefB, float* __restrict__ mean_out,
-                                        float* __restrict__ invstd_out) {
+                                        float* __restrict__ invstd_out,
+                                        const double* __restrict__ gmoments /* NULL, or global [2][N] */,
+                                        int64_t Mstat) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double sb, sg;
   block_colsum2(partial, nparts, 2 * (int64_t)N, c < N ? c : 0, N + (c < N ? c : 0), c < N, &sb, &sg);
   if (threadIdx.x >= 32 || c >= N) return;
-  dbeta[c] = (float)sb;
+  dbeta[c] = (float)sb;  // parameter gradients stay LOCAL sums (the data-parallel wrapper averages them)
   dgamma[c] = (float)sg;
+  if (gmoments) {
+    sb = gmoments[c];
+    sg = gmoments[N + c];
+    M = Mstat;
+  }
   c1[c] = training ? (float)(sb / (double)M) : 0.f;
   c2[c] = training ? (float)(sg / (double)M) : 0.f;
   const float a = gamma[c] * invstd[c];
@@ -234,7 +256,9 @@ __global__ void __launch_bounds__(kFinThreads)
                          const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ dW,
                          float* __restrict__ dbias, float* __restrict__ dgamma, float* __restrict__ dbeta,
                          float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ coefA,
-                         float* __restrict__ coefB, float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+                         float* __restrict__ coefB, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                         const double* __restrict__ gmoments /* NULL, or global (sum du, sum du zhat) [2][N] */,
+                         int64_t Mstat /* rows behind gmoments */) {
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const int Nc = N / nch, per_chunk = nparts / nch;
   const int kslabs = K / 32;
@@ -290,7 +314,11 @@ __global__ void __launch_bounds__(kFinThreads)
       sdu += s_acc[3][g * kFinRows + r][0];
       sdz += s_acc[3][g * kFinRows + r][1];
     }
-    const double k1 = training ? sdu / (double)M : 0.0, k2 = training ? sdz / (double)M : 0.0;
+    double k1 = training ? sdu / (double)M : 0.0, k2 = training ? sdz / (double)M : 0.0;
+    if (gmoments && training) {  // normalisation terms of the GLOBAL batch; P1, P2, hsum stay this replica's
+      k1 = gmoments[n] / (double)Mstat;
+      k2 = gmoments[N + n] / (double)Mstat;
+    }
     const double a = (double)gamma[n] * (double)invstd[n];
     dW[(int64_t)n * K + k] = (float)(a * (p1 - k1 * hs - k2 * p2));
     return;
@@ -319,10 +347,14 @@ __global__ void __launch_bounds__(kFinThreads)
     sdz += s_acc[1][g][lx];
     sz += s_acc[2][g][lx];
   }
-  const double k1 = training ? sdu / (double)M : 0.0, k2 = training ? sdz / (double)M : 0.0;
-  const double a = (double)gamma[col] * (double)invstd[col];
-  dbeta[col] = (float)sdu;
+  dbeta[col] = (float)sdu;  // parameter gradients stay LOCAL sums
   dgamma[col] = (float)sdz;
+  double k1 = training ? sdu / (double)M : 0.0, k2 = training ? sdz / (double)M : 0.0;
+  if (gmoments && training) {  // normalisation terms of the GLOBAL batch
+    k1 = gmoments[col] / (double)Mstat;
+    k2 = gmoments[N + col] / (double)Mstat;
+  }
+  const double a = (double)gamma[col] * (double)invstd[col];
   dbias[col] = (float)(a * (sdu - (double)M * k1 - k2 * sz));
   c1[col] = (float)k1;
   c2[col] = (float)k2;
@@ -331,6 +363,38 @@ __global__ void __launch_bounds__(kFinThreads)
   coefB[col] = beta[col] - mean[col] * af;
   mean_out[col] = mean[col];
   invstd_out[col] = invstd[col];
+}
+
+// col_partial of the tensor-core pass 1 ([b][3][Nc], CTA b owns chunk b % nch) -> fp64 moments [2][N] = (sum du,
+// sum du zhat) of this replica
+__global__ void gate_bwd_tc_moments(const float* __restrict__ col_partial, int nparts, int nch, int N,
+                                    double* __restrict__ moments) {
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int Nc = N / nch, per_chunk = nparts / nch;
+  const int col = (int)blockIdx.x * 32 + lx;
+  const bool ok = col < N;
+  const int c = (ok ? col : 0) / Nc, nl = (ok ? col : 0) % Nc;
+  const float* cp = col_partial + (int64_t)c * 3 * Nc;
+  __shared__ double s_acc[2][32][33];
+  double a1 = 0.0, a2 = 0.0;
+  if (ok)
+    for (int p = ly; p < per_chunk; p += 32) {
+      const float* row = cp + (int64_t)p * nch * 3 * Nc;
+      a1 += (double)row[nl];
+      a2 += (double)row[Nc + nl];
+    }
+  s_acc[0][ly][lx] = a1;
+  s_acc[1][ly][lx] = a2;
+  __syncthreads();
+  if (ly != 0 || !ok) return;
+  double sdu = 0.0, sdz = 0.0;
+#pragma unroll
+  for (int g = 0; g < 32; ++g) {
+    sdu += s_acc[0][g][lx];
+    sdz += s_acc[1][g][lx];
+  }
+  moments[col] = sdu;
+  moments[N + col] = sdz;
 }
 
 // ---- backward: materialise dz (fp32 FFMA path) + db partials ------------------------------
@@ -465,19 +529,26 @@ extern "C" size_t vmtl_gate_workspace_bytes(int64_t M, int K, int N, int precisi
 
 extern "C" int vmtl_gate_tc_supported(int K, int N) { return gate_tc_supported(K, N) ? 1 : 0; }
 
-extern "C" int vmtl_gate_fwd(const float* h, const float* h_coef, const float* s, const float* W, const float* bias,
-                             const float* gamma, const float* beta, float* running_mean,
-                             float* running_var, float momentum, float eps, int training, int precision,
-                             int64_t M, int K, int N, float* y, float* save_z, float* save_mean,
-                             float* save_invstd, void* workspace, size_t workspace_bytes, void* stream) {
+// phase 0: the whole forward on local statistics.  Global-batch statistics: phase 1 = contraction
+// (z, per-CTA partials) -> fp64 `moments` [2][N] = (sum z, sum z^2); phase 2 = finalize from the all-reduced moments
+// over `Mstat` rows + the gate pass over (z, s).
+static int gate_fwd_impl(const float* h, const float* h_coef, const float* s, const float* W, const float* bias,
+                         const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, float momentum, float eps, int training, int precision,
+                         int64_t M, int K, int N, float* y, float* save_z, float* save_mean,
+                         float* save_invstd, void* workspace, size_t workspace_bytes, void* stream, int phase,
+                         double* moments, int64_t Mstat) {
   int rc = gate_check(M, K, N, precision);
   if (rc != VMTL_OK) return rc;
-  if (!h || !s || !W || !bias || !gamma || !beta || !y || !workspace) return VMTL_EINVAL;
+  if (phase != 0 && (!training || !moments)) return VMTL_EINVAL;
+  if (phase == 2 && Mstat < 1) return VMTL_EINVAL;
+  if ((phase != 2 && (!h || !W || !bias)) || (phase != 1 && (!s || !gamma || !beta || !y)) || !workspace)
+    return VMTL_EINVAL;
   if (h_coef && (precision == VMTL_GATE_FP32_FFMA || !gate_tc_supported(K, N))) return VMTL_EUNSUPPORTED;
   if (training && !save_z) return VMTL_EINVAL;
   if (!training && (!running_mean || !running_var)) return VMTL_EINVAL;
-  if (!aligned16(h) || !aligned16(s) || !aligned16(W) || !aligned16(y) || !aligned16(workspace) ||
-      (save_z && !aligned16(save_z)))
+  if ((h && !aligned16(h)) || (s && !aligned16(s)) || (W && !aligned16(W)) || (y && !aligned16(y)) ||
+      !aligned16(workspace) || (save_z && !aligned16(save_z)))
     return VMTL_EALIGN;
   GateWs ws;
   const size_t need = gate_ws_floats(M, K, N, precision, 0, &ws, static_cast<float*>(workspace));
@@ -490,7 +561,7 @@ extern "C" int vmtl_gate_fwd(const float* h, const float* h_coef, const float* s
     gate_fwd_stats_finalize<<<(N + 31) / 32, kFinThreads, 0, st>>>(nullptr, 0, M, N, eps, momentum, 0, gamma,
                                                              beta, running_mean, running_var, ws.mean,
                                                              ws.invstd, ws.coefA, ws.coefB, save_mean,
-                                                             save_invstd);
+                                                             save_invstd, nullptr);
     if ((rc = launch_status()) != VMTL_OK) return rc;
     const bool tc = precision != VMTL_GATE_FP32_FFMA && gate_tc_supported(K, N);
     if (tc && !save_z)  // inference: single fused pass, z never stored
@@ -509,36 +580,75 @@ extern "C" int vmtl_gate_fwd(const float* h, const float* h_coef, const float* s
   }
 
   int nparts = 0;
-  if (precision != VMTL_GATE_FP32_FFMA && gate_tc_supported(K, N)) {
-    rc = gate_tc_fwd_gemm(h, h_coef, W, bias, M, K, N, split3, save_z, ws.partial, ws.partial_rows, &nparts, st);
-    if (rc != VMTL_OK) return rc;
-  } else {
-    rc = sgemm64(h, W, save_z, bias, M, N, K, K, 1, 1, K, N, 1, 0, st);
-    if (rc != VMTL_OK) return rc;
-    nparts = ew_grid(M, N);
-    gate_colstats_kernel<<<nparts, kEwThreads, 0, st>>>(save_z, M, C4, ws.partial);
-    if ((rc = launch_status()) != VMTL_OK) return rc;
+  if (phase != 2) {
+    if (precision != VMTL_GATE_FP32_FFMA && gate_tc_supported(K, N)) {
+      rc = gate_tc_fwd_gemm(h, h_coef, W, bias, M, K, N, split3, save_z, ws.partial, ws.partial_rows, &nparts, st);
+      if (rc != VMTL_OK) return rc;
+    } else {
+      rc = sgemm64(h, W, save_z, bias, M, N, K, K, 1, 1, K, N, 1, 0, st);
+      if (rc != VMTL_OK) return rc;
+      nparts = ew_grid(M, N);
+      gate_colstats_kernel<<<nparts, kEwThreads, 0, st>>>(save_z, M, C4, ws.partial);
+      if ((rc = launch_status()) != VMTL_OK) return rc;
+    }
   }
-  gate_fwd_stats_finalize<<<(N + 31) / 32, kFinThreads, 0, st>>>(ws.partial, nparts, M, N, eps, momentum, 1,
-                                                           gamma, beta, running_mean, running_var,
+  if (phase == 1) {
+    gate_moments_finalize<<<(N + 31) / 32, kFinThreads, 0, st>>>(ws.partial, nparts, N, moments);
+    return launch_status();
+  }
+  gate_fwd_stats_finalize<<<(N + 31) / 32, kFinThreads, 0, st>>>(ws.partial, nparts, phase == 2 ? Mstat : M, N, eps,
+                                                           momentum, 1, gamma, beta, running_mean, running_var,
                                                            ws.mean, ws.invstd, ws.coefA, ws.coefB,
-                                                           save_mean, save_invstd);
+                                                           save_mean, save_invstd, phase == 2 ? moments : nullptr);
   if ((rc = launch_status()) != VMTL_OK) return rc;
   gate_apply_kernel<<<ew_grid(M, N, blocks_per_sm(gate_apply_kernel, kEwThreads, 0, 8)), kEwThreads, 0, st>>>(save_z, s, M, C4, ws.coefA, ws.coefB, y);
   return launch_status();
 }
 
+extern "C" int vmtl_gate_fwd(const float* h, const float* h_coef, const float* s, const float* W, const float* bias,
+                             const float* gamma, const float* beta, float* running_mean,
+                             float* running_var, float momentum, float eps, int training, int precision,
+                             int64_t M, int K, int N, float* y, float* save_z, float* save_mean,
+                             float* save_invstd, void* workspace, size_t workspace_bytes, void* stream) {
+  return gate_fwd_impl(h, h_coef, s, W, bias, gamma, beta, running_mean, running_var, momentum, eps, training,
+                       precision, M, K, N, y, save_z, save_mean, save_invstd, workspace, workspace_bytes, stream, 0,
+                       nullptr, 0);
+}
+
+extern "C" int vmtl_gate_fwd_moments(const float* h, const float* h_coef, const float* W, const float* bias,
+                                     int precision, int64_t M, int K, int N, float* save_z, double* moments,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  return gate_fwd_impl(h, h_coef, nullptr, W, bias, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, 1, precision, M, K, N,
+                       nullptr, save_z, nullptr, nullptr, workspace, workspace_bytes, stream, 1, moments, 0);
+}
+
+extern "C" int vmtl_gate_fwd_global(const float* s, const float* z, const float* gamma, const float* beta,
+                                    float* running_mean, float* running_var, float momentum, float eps,
+                                    int precision, int64_t M, int K, int N, const double* moments, int64_t M_global,
+                                    float* y, float* save_mean, float* save_invstd, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  return gate_fwd_impl(nullptr, nullptr, s, nullptr, nullptr, gamma, beta, running_mean, running_var, momentum, eps, 1,
+                       precision, M, K, N, y, const_cast<float*>(z), save_mean, save_invstd, workspace,
+                       workspace_bytes, stream, 2, const_cast<double*>(moments), M_global);
+}
+
 // coefA/B from saved statistics (backward re-derives them instead of trusting workspace reuse)
-extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* h_coef, const float* s, const float* z,
-                             const float* W, const float* gamma, const float* beta,
-                             const float* save_mean, const float* save_invstd, int training,
-                             int precision, int64_t M, int K, int N, float* dh, float* ds, float* dW,
-                             float* dbias, float* dgamma, float* dbeta, void* workspace,
-                             size_t workspace_bytes, void* stream) {
+// phase 0: the whole backward.  Global-batch statistics: phase 1 = pass 1 (ds, this replica's sums and dW pieces,
+// kept in the workspace) -> fp64 `moments` [2][N] = (sum du, sum du zhat); phase 2 = finalize with the all-reduced
+// moments over `Mstat` rows (dW / dbias / dgamma / dbeta stay this replica's contributions) + the dh pass.  The
+// workspace must be the same, untouched buffer in both phases.
+static int gate_bwd_impl(const float* dy, const float* h, const float* h_coef, const float* s, const float* z,
+                         const float* W, const float* gamma, const float* beta,
+                         const float* save_mean, const float* save_invstd, int training,
+                         int precision, int64_t M, int K, int N, float* dh, float* ds, float* dW,
+                         float* dbias, float* dgamma, float* dbeta, void* workspace,
+                         size_t workspace_bytes, void* stream, int phase, double* moments, int64_t Mstat) {
   int rc = gate_check(M, K, N, precision);
   if (rc != VMTL_OK) return rc;
-  if (!dy || !h || !s || !z || !W || !gamma || !beta || !save_mean || !save_invstd || !dW || !dbias ||
-      !dgamma || !dbeta || !workspace)
+  if (phase != 0 && (!training || !moments)) return VMTL_EINVAL;
+  if (phase == 2 && Mstat < 1) return VMTL_EINVAL;
+  if (!dy || !h || !s || !z || !W || !gamma || !beta || !save_mean || !save_invstd ||
+      (phase != 1 && (!dW || !dbias || !dgamma || !dbeta)) || !workspace)
     return VMTL_EINVAL;
   if (h_coef && (precision == VMTL_GATE_FP32_FFMA || !gate_tc_supported(K, N))) return VMTL_EUNSUPPORTED;
   if (!aligned16(dy) || !aligned16(h) || !aligned16(s) || !aligned16(z) || !aligned16(W) ||
@@ -553,12 +663,20 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* h_coe
 
   if (precision != VMTL_GATE_FP32_FFMA && gate_tc_supported(K, N)) {
     // tensor-core path: pass 1 (ds + statistics + dW partials), finalize, pass 2 (dh)
-    int np1 = 0;
-    rc = gate_tc_bwd_pass1(dy, h, h_coef, s, z, gamma, beta, save_mean, save_invstd, M, K, N, split3, ds, ws, &np1, st);
-    if (rc != VMTL_OK) return rc;
+    int np1 = gate_tc_bwd_pass1_grid(M, N);
+    const int nch = N <= 64 ? 1 : N / 64;
+    if (phase != 2) {
+      rc = gate_tc_bwd_pass1(dy, h, h_coef, s, z, gamma, beta, save_mean, save_invstd, M, K, N, split3, ds, ws, &np1, st);
+      if (rc != VMTL_OK) return rc;
+    }
+    if (phase == 1) {
+      gate_bwd_tc_moments<<<(N + 31) / 32, kFinThreads, 0, st>>>(ws.partial, np1, nch, N, moments);
+      return launch_status();
+    }
     gate_bwd_tc_finalize<<<(N / kFinRows) * (K / 32) + (N + 31) / 32, kFinThreads, 0, st>>>(
-        ws.gemm_partial, ws.hs_partial, ws.partial, np1, N <= 64 ? 1 : N / 64, M, N, K, training, gamma, beta, save_mean, save_invstd, dW,
-        dbias, dgamma, dbeta, ws.c1, ws.c2, ws.coefA, ws.coefB, ws.mean, ws.invstd);
+        ws.gemm_partial, ws.hs_partial, ws.partial, np1, nch, M, N, K, training, gamma, beta, save_mean, save_invstd, dW,
+        dbias, dgamma, dbeta, ws.c1, ws.c2, ws.coefA, ws.coefB, ws.mean, ws.invstd, phase == 2 ? moments : nullptr,
+        Mstat);
     if ((rc = launch_status()) != VMTL_OK) return rc;
     return dh ? gate_tc_bwd_dh(dy, s, z, W, ws, M, K, N, split3, dh, st) : VMTL_OK;
   }
@@ -566,12 +684,19 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* h_coe
   // CUDA-core path
   // phase A
   const int nparts = ew_grid(M, N, blocks_per_sm(gate_bwd_stats_kernel, kEwThreads, 0, 8));
-  gate_bwd_stats_kernel<<<nparts, kEwThreads, 0, st>>>(dy, s, z, M, C4, gamma, beta, save_mean, save_invstd,
-                                                       ds, ws.partial);
-  if ((rc = launch_status()) != VMTL_OK) return rc;
+  if (phase != 2) {
+    gate_bwd_stats_kernel<<<nparts, kEwThreads, 0, st>>>(dy, s, z, M, C4, gamma, beta, save_mean, save_invstd,
+                                                         ds, ws.partial);
+    if ((rc = launch_status()) != VMTL_OK) return rc;
+  }
+  if (phase == 1) {
+    gate_moments_finalize<<<(N + 31) / 32, kFinThreads, 0, st>>>(ws.partial, nparts, N, moments);
+    return launch_status();
+  }
   gate_bwd_stats_finalize<<<(N + 31) / 32, kFinThreads, 0, st>>>(ws.partial, nparts, M, N, training, dgamma,
                                                            dbeta, ws.c1, ws.c2, gamma, beta, save_mean,
-                                                           save_invstd, ws.coefA, ws.coefB, ws.mean, ws.invstd);
+                                                           save_invstd, ws.coefA, ws.coefB, ws.mean, ws.invstd,
+                                                           phase == 2 ? moments : nullptr, Mstat);
   if ((rc = launch_status()) != VMTL_OK) return rc;
 
   // phase B
@@ -597,4 +722,34 @@ extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* h_coe
   if (rc != VMTL_OK) return rc;
   rows_sum_finalize<<<(N * K + 31) / 32, kFinThreads, 0, st>>>(ws.gemm_partial, splits, N * K, dW);
   return launch_status();
+}
+
+extern "C" int vmtl_gate_bwd(const float* dy, const float* h, const float* h_coef, const float* s, const float* z,
+                             const float* W, const float* gamma, const float* beta,
+                             const float* save_mean, const float* save_invstd, int training,
+                             int precision, int64_t M, int K, int N, float* dh, float* ds, float* dW,
+                             float* dbias, float* dgamma, float* dbeta, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  return gate_bwd_impl(dy, h, h_coef, s, z, W, gamma, beta, save_mean, save_invstd, training, precision, M, K, N, dh, ds,
+                       dW, dbias, dgamma, dbeta, workspace, workspace_bytes, stream, 0, nullptr, 0);
+}
+
+extern "C" int vmtl_gate_bwd_moments(const float* dy, const float* h, const float* h_coef, const float* s,
+                                     const float* z, const float* W, const float* gamma, const float* beta,
+                                     const float* save_mean, const float* save_invstd, int precision, int64_t M,
+                                     int K, int N, float* ds, double* moments, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  return gate_bwd_impl(dy, h, h_coef, s, z, W, gamma, beta, save_mean, save_invstd, 1, precision, M, K, N, nullptr, ds,
+                       nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream, 1, moments, 0);
+}
+
+extern "C" int vmtl_gate_bwd_global(const float* dy, const float* h, const float* h_coef, const float* s,
+                                    const float* z, const float* W, const float* gamma, const float* beta,
+                                    const float* save_mean, const float* save_invstd, int precision, int64_t M,
+                                    int K, int N, const double* moments, int64_t M_global, float* dh, float* dW,
+                                    float* dbias, float* dgamma, float* dbeta, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  return gate_bwd_impl(dy, h, h_coef, s, z, W, gamma, beta, save_mean, save_invstd, 1, precision, M, K, N, dh, nullptr,
+                       dW, dbias, dgamma, dbeta, workspace, workspace_bytes, stream, 2, const_cast<double*>(moments),
+                       M_global);
 }

@@ -75,6 +75,8 @@ int gate_tc_fwd_eval(const float* h, const float* h_coef, const float* s, const 
 int gate_tc_bwd_pass1(const float* dy, const float* h, const float* h_coef, const float* s, const float* z, const float* gamma,
                       const float* beta, const float* mean, const float* invstd, int64_t M, int K, int N,
                       int split3, float* ds, const GateWs& ws, int* nparts, cudaStream_t st);
+// grid (= number of per-CTA partial rows) gate_tc_bwd_pass1 launches for (M, N)
+int gate_tc_bwd_pass1_grid(int64_t M, int N);
 // Backward pass 2: dh = dz @ W with dz rebuilt per tile from (dy, s, z) and the finalized ws.c1 / ws.c2.
 int gate_tc_bwd_dh(const float* dy, const float* s, const float* z, const float* W, const GateWs& ws, int64_t M,
                    int K, int N, int split3, float* dh, cudaStream_t st);

@@ -70,16 +70,21 @@ static int tc_grid(int64_t M, int rows) {
   return (int)(n < sms ? n : sms);
 }
 
-int gate_tc_bwd_pass1(const float* dy, const float* h, const float* h_coef, const float* s, const float* z, const float* gamma,
-                      const float* beta, const float* mean, const float* invstd, int64_t M, int K, int N,
-                      int split3, float* ds, const GateWs& ws, int* nparts, cudaStream_t st) {
-  if (!gate_tc_supported(K, N) || !ws.hs_partial) return VMTL_EUNSUPPORTED;
+int gate_tc_bwd_pass1_grid(int64_t M, int N) {
   // (64-row unit, column chunk) items over the SMs; the grid is a multiple of the chunk count
   const int nch = N <= 64 ? 1 : N / 64;
   const int64_t items = ((M + 63) / 64) * nch;
   int grid = (int)(items < sm_count() ? items : sm_count());
   grid = grid / nch * nch;
-  if (grid < nch) grid = nch;
+  return grid < nch ? nch : grid;
+}
+
+int gate_tc_bwd_pass1(const float* dy, const float* h, const float* h_coef, const float* s, const float* z, const float* gamma,
+                      const float* beta, const float* mean, const float* invstd, int64_t M, int K, int N,
+                      int split3, float* ds, const GateWs& ws, int* nparts, cudaStream_t st) {
+  if (!gate_tc_supported(K, N) || !ws.hs_partial) return VMTL_EUNSUPPORTED;
+  const int nch = N <= 64 ? 1 : N / 64;
+  const int grid = gate_tc_bwd_pass1_grid(M, N);
   // per-CTA partials: [2][Nc][K] in ws.gemm_partial (2 sm_count slots of N*K), [3][Nc] in ws.partial, [K] in ws.hs_partial
   const int Nc = N <= 64 ? N : 64;
   if ((int64_t)grid * 2 * Nc > (int64_t)ws.gemm_slots * N || (int64_t)grid * 3 * Nc > (int64_t)ws.partial_rows * 2 * N ||

@@ -750,6 +750,22 @@ __global__ void __launch_bounds__(kLossThreads)
   }
 }
 
+// out[0..4] = {n, sum g, sum g^2, sum|p-t|, sum|p-t|/t}, out[7] = P  ->  out[5] = mean g, out[6] = D, scalars
+__device__ __forceinline__ void silog_from_moments(double* __restrict__ out, float* __restrict__ scalars) {
+  const double n = out[0], sg = out[1], sgg = out[2];
+  const double mean = sg / n;
+  // unbiased variance, as torch.var (losses.py:35); n <= 1 gives NaN like the reference
+  const double var = (sgg - sg * mean) / (n - 1.0);
+  const double D = var + 0.15 * mean * mean;
+  out[5] = mean;
+  out[6] = D;
+  if (scalars) {
+    scalars[0] = (float)(10.0 * sqrt(D));
+    scalars[1] = (float)(out[3] / out[7]);
+    scalars[2] = (float)(out[4] / n);
+  }
+}
+
 __global__ void silog_finalize(const double* __restrict__ partial, int nblocks, int64_t P,
                                double* __restrict__ out, float* __restrict__ scalars) {
   __shared__ double s[5];
@@ -758,25 +774,19 @@ __global__ void silog_finalize(const double* __restrict__ partial, int nblocks, 
   if (threadIdx.x < 5) s[threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
-    const double n = s[0], sg = s[1], sgg = s[2];
-    const double mean = sg / n;
-    // unbiased variance, as torch.var (losses.py:35); n <= 1 gives NaN like the reference
-    const double var = (sgg - sg * mean) / (n - 1.0);
-    const double D = var + 0.15 * mean * mean;
-    out[0] = n;
-    out[1] = sg;
-    out[2] = sgg;
+    out[0] = s[0];
+    out[1] = s[1];
+    out[2] = s[2];
     out[3] = s[3];
     out[4] = s[4];
-    out[5] = mean;
-    out[6] = D;
     out[7] = (double)P;
-    if (scalars) {
-      scalars[0] = (float)(10.0 * sqrt(D));
-      scalars[1] = (float)(s[3] / (double)P);
-      scalars[2] = (float)(s[4] / n);
-    }
+    silog_from_moments(out, scalars);
   }
+}
+
+// global-batch statistics: out[0..4] and out[7] hold all-reduced sums; re-derive mean, D and the scalars
+__global__ void silog_refinalize(double* __restrict__ out, float* __restrict__ scalars) {
+  if (threadIdx.x == 0) silog_from_moments(out, scalars);
 }
 
 // d silog / d zd_i = (5/sqrt(D)) * (2 (g_i - mean)/(n-1) + 0.3 mean / n) * (1 - p_i)   
@@ -1141,5 +1151,11 @@ extern "C" int vmtl_head_silog_bwd(const float* feat, const float* w, const floa
   int rc = launch_status();
   if (rc != VMTL_OK) return rc;
   silog_bwd_finalize<<<(Cin + 1 + 31) / 32, kFinThreads, 0, st>>>(partial, grid, Cin, dw, db);
+  return launch_status();
+}
+
+extern "C" int vmtl_silog_finalize(double* out, float* scalars, void* stream) {
+  if (!out) return VMTL_EINVAL;
+  silog_refinalize<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(out, scalars);
   return launch_status();
 }

@@ -72,8 +72,29 @@ def wrap_data_parallel(module, device_index: t.Optional[int] = None, **ddp_kwarg
     kwargs.update(ddp_kwargs)
     if device_index is not None:
         kwargs.setdefault("device_ids", [device_index])
-    module.model = DDP(module.model, **kwargs)
+    if device_index is not None and torch.cuda.is_available():
+        # whole-step CUDA-graph capture needs DDP constructed on a side stream (torch CUDA-graphs notes)
+        side = torch.cuda.Stream(device=device_index)
+        side.wait_stream(torch.cuda.current_stream(device_index))
+        with torch.cuda.stream(side):
+            module.model = DDP(module.model, **kwargs)
+        torch.cuda.current_stream(device_index).wait_stream(side)
+    else:
+        module.model = DDP(module.model, **kwargs)
     return module
+
+
+def enable_stat_sync(module, group=None) -> None:
+    """Global-batch-exact mode: call BEFORE ``wrap_data_parallel``.  The library's BatchNorm /
+    gate / SILog kernels all-reduce their moments between their two halves (``ops.set_stat_sync``); BatchNorm
+    layers that stay on ATen (the csnet / basic backbone leaves) become ``torch.nn.SyncBatchNorm``.  Cross-entropy
+    stays a per-replica mean: with equal shards and no ignored pixels the average over replicas is the global mean."""
+    if not is_distributed():
+        return
+    ops.set_stat_sync(True, group)
+    inner = module.model
+    if not hasattr(inner, "forward_features"):  # MTAN runs every BatchNorm through the library
+        module.model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(inner, group)
 
 
 STAT_EXTRA = 8

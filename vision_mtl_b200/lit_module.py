@@ -83,17 +83,19 @@ class MTLModule(nn.Module):
             heads = inner.map_tasks_to_heads
             loss_segm, pred = ops.head_cross_entropy(feats["segm"], heads["segm"].weight, heads["segm"].bias,
                                                      gt_mask, self.ignore_index, conf, True)
-            silog, mae, absrel, dpred = ops.head_silog(feats["depth"], heads["depth"].weight,
-                                                       heads["depth"].bias, gt_depth, self.depth_criterion.min_depth,
-                                                       want_preds)
+            silog, mae, absrel, dpred, moments = ops.head_silog(
+                feats["depth"], heads["depth"].weight, heads["depth"].bias, gt_depth,
+                self.depth_criterion.min_depth, want_preds, return_moments=True)
         else:
             raw = self.model(img)
             loss_segm, pred = ops.cross_entropy_logits(raw["segm"], gt_mask, self.ignore_index, conf, True)
-            silog, mae, absrel, dpred = ops.head_silog(raw["depth"], None, None, gt_depth,
-                                                       self.depth_criterion.min_depth, want_preds)
+            silog, mae, absrel, dpred, moments = ops.head_silog(
+                raw["depth"], None, None, gt_depth, self.depth_criterion.min_depth, want_preds, return_moments=True)
         seg = ops.seg_metrics(conf)
         loss = self.loss_segm_weight * loss_segm + self.loss_depth_weight * silog
         self.last_confusion = conf
+        # {P, sum|p-t|, n(t > min_depth), sum|p-t|/t}: the depth part of the packed data-parallel statistics
+        self.last_depth_sums = torch.stack([moments[7], moments[3], moments[0], moments[4]])
         return {
             "loss": loss, "loss_segm": loss_segm, "loss_depth": silog,
             "accuracy": seg[0], "jaccard_index": seg[1], "fbeta_score": seg[2], "mae": mae, "abs_rel": absrel,

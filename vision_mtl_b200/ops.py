@@ -53,6 +53,8 @@ _KERNELS_PER_CALL = {
     "head_silog_bwd": 2, "confusion_accum": 1, "depth_err_sums": 2, "seg_metrics": 1,
     "xstitch_cat_fwd": 1, "xstitch_cat_bwd": 2,
     "bnrelu_fwd": 3, "bnrelu_bwd": 3, "bnrelu_pool_fwd": 3, "bnrelu_pool_bwd": 3,
+    "bn_moments": 2, "bnrelu_fwd_global": 2, "bnrelu_bwd_moments": 2, "bnrelu_bwd_global": 2,
+    "gate_fwd_moments": 2, "gate_fwd_global": 2, "gate_bwd_moments": 2, "gate_bwd_global": 2, "silog_finalize": 1,
 }
 
 
@@ -149,6 +151,40 @@ def _nhwc(x: torch.Tensor) -> torch.Tensor:
 def _ptr_array(ts: Sequence[torch.Tensor]):
     arr = (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
     return arr
+
+
+# --------------------------------------------------------------------------------------
+# Global-batch statistics under data parallelism
+# --------------------------------------------------------------------------------------
+class _Sync:
+    enabled = False
+    group = None
+
+
+def set_stat_sync(enabled: bool, group=None) -> None:
+    """Global-batch-exact mode: every batch statistic of the hot path (BatchNorm moments of the gate, of the
+    hidden layer and of every conv -> BN -> ReLU chain, forward and backward; the SILog moments) is all-reduced
+    over ``group`` between the two halves of its op, so an N-GPU step computes what the reference computes on
+    the concatenated batch.  Needs an initialised ``torch.distributed`` process group (NCCL) and equal shards."""
+    _Sync.enabled = bool(enabled)
+    _Sync.group = group
+
+
+def stat_sync_world() -> int:
+    """Replicas whose statistics are combined (1: local statistics, the default data-parallel semantics)."""
+    if not _Sync.enabled:
+        return 1
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size(_Sync.group)
+
+
+def _allreduce_moments(t: torch.Tensor) -> None:
+    import torch.distributed as dist
+
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_Sync.group)
 
 
 # --------------------------------------------------------------------------------------
@@ -278,6 +314,70 @@ def cross_stitch_cat(skips: Sequence[torch.Tensor], xs: Sequence[torch.Tensor], 
 # --------------------------------------------------------------------------------------
 # BatchNorm2d (+ ReLU, + 2x2 max-pool)
 # --------------------------------------------------------------------------------------
+def _bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, pool, y, stats, world):
+    """Statistics + finalize (+ apply when ``y`` is given) of one BatchNorm; ``world > 1`` all-reduces the moments."""
+    B, C, H, W = x.shape
+    M = B * H * W
+    dev = x.device
+    ws = _workspace(_lib.load().vmtl_bnrelu_workspace_bytes(M, C), dev)
+    out_rows = 0 if y is None else y.numel() // C
+    if training and world > 1:
+        mom = torch.empty((2, C), dtype=torch.float64, device=dev)
+        _call("bn_moments", 4 * C * M, _p(x), M, C, _p(mom), _p(ws), ws.numel(), _stream())
+        _allreduce_moments(mom)
+        _call("bnrelu_fwd_global", 4 * C * (M + out_rows) if y is not None else 0, _p(x), _p(gamma.detach()),
+              _p(beta.detach()), _p(running_mean), _p(running_var), float(momentum), float(eps), 1 if relu else 0,
+              1 if pool else 0, B, H, W, C, _p(mom), M * world, _p(y), _p(stats[0]), _p(stats[1]), _p(stats[2:]), _p(ws),
+              ws.numel(), _stream())
+        if y is None:
+            _Prof.launches -= 1
+        return
+    nbytes = 4 * C * ((2 * M if training else M) + out_rows) if y is not None else (4 * C * M if training else 0)
+    if pool:
+        _call("bnrelu_pool_fwd", nbytes, _p(x), _p(gamma.detach()), _p(beta.detach()), _p(running_mean),
+              _p(running_var), float(momentum), float(eps), 1 if training else 0, 1 if relu else 0, B, H, W, C,
+              _p(y), _p(stats[0]), _p(stats[1]), _p(stats[2:]), _p(ws), ws.numel(), _stream())
+    else:
+        _call("bnrelu_fwd", nbytes, _p(x), _p(gamma.detach()), _p(beta.detach()), _p(running_mean),
+              _p(running_var), float(momentum), float(eps), 1 if training else 0, 1 if relu else 0, M, C,
+              _p(y), _p(stats[0]), _p(stats[1]), _p(stats[2:]), _p(ws), ws.numel(), _stream())
+    _Prof.launches -= (0 if training else 1) + (0 if y is not None else 1)  # no statistics / no apply pass
+
+
+def _bn_backward(dy, x, stats, training, relu, pool, need_dx, world):
+    """-> (dx | None, dgamma, dbeta) of one BatchNorm (+ReLU, +pool); ``world > 1``: global normalisation terms."""
+    B, C, H, W = x.shape
+    M = B * H * W
+    dev = x.device
+    dx = torch.empty_like(x) if need_dx else None
+    ws = _workspace(_lib.load().vmtl_bnrelu_workspace_bytes(M, C), dev)
+    dy_rows = dy.numel() // C
+    if training and world > 1:
+        mom = torch.empty((2, C), dtype=torch.float64, device=dev)
+        _call("bnrelu_bwd_moments", 4 * C * (M + dy_rows), _p(dy), _p(x), _p(stats[2:]), _p(stats[0]), _p(stats[1]),
+              1 if relu else 0, 1 if pool else 0, B, H, W, C, _p(mom), _p(ws), ws.numel(), _stream())
+        local = mom.to(torch.float32)  # this replica's (dbeta, dgamma): averaged with every other gradient
+        _allreduce_moments(mom)
+        if need_dx:
+            _call("bnrelu_bwd_global", 4 * C * (2 * M + dy_rows), _p(dy), _p(x), _p(stats[2:]), _p(stats[0]),
+                  _p(stats[1]), 1 if relu else 0, 1 if pool else 0, B, H, W, C, _p(mom), M * world, _p(dx), _p(ws),
+                  ws.numel(), _stream())
+        return dx, local[1], local[0]
+    dgb = torch.empty((2, C), dtype=torch.float32, device=dev)
+    nbytes = 4 * C * (2 * (M + dy_rows) + (M if need_dx else 0))
+    if pool:
+        _call("bnrelu_pool_bwd", nbytes, _p(dy), _p(x), _p(stats[2:]), _p(stats[0]), _p(stats[1]),
+              1 if training else 0, 1 if relu else 0, B, H, W, C, _p(dx), _p(dgb[0]), _p(dgb[1]), _p(ws),
+              ws.numel(), _stream())
+    else:
+        _call("bnrelu_bwd", nbytes, _p(dy), _p(x), _p(stats[2:]), _p(stats[0]), _p(stats[1]),
+              1 if training else 0, 1 if relu else 0, M, C, _p(dx), _p(dgb[0]), _p(dgb[1]), _p(ws), ws.numel(),
+              _stream())
+    if not need_dx:
+        _Prof.launches -= 1
+    return dx, dgb[0], dgb[1]
+
+
 class BNReLUFunction(torch.autograd.Function):
     """``[maxpool2(] relu( batch_norm(x) ) [)]`` in NHWC: statistics pass + apply pass (+ their backward)."""
 
@@ -286,7 +386,6 @@ class BNReLUFunction(torch.autograd.Function):
         x = _nhwc(x)
         _need_cuda(x, gamma, beta)
         B, C, H, W = x.shape
-        M = B * H * W
         dev = x.device
         if pool:
             y = torch.empty((B, C, H // 2, W // 2), dtype=torch.float32, device=dev).contiguous(
@@ -294,42 +393,18 @@ class BNReLUFunction(torch.autograd.Function):
         else:
             y = torch.empty_like(x)
         stats = torch.empty((4, C), dtype=torch.float32, device=dev)  # save_mean, save_invstd, A, B
-        ws = _workspace(_lib.load().vmtl_bnrelu_workspace_bytes(M, C), dev)
-        nbytes = 4 * C * ((2 * M if training else M) + y.numel() // C)
-        if pool:
-            _call("bnrelu_pool_fwd", nbytes, _p(x), _p(gamma.detach()), _p(beta.detach()), _p(running_mean),
-                  _p(running_var), float(momentum), float(eps), 1 if training else 0, 1 if relu else 0, B, H, W, C,
-                  _p(y), _p(stats[0]), _p(stats[1]), _p(stats[2:]), _p(ws), ws.numel(), _stream())
-        else:
-            _call("bnrelu_fwd", nbytes, _p(x), _p(gamma.detach()), _p(beta.detach()), _p(running_mean),
-                  _p(running_var), float(momentum), float(eps), 1 if training else 0, 1 if relu else 0, M, C,
-                  _p(y), _p(stats[0]), _p(stats[1]), _p(stats[2:]), _p(ws), ws.numel(), _stream())
-        if not training:
-            _Prof.launches -= 1  # no statistics pass on running statistics
-        ctx.cfg = (bool(training), bool(relu), bool(pool))
+        world = stat_sync_world() if training else 1
+        _bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, pool, y, stats, world)
+        ctx.cfg = (bool(training), bool(relu), bool(pool), world)
         ctx.save_for_backward(x, stats)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, stats = ctx.saved_tensors
-        training, relu, pool = ctx.cfg
-        dy = _nhwc(dy)
-        B, C, H, W = x.shape
-        M = B * H * W
-        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dgb = torch.empty((2, C), dtype=torch.float32, device=x.device)
-        ws = _workspace(_lib.load().vmtl_bnrelu_workspace_bytes(M, C), x.device)
-        nbytes = 4 * C * (2 * (M + dy.numel() // C) + (M if dx is not None else 0))
-        if pool:
-            _call("bnrelu_pool_bwd", nbytes, _p(dy), _p(x), _p(stats[2:]), _p(stats[0]), _p(stats[1]),
-                  1 if training else 0, 1 if relu else 0, B, H, W, C, _p(dx), _p(dgb[0]), _p(dgb[1]), _p(ws),
-                  ws.numel(), _stream())
-        else:
-            _call("bnrelu_bwd", nbytes, _p(dy), _p(x), _p(stats[2:]), _p(stats[0]), _p(stats[1]),
-                  1 if training else 0, 1 if relu else 0, M, C, _p(dx), _p(dgb[0]), _p(dgb[1]), _p(ws), ws.numel(),
-                  _stream())
-        return dx, dgb[0], dgb[1], None, None, None, None, None, None, None
+        training, relu, pool, world = ctx.cfg
+        dx, dgamma, dbeta = _bn_backward(_nhwc(dy), x, stats, training, relu, pool, ctx.needs_input_grad[0], world)
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None
 
 
 def bn_supported(bn: torch.nn.Module, x: torch.Tensor) -> bool:
@@ -384,6 +459,67 @@ def gate_bytes(M: int, K: int, N: int, training: bool, backward: bool, stored_z:
     return algo, issued
 
 
+def _gate_forward(h, h_coef, s, w2, bias, gamma, beta, running_mean, running_var, training, momentum, eps,
+                  precision, need_z, world):
+    """-> (y, z | None, mean, invstd); ``world > 1`` (training): the batch statistics of z are global."""
+    B, K, H, W = h.shape
+    N = s.shape[1]
+    M = B * H * W
+    dev = h.device
+    y = torch.empty_like(s)
+    z = torch.empty_like(s) if need_z else None
+    st = torch.empty((2, N), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    ws = _workspace(lib.vmtl_gate_workspace_bytes(M, K, N, precision, 0), dev)
+    algo, issued = gate_bytes(M, K, N, training, backward=False, stored_z=z is not None)
+    if training and world > 1:
+        mom = torch.empty((2, N), dtype=torch.float64, device=dev)
+        _call("gate_fwd_moments", 4 * M * (K + N), _p(h), _p(h_coef), _p(w2), _p(bias.detach()), precision, M, K, N,
+              _p(z), _p(mom), _p(ws), ws.numel(), _stream())
+        _allreduce_moments(mom)
+        _call("gate_fwd_global", algo - 4 * M * (K + N), _p(s), _p(z), _p(gamma.detach()), _p(beta.detach()),
+              _p(running_mean), _p(running_var), float(momentum), float(eps), precision, M, K, N, _p(mom), M * world,
+              _p(y), _p(st[0]), _p(st[1]), _p(ws), ws.numel(), _stream())
+        _Prof.launches -= 1  # moments + global = contraction, 2 x finalize, gate pass
+        return y, z, st[0], st[1]
+    _call("gate_fwd", algo, _p(h), _p(h_coef), _p(s), _p(w2), _p(bias.detach()), _p(gamma.detach()),
+          _p(beta.detach()), _p(running_mean), _p(running_var), float(momentum), float(eps),
+          1 if training else 0, precision, M, K, N, _p(y), _p(z), _p(st[0]), _p(st[1]), _p(ws),
+          ws.numel(), _stream(), issued=issued)
+    return y, z, st[0], st[1]
+
+
+def _gate_backward(dy, h, h_coef, s, z, w2, gamma, beta, mean, invstd, training, precision, need_dh, need_ds, world):
+    """-> (dh | None, ds | None, dW [N,K], dbias, dgamma, dbeta)."""
+    B, K, H, W = h.shape
+    N = s.shape[1]
+    M = B * H * W
+    dev = h.device
+    dh = torch.empty_like(h) if need_dh else None
+    ds = torch.empty_like(s) if need_ds else None
+    dW = torch.empty_like(w2)
+    small = torch.empty((3, N), dtype=torch.float32, device=dev)  # dbias, dgamma, dbeta
+    lib = _lib.load()
+    ws = _workspace(lib.vmtl_gate_workspace_bytes(M, K, N, precision, 1), dev)
+    algo, issued = gate_bytes(M, K, N, training, backward=True)
+    args = (_p(dy), _p(h), _p(h_coef), _p(s), _p(z), _p(w2), _p(gamma.detach()), _p(beta.detach()), _p(mean),
+            _p(invstd))
+    if training and world > 1:
+        mom = torch.empty((2, N), dtype=torch.float64, device=dev)
+        _call("gate_bwd_moments", 4 * M * (K + 4 * N), *args, precision, M, K, N, _p(ds), _p(mom), _p(ws), ws.numel(),
+              _stream())
+        _allreduce_moments(mom)
+        _call("gate_bwd_global", algo - 4 * M * (K + 4 * N), *args, precision, M, K, N, _p(mom), M * world, _p(dh),
+              _p(dW), _p(small[0]), _p(small[1]), _p(small[2]), _p(ws), ws.numel(), _stream())
+    else:
+        _call("gate_bwd", algo, *args, 1 if training else 0, precision, M, K, N, _p(dh), _p(ds), _p(dW),
+              _p(small[0]), _p(small[1]), _p(small[2]), _p(ws), ws.numel(), _stream(), issued=issued)
+    if precision != GATE_FP32_FFMA and N > 64 and bool(lib.vmtl_gate_tc_supported(K, N)):
+        # wider gates run extra dh launches: per 64 columns, or per 256 when every CTA owns a single 128-row tile
+        _Prof.launches += _gate_bwd_passes(M, N)[1] - 1
+    return dh, ds, dW, small[0], small[1], small[2]
+
+
 class GateFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, s, weight, bias, gamma, beta, running_mean, running_var, training, momentum,
@@ -394,56 +530,26 @@ class GateFunction(torch.autograd.Function):
         h = _nhwc(h)
         s = _nhwc(s)
         _need_cuda(h, s, weight)
-        B, K, H, W = h.shape
-        N = s.shape[1]
-        M = B * H * W
+        K, N = h.shape[1], s.shape[1]
         w2 = weight.detach().reshape(N, K).contiguous()
-        y = torch.empty_like(s)
         # z = conv output is kept for the backward; pure inference on the tensor-core path
         # fuses everything into one pass and never stores it
         need_z = training or precision == GATE_FP32_FFMA or any(ctx.needs_input_grad)
-        z = torch.empty_like(s) if need_z else None
-        mean = torch.empty(N, dtype=torch.float32, device=h.device)
-        invstd = torch.empty(N, dtype=torch.float32, device=h.device)
-        lib = _lib.load()
-        ws = _workspace(lib.vmtl_gate_workspace_bytes(M, K, N, precision, 0), h.device)
-        algo, issued = gate_bytes(M, K, N, training, backward=False, stored_z=z is not None)
-        _call("gate_fwd", algo, _p(h), _p(h_coef), _p(s), _p(w2), _p(bias.detach()), _p(gamma.detach()),
-              _p(beta.detach()), _p(running_mean), _p(running_var), float(momentum), float(eps),
-              1 if training else 0, precision, M, K, N, _p(y), _p(z), _p(mean), _p(invstd), _p(ws),
-              ws.numel(), _stream(), issued=issued)
-        ctx.training = bool(training)
-        ctx.precision = precision
-        ctx.dims = (M, K, N)
-        ctx.wshape = weight.shape
-        ctx.has_pre = h_coef is not None
+        world = stat_sync_world() if training else 1
+        y, z, mean, invstd = _gate_forward(h, h_coef, s, w2, bias, gamma, beta, running_mean, running_var, training,
+                                           momentum, eps, precision, need_z, world)
+        ctx.cfg = (bool(training), precision, weight.shape, world)
         ctx.save_for_backward(h, s, z, w2, gamma, beta, mean, invstd, *([h_coef] if h_coef is not None else []))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         h, s, z, w2, gamma, beta, mean, invstd, *pre = ctx.saved_tensors
-        h_coef = pre[0] if pre else None
-        M, K, N = ctx.dims
-        dy = _nhwc(dy)
-        need_dh, need_ds = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dh = torch.empty_like(h) if need_dh else None
-        ds = torch.empty_like(s) if need_ds else None
-        dW = torch.empty_like(w2)
-        dbias = torch.empty(N, dtype=torch.float32, device=h.device)
-        dgamma = torch.empty_like(dbias)
-        dbeta = torch.empty_like(dbias)
-        lib = _lib.load()
-        ws = _workspace(lib.vmtl_gate_workspace_bytes(M, K, N, ctx.precision, 1), h.device)
-        algo, issued = gate_bytes(M, K, N, ctx.training, backward=True)
-        _call("gate_bwd", algo, _p(dy), _p(h), _p(h_coef), _p(s), _p(z), _p(w2), _p(gamma.detach()),
-              _p(beta.detach()), _p(mean), _p(invstd), 1 if ctx.training else 0, ctx.precision, M, K, N,
-              _p(dh), _p(ds), _p(dW), _p(dbias), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream(),
-              issued=issued)
-        if ctx.precision != 0 and N > 64 and K == 128 and N % 64 == 0:
-            # wider gates run extra dh launches: per 64 columns, or per 256 when every CTA owns a single 128-row tile
-            _Prof.launches += _gate_bwd_passes(M, N)[1] - 1
-        return (dh, ds, dW.reshape(ctx.wshape), dbias, dgamma, dbeta, None, None, None, None, None, None, None)
+        training, precision, wshape, world = ctx.cfg
+        dh, ds, dW, dbias, dgamma, dbeta = _gate_backward(
+            _nhwc(dy), h, pre[0] if pre else None, s, z, w2, gamma, beta, mean, invstd, training, precision,
+            ctx.needs_input_grad[0], ctx.needs_input_grad[1], world)
+        return (dh, ds, dW.reshape(wshape), dbias, dgamma, dbeta, None, None, None, None, None, None, None)
 
 
 class FoldedGateFunction(torch.autograd.Function):
@@ -458,60 +564,30 @@ class FoldedGateFunction(torch.autograd.Function):
         c = _nhwc(c)
         s = _nhwc(s)
         _need_cuda(c, s, weight)
-        B, K, H, W = c.shape
-        N = s.shape[1]
-        M = B * H * W
-        dev = c.device
-        lib = _lib.load()
-        stats1 = torch.empty((4, K), dtype=torch.float32, device=dev)  # mean1, invstd1, A1, B1
-        ws1 = _workspace(lib.vmtl_bnrelu_workspace_bytes(M, K), dev)
-        _call("bnrelu_fwd", 4 * K * M if train1 else 0, _p(c), _p(g1.detach()), _p(b1.detach()), _p(rm1), _p(rv1),
-              float(mom1), float(eps1), 1 if train1 else 0, 1, M, K, _p(None), _p(stats1[0]), _p(stats1[1]),
-              _p(stats1[2:]), _p(ws1), ws1.numel(), _stream())
-        _Prof.launches -= 1 if train1 else 2  # statistics (+ finalize) only: nothing is applied
+        K, N = c.shape[1], s.shape[1]
+        world1 = stat_sync_world() if train1 else 1
+        world2 = stat_sync_world() if train2 else 1
+        stats1 = torch.empty((4, K), dtype=torch.float32, device=c.device)  # mean1, invstd1, A1, B1
+        _bn_forward(c, g1, b1, rm1, rv1, train1, mom1, eps1, True, False, None, stats1, world1)
         w2 = weight.detach().reshape(N, K).contiguous()
-        y = torch.empty_like(s)
         need_z = train2 or any(ctx.needs_input_grad)
-        z = torch.empty_like(s) if need_z else None
-        st2 = torch.empty((2, N), dtype=torch.float32, device=dev)
-        ws = _workspace(lib.vmtl_gate_workspace_bytes(M, K, N, precision, 0), dev)
-        algo, issued = gate_bytes(M, K, N, train2, backward=False, stored_z=z is not None)
-        _call("gate_fwd", algo, _p(c), _p(stats1[2:]), _p(s), _p(w2), _p(bias.detach()), _p(g2.detach()),
-              _p(b2.detach()), _p(rm2), _p(rv2), float(mom2), float(eps2), 1 if train2 else 0, precision, M, K, N,
-              _p(y), _p(z), _p(st2[0]), _p(st2[1]), _p(ws), ws.numel(), _stream(), issued=issued)
-        ctx.cfg = (bool(train1), bool(train2), precision, (M, K, N), weight.shape)
-        ctx.save_for_backward(c, stats1, s, z, w2, g2, b2, st2)
+        y, z, mean2, invstd2 = _gate_forward(c, stats1[2:], s, w2, bias, g2, b2, rm2, rv2, train2, mom2, eps2,
+                                             precision, need_z, world2)
+        ctx.cfg = (bool(train1), bool(train2), precision, weight.shape, world1, world2)
+        ctx.save_for_backward(c, stats1, s, z, w2, g2, b2, mean2, invstd2)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        c, stats1, s, z, w2, g2, b2, st2 = ctx.saved_tensors
-        train1, train2, precision, (M, K, N), wshape = ctx.cfg
-        dy = _nhwc(dy)
-        dev = c.device
-        lib = _lib.load()
+        c, stats1, s, z, w2, g2, b2, mean2, invstd2 = ctx.saved_tensors
+        train1, train2, precision, wshape, world1, world2 = ctx.cfg
         need_dc = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        dh = torch.empty_like(c) if need_dc else None
-        ds = torch.empty_like(s) if ctx.needs_input_grad[8] else None
-        dW = torch.empty_like(w2)
-        small = torch.empty((3, N), dtype=torch.float32, device=dev)  # dbias, dgamma2, dbeta2
-        ws = _workspace(lib.vmtl_gate_workspace_bytes(M, K, N, precision, 1), dev)
-        algo, issued = gate_bytes(M, K, N, train2, backward=True)
-        _call("gate_bwd", algo, _p(dy), _p(c), _p(stats1[2:]), _p(s), _p(z), _p(w2), _p(g2.detach()),
-              _p(b2.detach()), _p(st2[0]), _p(st2[1]), 1 if train2 else 0, precision, M, K, N, _p(dh), _p(ds), _p(dW),
-              _p(small[0]), _p(small[1]), _p(small[2]), _p(ws), ws.numel(), _stream(), issued=issued)
-        if N > 64:
-            _Prof.launches += _gate_bwd_passes(M, N)[1] - 1
+        dh, ds, dW, dbias, dg2, db2 = _gate_backward(_nhwc(dy), c, stats1[2:], s, z, w2, g2, b2, mean2, invstd2, train2,
+                                                     precision, need_dc, ctx.needs_input_grad[8], world2)
         dc = dg1 = db1 = None
         if need_dc:  # relu + bn1 backward over (dh, c): statistics pass, finalize, apply pass
-            dc = torch.empty_like(c) if ctx.needs_input_grad[0] else None
-            dgb = torch.empty((2, K), dtype=torch.float32, device=dev)
-            ws1 = _workspace(lib.vmtl_bnrelu_workspace_bytes(M, K), dev)
-            _call("bnrelu_bwd", 4 * K * M * (5 if dc is not None else 2), _p(dh), _p(c), _p(stats1[2:]),
-                  _p(stats1[0]), _p(stats1[1]), 1 if train1 else 0, 1, M, K, _p(dc), _p(dgb[0]), _p(dgb[1]), _p(ws1),
-                  ws1.numel(), _stream())
-            dg1, db1 = dgb[0], dgb[1]
-        return (dc, dg1, db1, None, None, None, None, None, ds, dW.reshape(wshape), small[0], small[1], small[2],
+            dc, dg1, db1 = _bn_backward(dh, c, stats1, train1, True, False, ctx.needs_input_grad[0], world1)
+        return (dc, dg1, db1, None, None, None, None, None, ds, dW.reshape(wshape), dbias, dg2, db2,
                 None, None, None, None, None, None)
 
 
@@ -689,6 +765,11 @@ class HeadSilogFunction(torch.autograd.Function):
         _call("head_silog_fwd", P * (4 * Cin + 4 + (4 if want_pred else 0)), _p(feat), _p(w1),
               _p(bias.detach() if has_head else None), _p(tgt), P, Cin, float(min_depth), _p(out),
               _p(scalars), _p(pred), _p(ws), ws.numel(), _stream())
+        world = stat_sync_world()
+        if world > 1:  # SILog of the GLOBAL batch: all-reduce the sums, re-derive mean / D / scalars
+            _allreduce_moments(out)
+            _call("silog_finalize", 0, _p(out), _p(scalars), _stream())
+        ctx.world = world
         ctx.min_depth = float(min_depth)
         ctx.has_head = has_head
         ctx.wshape = weight.shape if has_head else None
@@ -698,11 +779,11 @@ class HeadSilogFunction(torch.autograd.Function):
             ctx.save_for_backward(feat, tgt, out)
         if pred is None:
             pred = torch.empty(0, dtype=torch.float32, device=feat.device)
-        ctx.mark_non_differentiable(pred)
-        return scalars, pred
+        ctx.mark_non_differentiable(pred, out)
+        return scalars, pred, out
 
     @staticmethod
-    def backward(ctx, gscalars, _gpred):
+    def backward(ctx, gscalars, _gpred, _gout):
         gsilog = gscalars[0:1]  # only silog (scalars[0]) is differentiable; mae/abs_rel are metrics
         if ctx.has_head:
             feat, tgt, out, w1, bias = ctx.saved_tensors
@@ -712,6 +793,8 @@ class HeadSilogFunction(torch.autograd.Function):
         B, Cin, H, W = feat.shape
         P = B * H * W
         g = gsilog.detach().to(torch.float32).contiguous()
+        if ctx.world > 1:  # the data-parallel wrapper averages gradients; the global loss is not a per-replica mean
+            g = g * float(ctx.world)
         need_dfeat = ctx.needs_input_grad[0] or not ctx.has_head
         dfeat = torch.empty_like(feat) if need_dfeat else None
         dw = torch.empty(Cin, dtype=torch.float32, device=feat.device) if ctx.has_head else None
@@ -725,10 +808,14 @@ class HeadSilogFunction(torch.autograd.Function):
         return dfeat, None, None, None, None, None
 
 
-def head_silog(feat, weight, bias, target, min_depth: float = 1e-3, want_pred: bool = True):
-    """Returns (silog, mae, abs_rel, pred [B,H,W,1]); only silog carries a gradient."""
-    scalars, pred = HeadSilogFunction.apply(feat, weight, bias, target, min_depth, want_pred)
-    return scalars[0], scalars[1].detach(), scalars[2].detach(), pred
+def head_silog(feat, weight, bias, target, min_depth: float = 1e-3, want_pred: bool = True,
+               return_moments: bool = False):
+    """Returns (silog, mae, abs_rel, pred [B,H,W,1]); only silog carries a gradient.  ``return_moments``
+    appends the float64 [8] moment vector of ``vmtl_head_silog_fwd`` ({n, sum g, sum g^2, sum|p-t|,
+    sum|p-t|/t, mean g, D, P}): what a data-parallel step all-reduces."""
+    scalars, pred, moments = HeadSilogFunction.apply(feat, weight, bias, target, min_depth, want_pred)
+    out = (scalars[0], scalars[1].detach(), scalars[2].detach(), pred)
+    return out + (moments,) if return_moments else out
 
 
 # --------------------------------------------------------------------------------------

@@ -8,7 +8,10 @@ exactly like the reference -- SURVEY F2 --, periodic checkpoints), with three ch
   (``module.last_step_scalars``) instead of six ``.item()`` syncs (SURVEY F12);
 * ``ReduceLROnPlateau`` is built without the ``verbose`` argument torch 2.11 rejects (F11);
 * under ``torchrun`` every rank runs the same loop on its batch shard: gradients are all-reduced
-  by DDP, the step's confusion matrix and loss by one packed all-reduce, rank 0 logs and saves.
+  by DDP, the step's confusion matrix, loss and depth sums by one packed all-reduce whose result (the
+  GLOBAL loss / metrics) is what every rank records and rank 0 logs and saves;
+* on CUDA the training step replays as one CUDA graph (``--no_graph_step`` keeps it eager);
+  ``--sync_stats`` makes an N-GPU step equal the single-GPU step on the concatenated batch.
 
 Experiment tracking (comet) and TensorBoard are optional duck-typed hooks (``exp.log_metric``,
 ``logger.log_metrics`` / ``logger.log_dir``); none is required.
@@ -67,12 +70,37 @@ def _log(logger, exp, values: dict, step: int) -> None:
 
 def _step_scalars_to_host(module: MTLModule, stage: str) -> dict:
     """One D2H copy for the step's loss and metrics; replaces the device scalars stored in
-    ``step_outputs`` by host floats so epoch summaries need no further syncs."""
-    vals = module.last_step_scalars.tolist()
+    ``step_outputs`` by host floats so epoch summaries need no further syncs.  Under data parallelism the
+    GLOBAL values (all ranks: mean loss, metrics of the summed confusion matrix) travel in the same copy and
+    are what gets recorded and logged."""
+    glob = getattr(module, "last_global_scalars", None)
+    if glob is not None:
+        vals = torch.cat([module.last_step_scalars, glob]).tolist()[len(STEP_KEYS):]
+    else:
+        vals = module.last_step_scalars.tolist()
     rec = module.step_outputs[stage]
     for k, v in zip(STEP_KEYS, vals):
         rec[k][-1] = v
     return dict(zip(STEP_KEYS, vals))
+
+
+def _make_metric_exchange(module: MTLModule, world: int) -> t.Optional[t.Callable[[], None]]:
+    """The step's ONE metric collective (dist.allreduce_step_stats); ``None`` for a single process."""
+    if world <= 1:
+        module.last_global_scalars = None
+        return None
+
+    def exchange() -> None:
+        stats = vdist.allreduce_step_stats(module.last_confusion, module.last_step_scalars[0], module.last_depth_sums)
+        module.last_global_stats = stats
+        module.last_global_scalars = torch.stack(
+            [stats[k].to(torch.float32) for k in ("loss", "accuracy", "jaccard_index", "fbeta_score", "mae")])
+
+    return exchange
+
+
+def _same_shapes(batch: dict, static: dict) -> bool:
+    return all(k in static and batch[k].shape == static[k].shape and batch[k].dtype == static[k].dtype for k in batch)
 
 
 def run_pipe(
@@ -84,17 +112,43 @@ def run_pipe(
     exp=None,
     logger=None,
 ) -> t.Dict[str, t.Dict[str, list]]:
-    """Train for ``num_epochs``; returns the per-epoch train / val metric histories."""
+    """Train for ``num_epochs``; returns the per-epoch train / val metric histories.
+
+    On CUDA (``args.graph_step``, default on) the training step -- forward, fused losses / metrics, backward,
+    DDP's gradient all-reduce, the packed metric all-reduce and Adam -- replays as ONE CUDA graph
+    (``graph_step.GraphedTrainStep``); batches whose shape differs from the captured one (a short last batch)
+    run the same step eagerly.  ``args.sync_stats`` turns on the global-batch-exact mode: every
+    batch statistic (BatchNorm moments forward and backward, SILog moments) is all-reduced between the two
+    phases of its kernel pair, so an N-GPU step equals the single-GPU step on the concatenated batch."""
     rank, _, world = vdist.env_world()
     is_main = rank == 0
+    on_cuda = str(device).startswith("cuda")
     module.to(device)
-    if str(device).startswith("cuda"):
+    if on_cuda:
         module.model.to(memory_format=torch.channels_last)
     if world > 1:
+        if getattr(args, "sync_stats", False):
+            vdist.enable_stat_sync(module)
         vdist.wrap_data_parallel(module, torch.device(device).index)
-    optimizer = torch.optim.Adam(module.parameters(), lr=args.lr)
+    use_graph = on_cuda and bool(getattr(args, "graph_step", True))
+    if on_cuda:  # capturable Adam with a device-tensor learning rate: the same object serves graph and eager steps
+        from .graph_step import GraphedTrainStep, make_optimizer
+
+        optimizer = make_optimizer(module.parameters(), args.lr, device)
+    else:
+        optimizer = torch.optim.Adam(module.parameters(), lr=args.lr)
     scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, patience=2, factor=0.9)
     module.model.train()
+    exchange = _make_metric_exchange(module, world)
+    graphed = None
+
+    def eager_step(batch: dict) -> None:
+        optimizer.zero_grad(set_to_none=True)
+        loss = module.training_step(batch, batch_idx=0)
+        loss.backward()
+        if exchange is not None:
+            exchange()
+        optimizer.step()
 
     epoch_metrics = {"train": defaultdict(list), "val": defaultdict(list)}
     global_step = val_step = 0
@@ -104,13 +158,15 @@ def run_pipe(
         for batch in datamodule.train_dataloader():
             if world > 1:
                 batch = vdist.shard_batch(batch, rank, world)
-            optimizer.zero_grad(set_to_none=True)
             batch = module.transfer_batch_to_device(batch, device, 0)
-            loss = module.training_step(batch, batch_idx=0)
-            loss.backward()
-            optimizer.step()
-            if world > 1:
-                vdist.allreduce_step_stats(module.last_confusion, loss)
+            if use_graph and graphed is None:
+                # DDP rebuilds its buckets during the first iterations: capture after they have settled
+                graphed = GraphedTrainStep(module, optimizer, batch, warmup=11 if world > 1 else 3,
+                                           after_backward=exchange, preserve_state=True, record_step_outputs=True)
+            if graphed is not None and _same_shapes(batch, graphed.static):
+                graphed(batch)
+            else:
+                eager_step(batch)
             scal = _step_scalars_to_host(module, "train")
             if is_main:
                 _log(logger, exp, {f"step/train/{k}": v for k, v in scal.items()}, global_step)
@@ -133,6 +189,8 @@ def run_pipe(
                         batch = vdist.shard_batch(batch, rank, world)
                     batch = module.transfer_batch_to_device(batch, device, 0)
                     module.validation_step(batch, batch_idx=0)
+                    if exchange is not None:
+                        exchange()
                     scal = _step_scalars_to_host(module, "val")
                     val_loss += scal["loss"]
                     if is_main:
@@ -144,7 +202,9 @@ def run_pipe(
             if is_main:
                 print_metrics("epoch/val", val_epoch)
                 _log(logger, exp, {f"epoch/{k}": v for k, v in val_epoch.items()}, epoch)
-            scheduler.step(val_loss)  # the SUM of val batch losses, as in the reference
+            # the SUM of val batch losses, as in the reference; under data parallelism it is the sum of the
+            # GLOBAL losses, identical on every rank, so every replica takes the same plateau decision
+            scheduler.step(val_loss)
 
         last = epoch == getattr(args, "num_epochs", num_epochs) - 1
         if is_main and logger is not None and ((epoch + 1) % args.save_epoch_freq == 0 or last):

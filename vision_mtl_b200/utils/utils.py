@@ -26,6 +26,11 @@ def build_arg_parser() -> argparse.ArgumentParser:
     g.add_argument("--stitch_mode", choices=["reference_diag", "full_mix"], default="reference_diag")
     g.add_argument("--gate_precision", choices=["tc_3xtf32", "tc_tf32", "fp32_ffma"], default="tc_3xtf32")
     g.add_argument("--conv_tf32", action="store_true", help="let cuDNN use TF32 for the 3x3 convs")
+    g.add_argument("--no_graph_step", dest="graph_step", action="store_false",
+                   help="run the training step eagerly instead of replaying one CUDA graph per step")
+    g.add_argument("--sync_stats", action="store_true",
+                   help="data parallel: all-reduce every batch statistic (BatchNorm, SILog) so that an N-GPU "
+                        "step equals the single-GPU step on the concatenated batch")
     g = p.add_argument_group("data")
     g.add_argument("--dataset_name", choices=["cityscapes", "nyuv2", "synthetic"], default="cityscapes")
     g.add_argument("--batch_size", type=int, default=1)
