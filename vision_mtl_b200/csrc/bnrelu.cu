@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(kBnThreads)
 }
 
 // partial [nparts][2][C] -> mean, invstd, folded coefficients, running statistics
-__global__ void bn_fwd_finalize(const float* __restrict__ partial, int nparts, int64_t M, int C, float eps,
+__global__ void __launch_bounds__(kFinThreads)
+    bn_fwd_finalize(const float* __restrict__ partial, int nparts, int64_t M, int C, float eps,
                                 float momentum, int training, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float* __restrict__ running_mean,
                                 float* __restrict__ running_var, float* __restrict__ save_mean,
@@ -286,7 +287,8 @@ __global__ void __launch_bounds__(kBnThreads)
 // partial [nparts][2][C] -> dbeta, dgamma, c1 = dbeta/Mnorm, c2 = dgamma/Mnorm (0 in eval mode).
 // gmoments != NULL (global-batch statistics): the two sums come from there (all ranks, Mnorm = global rows) and
 // only c1 / c2 are produced -- dbeta / dgamma are the caller's LOCAL moments.
-__global__ void bn_bwd_finalize(const float* __restrict__ partial, int nparts, int64_t Mnorm, int C, int training,
+__global__ void __launch_bounds__(kFinThreads)
+    bn_bwd_finalize(const float* __restrict__ partial, int nparts, int64_t Mnorm, int C, int training,
                                 float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c12,
                                 const double* __restrict__ gmoments) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -305,7 +307,8 @@ __global__ void bn_bwd_finalize(const float* __restrict__ partial, int nparts, i
 }
 
 // partial [nparts][2][C] -> fp64 moments [2][C] (fixed-order second stage), what a data-parallel caller all-reduces
-__global__ void bn_moments_finalize(const float* __restrict__ partial, int nparts, int C, double* __restrict__ moments) {
+__global__ void __launch_bounds__(kFinThreads)
+    bn_moments_finalize(const float* __restrict__ partial, int nparts, int C, double* __restrict__ moments) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double a, b;
   block_colsum2(partial, nparts, 2 * (int64_t)C, c < C ? c : 0, C + (c < C ? c : 0), c < C, &a, &b);

@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(kEwThreads)
 
 // partial [nparts][2][N] -> mean, invstd, coefA/B, running statistics (nn.BatchNorm2d rules:
 // biased variance normalises, unbiased variance feeds running_var)
-__global__ void gate_fwd_stats_finalize(const float* __restrict__ partial, int nparts, int64_t M, int N,
+__global__ void __launch_bounds__(kFinThreads)
+    gate_fwd_stats_finalize(const float* __restrict__ partial, int nparts, int64_t M, int N,
                                         float eps, float momentum, int training,
                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                         float* __restrict__ running_mean, float* __restrict__ running_var,
@@ -137,7 +138,8 @@ __global__ void gate_fwd_stats_finalize(const float* __restrict__ partial, int n
 }
 
 // partial [nparts][2][N] -> fp64 moments [2][N]: what a data-parallel caller all-reduces between the two phases
-__global__ void gate_moments_finalize(const float* __restrict__ partial, int nparts, int N, double* __restrict__ moments) {
+__global__ void __launch_bounds__(kFinThreads)
+    gate_moments_finalize(const float* __restrict__ partial, int nparts, int N, double* __restrict__ moments) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double a, b;
   block_colsum2(partial, nparts, 2 * (int64_t)N, c < N ? c : 0, N + (c < N ? c : 0), c < N, &a, &b);
@@ -208,7 +210,8 @@ __global__ void __launch_bounds__(kEwThreads)
 }
 
 // also publishes the folded BN coefficients for phase B (same arithmetic as gate_bwd_stats_kernel)
-__global__ void gate_bwd_stats_finalize(const float* __restrict__ partial, int nparts, int64_t M, int N,
+__global__ void __launch_bounds__(kFinThreads)
+    gate_bwd_stats_finalize(const float* __restrict__ partial, int nparts, int64_t M, int N,
                                         int training, float* __restrict__ dgamma,
                                         float* __restrict__ dbeta, float* __restrict__ c1,
                                         float* __restrict__ c2, const float* __restrict__ gamma,
@@ -367,7 +370,8 @@ __global__ void __launch_bounds__(kFinThreads)
 
 // col_partial of the tensor-core pass 1 ([b][3][Nc], CTA b owns chunk b % nch) -> fp64 moments [2][N] = (sum du,
 // sum du zhat) of this replica
-__global__ void gate_bwd_tc_moments(const float* __restrict__ col_partial, int nparts, int nch, int N,
+__global__ void __launch_bounds__(kFinThreads)
+    gate_bwd_tc_moments(const float* __restrict__ col_partial, int nparts, int nch, int N,
                                     double* __restrict__ moments) {
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const int Nc = N / nch, per_chunk = nparts / nch;
@@ -427,7 +431,8 @@ __global__ void __launch_bounds__(kEwThreads)
 }
 
 // out[j] = fixed-order fp64 sum over nparts rows of length `len`
-__global__ void rows_sum_finalize(const float* __restrict__ partial, int nparts, int len,
+__global__ void __launch_bounds__(kFinThreads)
+    rows_sum_finalize(const float* __restrict__ partial, int nparts, int len,
                                   float* __restrict__ out) {
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   const double s = block_colsum(partial, nparts, (int64_t)len, j < len ? j : 0, j < len);

@@ -114,7 +114,8 @@ __device__ __forceinline__ void block_partial2(double a, double b, double* parti
   }
 }
 
-__global__ void ce_finalize(const double* __restrict__ partial, int nblocks, double* __restrict__ out,
+__global__ void __launch_bounds__(kFinThreads)
+    ce_finalize(const double* __restrict__ partial, int nblocks, double* __restrict__ out,
                             float* __restrict__ loss) {
   __shared__ double s_v[2];
   const int col = threadIdx.x & 31;
@@ -360,7 +361,8 @@ __global__ void __launch_bounds__(kLossThreads)
 }
 
 // dW[c][k] / db[c] = fixed-order fp64 sum of the block partials ([grid][CPAD][33])
-__global__ void head_ce_bwd_finalize(const float* __restrict__ partial, int nblocks, int CPAD, int C,
+__global__ void __launch_bounds__(kFinThreads)
+    head_ce_bwd_finalize(const float* __restrict__ partial, int nblocks, int CPAD, int C,
                                      float* __restrict__ dW, float* __restrict__ db) {
   const int i = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ROW = CPAD * (kHeadCin + 1);
@@ -766,7 +768,8 @@ __device__ __forceinline__ void silog_from_moments(double* __restrict__ out, flo
   }
 }
 
-__global__ void silog_finalize(const double* __restrict__ partial, int nblocks, int64_t P,
+__global__ void __launch_bounds__(kFinThreads)
+    silog_finalize(const double* __restrict__ partial, int nblocks, int64_t P,
                                double* __restrict__ out, float* __restrict__ scalars) {
   __shared__ double s[5];
   const int col = threadIdx.x & 31;
@@ -888,7 +891,8 @@ __global__ void __launch_bounds__(kLossThreads)
   }
 }
 
-__global__ void silog_bwd_finalize(const float* __restrict__ partial, int nblocks, int cin,
+__global__ void __launch_bounds__(kFinThreads)
+    silog_bwd_finalize(const float* __restrict__ partial, int nblocks, int cin,
                                    float* __restrict__ dw, float* __restrict__ db) {
   const int i = blockIdx.x * 32 + (threadIdx.x & 31);
   const double s = block_colsum(partial, nblocks, (int64_t)(cin + 1), i <= cin ? i : 0, i <= cin);

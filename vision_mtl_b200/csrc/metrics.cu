@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-__global__ void depth_err_finalize(const double* __restrict__ partial, int nblocks, int64_t P,
+__global__ void __launch_bounds__(kFinThreads)
+    depth_err_finalize(const double* __restrict__ partial, int nblocks, int64_t P,
                                    double* __restrict__ out) {
   const int col = threadIdx.x & 31;
   const double s = block_colsum(partial, nblocks, 3, col < 3 ? col : 0, col < 3);
