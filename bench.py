@@ -298,7 +298,9 @@ def run_workload(args, name: str, rank: int, local_rank: int, world: int, with_p
         with torch.cuda.stream(side):
             vdist.wrap_data_parallel(module, local_rank)
         torch.cuda.current_stream().wait_stream(side)
-    opt = torch.optim.Adam(module.parameters(), lr=args.lr, fused=True, capturable=use_graph)
+    from vision_mtl_b200.optim import Adam  # the library's one-launch multi-tensor Adam (capture-safe)
+
+    opt = Adam(module.parameters(), lr=args.lr)
     _phase(f"[{name}] model + optimizer built")
 
     host = make_batch(B, H, W, C, dataset, seed=11 + rank, pin=True)          # pinned host copy

@@ -311,6 +311,31 @@ int vmtl_depth_err_sums(const float* pred, const float* target, int64_t P, float
  * from an int64 [C,C] confusion matrix (lit_module.py:48-67 configuration). */
 int vmtl_seg_metrics(const int64_t* conf, int C, float* metrics, void* stream);
 
+/* Shape coverage of the fused heads: kind 0 = vmtl_head_ce_* (Cin, C), 1 = vmtl_head_silog_* (Cin),
+ * 2 = vmtl_ce_logits_* (C).  Returns 1 when the sm_100a kernels cover the shape (else the calls return
+ * VMTL_EUNSUPPORTED and the host side runs the 1x1 projection through cuDNN and the loss on its logits). */
+int vmtl_head_supported(int kind, int Cin, int C);
+
+/* ------------------------------------------------------------------------------------
+ * Multi-tensor Adam: torch.optim.Adam(params, lr) of training_lit.py:56 / lit_module.py:225-239,
+ * stepped at training_lit.py:97 -- every tensor of a parameter group in one launch (28 bytes per parameter).
+ * Arithmetic of torch's _single_tensor_adam (no amsgrad, not maximize; weight_decay is the L2 form g += wd * p).
+ *   params / grads / numel / moment_offset: HOST arrays with n_tensors entries -- device pointers of the fp32
+ *     parameter and gradient tensors, their element counts, and each tensor's element offset (a multiple of 4)
+ *     inside the flat moment buffers;
+ *   exp_avg / exp_avg_sq: DEVICE, flat fp32 moment buffers (16-byte aligned), updated in place;
+ *   lr_dev: DEVICE float[1] or NULL (then `lr`); hyper-parameters are doubles like torch's Python scalars (1 - beta
+ *     is formed in double before it is rounded to fp32); step_dev: DEVICE float[1], steps taken so far, incremented by the
+ *     call; ticket: DEVICE uint32[1], must be zero before the first call and is left zero.
+ * Tables travel in the kernel parameter space (vmtl_adam_max_tensors_per_launch tensors per launch), so the call is
+ * capture-safe without any host buffer outliving it.
+ * ---------------------------------------------------------------------------------- */
+int vmtl_adam_max_tensors_per_launch(void);
+int vmtl_adam_step(const void* const* params, const void* const* grads, const int64_t* numel,
+                   const int64_t* moment_offset, int n_tensors, float* exp_avg, float* exp_avg_sq,
+                   const float* lr_dev, double lr, float* step_dev, unsigned int* ticket, double beta1, double beta2,
+                   double eps, double weight_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

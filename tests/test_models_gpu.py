@@ -144,6 +144,38 @@ def test_mtan_cityscapes_shape_vs_oracle_forward():
             assert rel_err(b, p[k]) <= TOL, k
 
 
+def test_mtan_reference_default_width_vs_oracle():
+    """``MTANMiniUnet`` with the reference's DEFAULT constructor arguments (mtan_model.py:258-265:
+    ``encoder_first_channel=64`` -> gates up to N = 512, heads on 64 input channels -- outside the fused head
+    kernels' Cin = 32): the step must run (projection through cuDNN, loss kernels on its logits) and match the
+    CPU oracle; head and first-layer gradients against the oracle's autograd."""
+    from vision_mtl_b200.lit_module import MTLModule
+    from vision_mtl_b200.models.mtan_model import MTANMiniUnet
+
+    C, B, H, W = 19, 2, 32, 64
+    net = MTANMiniUnet(3, {"depth": 1, "segm": C})
+    sd = FX.fill_state_dict(net.state_dict(), salt=4)
+    net.load_state_dict(sd)
+    batch = FX.image_batch(B, H, W, C, "default-width")
+    p = {k: v.clone().requires_grad_(v.dtype == torch.float32 and "running" not in k) for k, v in sd.items()}
+    raw = TP.mtan_forward(p, batch["img"], training=True)
+    res = TP.step_losses_and_metrics(raw, batch["mask"], batch["depth"], C)
+    res["loss"].backward()
+    net.to(dev()).to(memory_format=torch.channels_last).train()
+    module = MTLModule(net, num_classes=C, device=dev())
+    out = module.fused_losses_and_metrics(*[to_dev(batch)[k] for k in ("img", "mask", "depth")], want_preds=True)
+    out["loss"].backward()
+    assert rel_err(out["loss_segm"], res["loss_segm"]) <= TOL
+    assert rel_err(out["loss_depth"], res["loss_depth"]) <= TOL
+    assert rel_err(out["mae"], torch.tensor(res["mae"])) <= TOL
+    assert rel_err(out["depth_predictions"], res["depth_predictions"]) <= TOL
+    assert int(module.last_confusion.sum()) == B * H * W
+    assert int((out["segm_predictions"].cpu().long() != res["segm_predictions"]).sum()) <= 4
+    named = dict(net.named_parameters())
+    for k in ("map_tasks_to_heads.segm.weight", "map_tasks_to_heads.segm.bias", "map_tasks_to_heads.depth.weight"):
+        assert rel_err(named[k].grad, p[k].grad) <= 2e-4, k
+
+
 @pytest.mark.parametrize("cw", [True, False])
 @pytest.mark.parametrize("mode", ["reference_diag", "full_mix"])
 def test_csnet_vs_oracle_same_device(cw, mode):

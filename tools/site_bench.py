@@ -5,7 +5,7 @@ CUDA events around the replay (device time of all launches of the call, no host 
 flush (write of a 256 MiB buffer) before every replay and between forward and backward, and reported
 as algorithmic GB/s against MEASURED_PEAKS.json.  Also the target command for the ncu captures kept under profiles/.
 
-    python tools/site_bench.py [--iters 5] [--only gate|xstitch|heads|metrics] [--once] [--json out.json]
+    python tools/site_bench.py [--iters 5] [--only gate|bn|xstitch|heads|metrics] [--once] [--json out.json]
 """
 from __future__ import annotations
 
@@ -115,7 +115,44 @@ def main():
                 hh.grad = ss.grad = None
                 y.backward(dy)
 
-            timed("gate", f"{site} N={N} M={M}", 4 * M * (128 + 4 * N), 4 * M * (2 * 128 + 7 * N), fwd, bwd)
+            # SURVEY 8(d) algorithmic bytes (what the kernels issue is ops.gate_bytes(...)[1])
+            nb_f, nb_b = ops.gate_bytes(M, 128, N, True, False)[0], ops.gate_bytes(M, 128, N, True, True)[0]
+            timed("gate", f"{site} N={N} M={M}", nb_f, nb_b, fwd, bwd)
+            if args.profile_set:
+                continue
+            # the same gate with the hidden layer folded in: c = conv1 output, h = relu(bn1(c)) never materialised
+            # (statistics pass over c + gate forward; gate backward + BatchNorm/ReLU backward over (dh, c))
+            cc = cl(B, 128, h, w).requires_grad_(True)
+            bn1 = torch.nn.BatchNorm2d(128).to(dev)
+
+            def fwd_f():
+                return ops.attention_gate_folded(cc, bn1, ss, conv, bn, args.precision)
+
+            def bwd_f(y):
+                cc.grad = ss.grad = None
+                y.backward(dy)
+
+            timed("gate_folded", f"{site} N={N} M={M}", nb_f + 4 * M * 128, nb_b + 4 * M * 128 * 5, fwd_f, bwd_f)
+
+    if args.only in ("", "bn") and not args.profile_set:
+        # DoubleConv / attention conv3 BatchNorm + ReLU (+ 2x2 max-pool) sites of the MTAN network, batch statistics
+        for Cc, down, pool in ((32, 1, False), (64, 2, False), (128, 4, False), (256, 8, False), (32, 1, True), (64, 2, True)):
+            h, w = H // down, W // down
+            M = B * h * w
+            x = cl(B, Cc, h, w).requires_grad_(True)
+            bnm = torch.nn.BatchNorm2d(Cc).to(dev)
+            dyb = cl(B, Cc, h // 2, w // 2) if pool else cl(B, Cc, h, w)
+            out_rows = M // 4 if pool else M
+
+            def fwd_b():
+                return ops.batch_norm_relu(x, bnm, True, pool)
+
+            def bwd_b(y):
+                x.grad = None
+                y.backward(dyb)
+
+            timed("bnrelu_pool" if pool else "bnrelu", f"C={Cc} M={M}", 4 * Cc * (2 * M + out_rows),
+                  4 * Cc * (2 * (M + out_rows) + M), fwd_b, bwd_b)
 
     if args.only in ("", "xstitch"):
         for Cc, h, w in (XS_SITES[-1:] if args.profile_set else XS_SITES):

@@ -82,18 +82,17 @@ __global__ void __launch_bounds__(kBnThreads)
   if (m.active) {
     const int64_t step = (int64_t)gridDim.x * m.rows;
     int64_t p = (int64_t)blockIdx.x * m.rows + m.r;
-    for (; p + step < M; p += 2 * step) {  // two rows in flight
-      const float4 v = bn_ld(x, p * C4 + m.g), w = bn_ld(x, (p + step) * C4 + m.g);
-      acc[0].x += v.x + w.x; acc[0].y += v.y + w.y; acc[0].z += v.z + w.z; acc[0].w += v.w + w.w;
-      acc[1].x = fmaf(v.x, v.x, fmaf(w.x, w.x, acc[1].x)); acc[1].y = fmaf(v.y, v.y, fmaf(w.y, w.y, acc[1].y));
-      acc[1].z = fmaf(v.z, v.z, fmaf(w.z, w.z, acc[1].z)); acc[1].w = fmaf(v.w, v.w, fmaf(w.w, w.w, acc[1].w));
-    }
-    for (; p < M; p += step) {
-      const float4 v = bn_ld(x, p * C4 + m.g);
+    auto add = [&](const float4& v) {
       acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
       acc[1].x = fmaf(v.x, v.x, acc[1].x); acc[1].y = fmaf(v.y, v.y, acc[1].y);
       acc[1].z = fmaf(v.z, v.z, acc[1].z); acc[1].w = fmaf(v.w, v.w, acc[1].w);
+    };
+    for (; p + 3 * step < M; p += 4 * step) {  // four rows in flight (a read-only pass has nothing else to overlap)
+      const float4 v0 = bn_ld(x, p * C4 + m.g), v1 = bn_ld(x, (p + step) * C4 + m.g),
+                   v2 = bn_ld(x, (p + 2 * step) * C4 + m.g), v3 = bn_ld(x, (p + 3 * step) * C4 + m.g);
+      add(v0); add(v1); add(v2); add(v3);
     }
+    for (; p < M; p += step) add(bn_ld(x, p * C4 + m.g));
   }
   bn_block_reduce<2>(acc, m, C4, partial + (int64_t)blockIdx.x * 8 * C4);
 }
@@ -156,11 +155,16 @@ __global__ void __launch_bounds__(kBnThreads)
   const float4 A = bn_c4(coef, m.g), B = bn_c4(coef + 4 * C4, m.g);
   const int64_t step = (int64_t)gridDim.x * m.rows;
   int64_t p = (int64_t)blockIdx.x * m.rows + m.r;
-  for (; p + step < M; p += 2 * step) {
-    const int64_t i0 = p * C4 + m.g, i1 = (p + step) * C4 + m.g;
-    const float4 v0 = bn_ld(x, i0), v1 = bn_ld(x, i1);
-    bn_st(y, i0, bn_act<RELU>(v0, A, B));
-    bn_st(y, i1, bn_act<RELU>(v1, A, B));
+  for (; p + 3 * step < M; p += 4 * step) {
+    int64_t i[4];
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      i[k] = (p + k * step) * C4 + m.g;
+      v[k] = bn_ld(x, i[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bn_st(y, i[k], bn_act<RELU>(v[k], A, B));
   }
   for (; p < M; p += step) {
     const int64_t i0 = p * C4 + m.g;

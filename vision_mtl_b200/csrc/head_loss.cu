@@ -1104,6 +1104,16 @@ static int silog_lpp(int Cin) {
   }
 }
 
+// kind 0: vmtl_head_ce_* (Cin, C); kind 1: vmtl_head_silog_* (Cin); kind 2: vmtl_ce_logits_* (C).  1 = covered.
+extern "C" int vmtl_head_supported(int kind, int Cin, int C) {
+  switch (kind) {
+    case 0: return Cin == kHeadCin && C >= 1 && cpad_for(C) != 0;
+    case 1: return silog_lpp(Cin) != 0;
+    case 2: return C >= 1 && cpad_for(C) != 0;
+    default: return 0;
+  }
+}
+
 extern "C" int vmtl_head_silog_fwd(const float* feat, const float* w, const float* b, const float* target,
                                    int64_t P, int Cin, float min_depth, double* out, float* scalars,
                                    float* pred, void* workspace, size_t workspace_bytes, void* stream) {

@@ -24,11 +24,13 @@ import torch
 from .lit_module import STEP_KEYS, MTLModule
 
 
-def make_optimizer(params, lr: float, device) -> torch.optim.Adam:
-    """Adam as the reference builds it (training_lit.py:56), capture-safe: fused + capturable, with the
-    learning rate held in a device tensor so schedulers (which ``fill_`` it) act on graph replays."""
-    return torch.optim.Adam(params, lr=torch.tensor(float(lr), dtype=torch.float32, device=device),
-                            fused=True, capturable=True)
+def make_optimizer(params, lr: float, device) -> torch.optim.Optimizer:
+    """Adam as the reference builds it (training_lit.py:56) on the library's multi-tensor kernel
+    (``optim.Adam``: one launch per step, device-side step counter), with the learning rate held in a device
+    tensor so schedulers (which ``fill_`` it) act on graph replays."""
+    from .optim import Adam
+
+    return Adam(params, lr=torch.tensor(float(lr), dtype=torch.float32, device=device))
 
 
 class GraphedTrainStep:

@@ -79,7 +79,8 @@ class MTLModule(nn.Module):
         inner = self._inner_model()
         if hasattr(inner, "forward_features"):
             # MTAN: the 1x1 heads are fused with their losses, logits never reach HBM
-            feats = self.model(img, features_only=True)
+            with ops.deferred_batch_counters():  # one multi-tensor add for every BatchNorm step counter
+                feats = self.model(img, features_only=True)
             heads = inner.map_tasks_to_heads
             loss_segm, pred = ops.head_cross_entropy(feats["segm"], heads["segm"].weight, heads["segm"].bias,
                                                      gt_mask, self.ignore_index, conf, True)
@@ -87,7 +88,8 @@ class MTLModule(nn.Module):
                 feats["depth"], heads["depth"].weight, heads["depth"].bias, gt_depth,
                 self.depth_criterion.min_depth, want_preds, return_moments=True)
         else:
-            raw = self.model(img)
+            with ops.deferred_batch_counters():
+                raw = self.model(img)
             loss_segm, pred = ops.cross_entropy_logits(raw["segm"], gt_mask, self.ignore_index, conf, True)
             silog, mae, absrel, dpred, moments = ops.head_silog(
                 raw["depth"], None, None, gt_depth, self.depth_criterion.min_depth, want_preds, return_moments=True)
@@ -182,7 +184,13 @@ class MTLModule(nn.Module):
     def configure_optimizers(self):
         if self.optim_dict:
             return self.optim_dict
-        optimizer = torch.optim.Adam(params=self.parameters(), lr=self.hparams["lr"])
+        params = list(self.parameters())
+        if params and params[0].is_cuda:  # the library's one-launch multi-tensor Adam (same arithmetic, same state_dict)
+            from .optim import Adam
+
+            optimizer = Adam(params, lr=self.hparams["lr"])
+        else:
+            optimizer = torch.optim.Adam(params=params, lr=self.hparams["lr"])
         scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer=optimizer, patience=5, factor=0.95)
         return {"optimizer": optimizer,
                 "lr_scheduler": {"scheduler": scheduler, "interval": "epoch", "monitor": "train_loss"}}

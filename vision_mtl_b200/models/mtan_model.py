@@ -51,8 +51,7 @@ class _GatedAttention(nn.Module):
         hidden = self._bn_relu(squeezed, self.bn1, self.relu1)
         bn = self.bn2
         use_batch_stats = bn.training or bn.running_mean is None
-        if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+        ops._bump_batch_counter(bn)
         momentum = 0.1 if bn.momentum is None else bn.momentum
         return ops.attention_gate(
             hidden, shared, self.conv2.weight, self.conv2.bias, bn.weight, bn.bias,

@@ -314,6 +314,41 @@ def cross_stitch_cat(skips: Sequence[torch.Tensor], xs: Sequence[torch.Tensor], 
 # --------------------------------------------------------------------------------------
 # BatchNorm2d (+ ReLU, + 2x2 max-pool)
 # --------------------------------------------------------------------------------------
+class _Counters:
+    pending: Optional[dict] = None  # id(counter) -> [counter, increments] while deferred_batch_counters() is active
+
+
+@contextmanager
+def deferred_batch_counters():
+    """Collect the ``num_batches_tracked += 1`` of every BatchNorm call made inside the block and apply them with
+    ONE multi-tensor add at exit (the reference bumps each counter with its own kernel: ~100 launches per MTAN
+    forward).  Only for modules with a fixed momentum -- a cumulative average needs its count at call time."""
+    if _Counters.pending is not None:  # nested: the outermost block flushes
+        yield
+        return
+    _Counters.pending = {}
+    try:
+        yield
+    finally:
+        pending, _Counters.pending = _Counters.pending, None
+        once = [c for c, n in pending.values() if n == 1]
+        if once:
+            torch._foreach_add_(once, 1)
+        for c, n in pending.values():
+            if n > 1:
+                c.add_(n)
+
+
+def _bump_batch_counter(bn) -> None:
+    if not (bn.training and bn.track_running_stats and bn.num_batches_tracked is not None):
+        return
+    if _Counters.pending is not None and bn.momentum is not None:
+        slot = _Counters.pending.setdefault(id(bn.num_batches_tracked), [bn.num_batches_tracked, 0])
+        slot[1] += 1
+    else:
+        bn.num_batches_tracked.add_(1)
+
+
 def _bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, pool, y, stats, world):
     """Statistics + finalize (+ apply when ``y`` is given) of one BatchNorm; ``world > 1`` all-reduces the moments."""
     B, C, H, W = x.shape
@@ -417,8 +452,7 @@ def batch_norm_relu(x: torch.Tensor, bn: torch.nn.BatchNorm2d, relu: bool = True
     """``maxpool2(relu(bn(x)))`` (each optional) with ``bn``'s parameters, mode and running statistics
     (updated in place like ``nn.BatchNorm2d.forward``)."""
     use_batch_stats = bn.training or bn.running_mean is None
-    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+    _bump_batch_counter(bn)
     if bn.momentum is None:  # cumulative moving average
         momentum = 1.0 / float(bn.num_batches_tracked) if bn.training and bn.track_running_stats else 0.0
     else:
@@ -594,8 +628,7 @@ class FoldedGateFunction(torch.autograd.Function):
 def _bn_mode(bn):
     """(use batch statistics, momentum) of an ``nn.BatchNorm2d`` call; bumps ``num_batches_tracked``."""
     use_batch_stats = bn.training or bn.running_mean is None
-    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+    _bump_batch_counter(bn)
     if bn.momentum is None:
         momentum = 1.0 / float(bn.num_batches_tracked) if bn.training and bn.track_running_stats else 0.0
     else:
@@ -684,7 +717,15 @@ class HeadCEFunction(torch.autograd.Function):
 
 def head_cross_entropy(feat, weight, bias, target, ignore_index: int = -100,
                        conf: Optional[torch.Tensor] = None, want_pred: bool = True):
-    """Returns (loss, pred uint8 [B,H,W]); ``conf`` (int64 [C,C]) is accumulated in place."""
+    """Returns (loss, pred uint8 [B,H,W]); ``conf`` (int64 [C,C]) is accumulated in place.
+
+    Head shapes outside the fused kernels' set (Cin != 32, e.g. the reference-default ``encoder_first_channel=64``
+    MTAN) run the 1x1 projection through cuDNN and the loss kernels on its logits -- still on the GPU, still one
+    pass over the logits; more than 32 classes raise ``VmtlError``."""
+    Cin, C = feat.shape[1], weight.shape[0]
+    if not _lib.load().vmtl_head_supported(0, Cin, C):
+        logits = torch.nn.functional.conv2d(_nhwc(feat), weight, bias)
+        return cross_entropy_logits(logits, target, ignore_index, conf, want_pred)
     return HeadCEFunction.apply(feat, weight, bias, target, ignore_index, conf, want_pred)
 
 
@@ -813,6 +854,9 @@ def head_silog(feat, weight, bias, target, min_depth: float = 1e-3, want_pred: b
     """Returns (silog, mae, abs_rel, pred [B,H,W,1]); only silog carries a gradient.  ``return_moments``
     appends the float64 [8] moment vector of ``vmtl_head_silog_fwd`` ({n, sum g, sum g^2, sum|p-t|,
     sum|p-t|/t, mean g, D, P}): what a data-parallel step all-reduces."""
+    if weight is not None and not _lib.load().vmtl_head_supported(1, feat.shape[1], 1):
+        # projection widths the fused kernel does not cover: cuDNN 1x1 conv, then the loss on the depth logit
+        feat, weight, bias = torch.nn.functional.conv2d(_nhwc(feat), weight, bias), None, None
     scalars, pred, moments = HeadSilogFunction.apply(feat, weight, bias, target, min_depth, want_pred)
     out = (scalars[0], scalars[1].detach(), scalars[2].detach(), pred)
     return out + (moments,) if return_moments else out
