@@ -269,6 +269,38 @@ def test_head_silog(B, H, W, cin):
         assert_rel(bd.grad, head.bias.grad, what="db")
 
 
+def test_silog_loss_module_mask_and_saturation():
+    """``SILogLoss.forward`` on sigmoid predictions (the API path of losses.py:14-36): explicit ``mask`` argument
+    (losses.py:29-33), and saturated logits -- fp32 sigmoid(-100) is a denormal the reference still takes the log of."""
+    from vision_mtl_b200 import ops
+    from vision_mtl_b200.losses import SILogLoss
+
+    g = torch.Generator().manual_seed(5)
+    B, H, W = 2, 12, 20
+    target = torch.rand(B, H, W, 1, generator=g) * 0.5 + 0.01
+    mask = torch.rand(B, H, W, 1, generator=g) < 0.6
+    z = torch.randn(B, H, W, 1, generator=g)
+    pr = torch.sigmoid(z).requires_grad_(True)
+    gref = torch.log(pr[mask]) - torch.log(target[mask])  # the reference's arithmetic
+    loss_r = 10 * torch.sqrt(torch.var(gref) + 0.15 * torch.mean(gref) ** 2)
+    loss_r.backward()
+    pd = torch.sigmoid(z).to(dev()).requires_grad_(True)
+    loss = SILogLoss()(pd, target.to(dev()), mask=mask.to(dev()))
+    loss.backward()
+    assert_rel(loss, loss_r, what="masked silog")
+    assert_rel(pd.grad, pr.grad, what="masked silog d/dpred")
+    # saturation: logits down to -100 (sigmoid flushes to 0 in the fast form) and up to +40 (sigmoid == 1.0f)
+    zs = torch.linspace(-100.0, 40.0, B * H * W).reshape(B, 1, H, W)
+    ts = torch.full((B, H, W, 1), 0.25)
+    gs = torch.nn.functional.logsigmoid(zs.double()).reshape(-1) - torch.log(ts.double()).reshape(-1)
+    ref = 10 * torch.sqrt(torch.var(gs) + 0.15 * torch.mean(gs) ** 2)
+    zd = zs.to(dev()).requires_grad_(True)
+    silog, _, _, _ = ops.head_silog(zd, None, None, ts.to(dev()), 1e-3, False)
+    silog.backward()
+    assert torch.isfinite(silog) and torch.isfinite(zd.grad).all()
+    assert_rel(silog, ref.float(), what="saturated silog")
+
+
 # ----------------------------------------------------------------------------- MTAN gate
 GATE_SHAPES = [(2, 32, 16, 24), (1, 64, 9, 13), (2, 128, 8, 8), (1, 256, 4, 8), (4, 32, 64, 64),
                (3, 128, 20, 24), (2, 256, 12, 10), (1, 192, 16, 20),

@@ -70,7 +70,11 @@ def test_bn_global_statistics_equal_whole_batch(C, H, W, relu, pool):
     gamma = (torch.rand(C, generator=g) + 0.5).to(dev)
     beta = torch.randn(C, generator=g).to(dev)
     dy_shape = (4, C, H // 2, W // 2) if pool else (4, C, H, W)
-    dy = _cl(torch.randn(dy_shape, generator=g).to(dev))
+    # a non-zero mean (and a correlation with x) keeps the batch terms c1 = sum(g)/M, c2 = sum(g xhat)/M away from
+    # zero: with centred random gradients a wrong normalisation of those terms would go unnoticed
+    dy = _cl((torch.randn(dy_shape, generator=g) + 0.7).to(dev))
+    if not pool:
+        dy = _cl(dy + 0.2 * x)
 
     def run(xs, dys, rm, rv):
         xs = xs.clone().requires_grad_(True)
@@ -115,7 +119,9 @@ def test_gate_global_statistics_equal_whole_batch(N, H, W, folded):
     g = torch.Generator().manual_seed(9)
     h = _cl(torch.randn(4, K, H, W, generator=g).to(dev))
     s = _cl(torch.randn(4, N, H, W, generator=g).to(dev))
-    dy = _cl(torch.randn(4, N, H, W, generator=g).to(dev))
+    # non-zero-mean s and dy: the batch terms c1 / c2 of the gate's BatchNorm backward stay away from zero
+    s = _cl(s + 0.8)
+    dy = _cl((torch.randn(4, N, H, W, generator=g) + 0.6).to(dev))
     Wt = (torch.randn(N, K, 1, 1, generator=g) / K ** 0.5).to(dev)
     bias = torch.randn(N, generator=g).to(dev)
     g2, b2 = (torch.rand(N, generator=g) + 0.5).to(dev), torch.randn(N, generator=g).to(dev)

@@ -77,6 +77,7 @@ __device__ __forceinline__ void bn_block_reduce(const float4 (&acc)[NV], const B
 // ---- forward --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBnThreads)
     bn_stats_kernel(const float* __restrict__ x, int64_t M, int C4, float* __restrict__ partial) {
+  pdl_trigger();  // the finalize kernel may be scheduled while this one drains
   const BnMap m = bn_map(C4);
   float4 acc[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
   if (m.active) {
@@ -105,6 +106,8 @@ __global__ void __launch_bounds__(kFinThreads)
                                 float* __restrict__ running_var, float* __restrict__ save_mean,
                                 float* __restrict__ save_invstd, float* __restrict__ coef /* [2][C] */,
                                 const double* __restrict__ gmoments /* NULL, or global [2][C] over M rows */) {
+  pdl_wait();     // statistics pass complete, its partials visible
+  pdl_trigger();  // the apply pass may be scheduled while this block reduces
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double s = 0.0, q = 0.0;
   if (training && !gmoments)  // block-uniform branch: the reduction synchronises
@@ -150,6 +153,7 @@ template <bool RELU>
 __global__ void __launch_bounds__(kBnThreads)
     bn_apply_kernel(const float* __restrict__ x, int64_t M, int C4, const float* __restrict__ coef,
                     float* __restrict__ y) {
+  pdl_wait();  // coefficients of the finalize kernel
   const BnMap m = bn_map(C4);
   if (!m.active) return;
   const float4 A = bn_c4(coef, m.g), B = bn_c4(coef + 4 * C4, m.g);
@@ -181,6 +185,7 @@ template <bool RELU>
 __global__ void __launch_bounds__(kBnThreads)
     bn_pool_apply_kernel(const float* __restrict__ x, int B, int H, int W, int C4, const float* __restrict__ coef,
                          float* __restrict__ y) {
+  pdl_wait();
   const BnMap m = bn_map(C4);
   if (!m.active) return;
   const float4 A = bn_c4(coef, m.g), Bc = bn_c4(coef + 4 * C4, m.g);
@@ -209,6 +214,7 @@ __global__ void __launch_bounds__(kBnThreads)
     bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x, int64_t M, int C4,
                         const float* __restrict__ coef, const float* __restrict__ mean,
                         const float* __restrict__ invstd, float* __restrict__ partial) {
+  pdl_trigger();
   const BnMap m = bn_map(C4);
   float4 acc[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
   if (m.active) {
@@ -258,6 +264,7 @@ __global__ void __launch_bounds__(kBnThreads)
     bn_pool_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x, int B, int H, int W, int C4,
                              const float* __restrict__ coef, const float* __restrict__ mean,
                              const float* __restrict__ invstd, float* __restrict__ partial) {
+  pdl_trigger();
   const BnMap m = bn_map(C4);
   float4 acc[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
   if (m.active) {
@@ -295,6 +302,8 @@ __global__ void __launch_bounds__(kFinThreads)
     bn_bwd_finalize(const float* __restrict__ partial, int nparts, int64_t Mnorm, int C, int training,
                                 float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c12,
                                 const double* __restrict__ gmoments) {
+  pdl_wait();
+  pdl_trigger();
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double sb = 0.0, sg = 0.0;
   if (!gmoments) block_colsum2(partial, nparts, 2 * (int64_t)C, c < C ? c : 0, C + (c < C ? c : 0), c < C, &sb, &sg);
@@ -326,6 +335,7 @@ __global__ void __launch_bounds__(kBnThreads)
     bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, int64_t M, int C4,
                         const float* __restrict__ coef, const float* __restrict__ mean,
                         const float* __restrict__ invstd, const float* __restrict__ c12, float* __restrict__ dx) {
+  pdl_wait();
   const BnMap m = bn_map(C4);
   if (!m.active) return;
   const float4 A = bn_c4(coef, m.g), B = bn_c4(coef + 4 * C4, m.g), mu = bn_c4(mean, m.g), rs = bn_c4(invstd, m.g);
@@ -349,6 +359,7 @@ __global__ void __launch_bounds__(kBnThreads)
                              const float* __restrict__ coef, const float* __restrict__ mean,
                              const float* __restrict__ invstd, const float* __restrict__ c12,
                              float* __restrict__ dx) {
+  pdl_wait();
   const BnMap m = bn_map(C4);
   if (!m.active) return;
   const float4 A = bn_c4(coef, m.g), Bc = bn_c4(coef + 4 * C4, m.g), mu = bn_c4(mean, m.g), rs = bn_c4(invstd, m.g);
@@ -446,9 +457,10 @@ static int bnrelu_fwd_impl(const float* x, const float* gamma, const float* beta
     bn_stats_kernel<<<nparts, kBnThreads, 0, st>>>(x, M, C4, partial);
     if ((rc = launch_status()) != VMTL_OK) return rc;
   }
-  bn_fwd_finalize<<<(C + 31) / 32, kFinThreads, 0, st>>>(partial, nparts, phase == 2 ? Mstat : M, C, eps, momentum,
-                                                         training, gamma, beta, running_mean, running_var, save_mean,
-                                                         save_invstd, coef, phase == 2 ? moments : nullptr);
+  // finalize and apply are programmatic dependents (vmtl_common.cuh): each is scheduled while its predecessor drains
+  launch_pdl(bn_fwd_finalize, (C + 31) / 32, kFinThreads, 0, st, (const float*)partial, nparts, phase == 2 ? Mstat : M, C, eps,
+             momentum, training, gamma, beta, running_mean, running_var, save_mean, save_invstd, coef,
+             (const double*)(phase == 2 ? moments : nullptr));
   if ((rc = launch_status()) != VMTL_OK) return rc;
   if (!y) return VMTL_OK;
   if (pool) {
@@ -456,19 +468,19 @@ static int bnrelu_fwd_impl(const float* x, const float* gamma, const float* beta
     if (Mo < 1) return VMTL_EINVAL;
     if (relu) {
       const int grid = bn_grid(Mo, C, blocks_per_sm(bn_pool_apply_kernel<true>, kBnThreads, 0, 8));
-      bn_pool_apply_kernel<true><<<grid, kBnThreads, 0, st>>>(x, B, H, W, C4, coef, y);
+      launch_pdl(bn_pool_apply_kernel<true>, grid, kBnThreads, 0, st, x, B, H, W, C4, (const float*)coef, y);
     } else {
       const int grid = bn_grid(Mo, C, blocks_per_sm(bn_pool_apply_kernel<false>, kBnThreads, 0, 8));
-      bn_pool_apply_kernel<false><<<grid, kBnThreads, 0, st>>>(x, B, H, W, C4, coef, y);
+      launch_pdl(bn_pool_apply_kernel<false>, grid, kBnThreads, 0, st, x, B, H, W, C4, (const float*)coef, y);
     }
     return launch_status();
   }
   if (relu) {
     const int grid = bn_grid(M, C, blocks_per_sm(bn_apply_kernel<true>, kBnThreads, 0, 8));
-    bn_apply_kernel<true><<<grid, kBnThreads, 0, st>>>(x, M, C4, coef, y);
+    launch_pdl(bn_apply_kernel<true>, grid, kBnThreads, 0, st, x, M, C4, (const float*)coef, y);
   } else {
     const int grid = bn_grid(M, C, blocks_per_sm(bn_apply_kernel<false>, kBnThreads, 0, 8));
-    bn_apply_kernel<false><<<grid, kBnThreads, 0, st>>>(x, M, C4, coef, y);
+    launch_pdl(bn_apply_kernel<false>, grid, kBnThreads, 0, st, x, M, C4, (const float*)coef, y);
   }
   return launch_status();
 }
@@ -532,20 +544,22 @@ static int bnrelu_bwd_impl(const float* dy, const float* x, const float* coef, c
     bn_moments_finalize<<<(C + 31) / 32, kFinThreads, 0, st>>>(partial, nparts, C, moments);
     return launch_status();
   }
-  bn_bwd_finalize<<<(C + 31) / 32, kFinThreads, 0, st>>>(partial, nparts, phase == 2 ? Mstat : M, C, training, dgamma,
-                                                         dbeta, c12, phase == 2 ? moments : nullptr);
+  launch_pdl(bn_bwd_finalize, (C + 31) / 32, kFinThreads, 0, st, (const float*)partial, nparts, phase == 2 ? Mstat : M, C,
+             training, dgamma, dbeta, c12, (const double*)(phase == 2 ? moments : nullptr));
   if ((rc = launch_status()) != VMTL_OK) return rc;
   if (!dx) return VMTL_OK;
-  int unused;
-  (void)unused;
+#define VMTL_BN_LAUNCH_PDL(KERN, ROWS, ...)                                                \
+  launch_pdl(KERN, bn_grid(ROWS, C, blocks_per_sm(KERN, kBnThreads, 0, 8)), kBnThreads, 0, st, __VA_ARGS__)
+  const float* c12c = c12;
   if (pool) {
     const int64_t Mc = (int64_t)B * ((H + 1) / 2) * ((W + 1) / 2);
-    if (relu) VMTL_BN_LAUNCH(bn_pool_bwd_apply_kernel<true>, Mc, dy, x, B, H, W, C4, coef, save_mean, save_invstd, c12, dx);
-    else VMTL_BN_LAUNCH(bn_pool_bwd_apply_kernel<false>, Mc, dy, x, B, H, W, C4, coef, save_mean, save_invstd, c12, dx);
+    if (relu) VMTL_BN_LAUNCH_PDL(bn_pool_bwd_apply_kernel<true>, Mc, dy, x, B, H, W, C4, coef, save_mean, save_invstd, c12c, dx);
+    else VMTL_BN_LAUNCH_PDL(bn_pool_bwd_apply_kernel<false>, Mc, dy, x, B, H, W, C4, coef, save_mean, save_invstd, c12c, dx);
   } else {
-    if (relu) VMTL_BN_LAUNCH(bn_bwd_apply_kernel<true>, M, dy, x, M, C4, coef, save_mean, save_invstd, c12, dx);
-    else VMTL_BN_LAUNCH(bn_bwd_apply_kernel<false>, M, dy, x, M, C4, coef, save_mean, save_invstd, c12, dx);
+    if (relu) VMTL_BN_LAUNCH_PDL(bn_bwd_apply_kernel<true>, M, dy, x, M, C4, coef, save_mean, save_invstd, c12c, dx);
+    else VMTL_BN_LAUNCH_PDL(bn_bwd_apply_kernel<false>, M, dy, x, M, C4, coef, save_mean, save_invstd, c12c, dx);
   }
+#undef VMTL_BN_LAUNCH_PDL
 #undef VMTL_BN_LAUNCH
   return launch_status();
 }

@@ -661,8 +661,12 @@ struct SilogAcc {
 };
 
 __device__ __forceinline__ float sigmoid_fast(float u) { return __fdividef(1.f, 1.f + fast_ex2(-u * kLog2e)); }
-// log(p) - log(t) through MUFU lg2
-__device__ __forceinline__ float log_ratio(float p, float t) { return (fast_lg2(p) - fast_lg2(t)) * kLn2; }
+// log(p) - log(t) through MUFU lg2, p = sigmoid(z).  Below z = -80 the fast sigmoid flushes to 0 (its exponential
+// overflows) while the reference's stays a finite denormal with log p = z to 1e-35: take z there.
+__device__ __forceinline__ float log_ratio(float z, float p, float t) {
+  const float lt = fast_lg2(t);
+  return z < -80.f ? fmaf(-lt, kLn2, z) : (fast_lg2(p) - lt) * kLn2;
+}
 
 __device__ __forceinline__ void silog_pixel(float zd, float t, float min_depth, SilogAcc& a, float& p_out) {
   const float p = sigmoid_fast(zd);
@@ -670,7 +674,7 @@ __device__ __forceinline__ void silog_pixel(float zd, float t, float min_depth, 
   const float d = fabsf(p - t);
   a.sabs += (double)d;
   if (t > min_depth) {
-    const float g = log_ratio(p, t);
+    const float g = log_ratio(zd, p, t);
     a.n += 1.0;
     a.sg += (double)g;
     a.sgg += (double)g * (double)g;
@@ -812,8 +816,9 @@ __global__ void __launch_bounds__(kLossThreads)
       const float t = __ldg(target + p);
       float dz = 0.f;
       if (t > min_depth) {
-        const float pr = sigmoid_fast(__ldg(feat + p));
-        const float g = log_ratio(pr, t);
+        const float zd = __ldg(feat + p);
+        const float pr = sigmoid_fast(zd);
+        const float g = log_ratio(zd, pr, t);
         dz = (cA * (g - fmean) + cB) * (1.f - pr);
       }
       dfeat[p] = dz;
@@ -851,7 +856,7 @@ __global__ void __launch_bounds__(kLossThreads)
         float dz = 0.f;
         if (ok[u] && tg[u] > min_depth) {
           const float pr = sigmoid_fast(d + bias);
-          const float g = log_ratio(pr, tg[u]);
+          const float g = log_ratio(d + bias, pr, tg[u]);
           dz = (cA * (g - fmean) + cB) * (1.f - pr);
         }
         if (dfeat && ok[u])

@@ -44,6 +44,31 @@ inline int launch_status() {
   return e == cudaSuccess ? VMTL_OK : VMTL_ECUDA;
 }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------
+// Every op here is a short chain (statistics -> finalize -> apply) of kernels that each wait for the previous one to
+// drain completely before the next is even scheduled: ~2-4 us of idle GPU per link, a large share of a 20-50 us call.
+// A kernel launched through launch_pdl() may be scheduled as soon as every block of its predecessor has executed
+// pdl_trigger() (or exited); it must execute pdl_wait() -- which returns once the predecessor has COMPLETED and its
+// writes are visible -- before it reads anything a predecessor produced.  Inside a stream capture the attribute
+// becomes a programmatic edge of the graph.  Both instructions are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through launch_status()
+}
+
 // ---- streaming loads/stores: the feature maps are read once, keep them out of L1 ----
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 r;

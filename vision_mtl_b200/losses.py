@@ -37,10 +37,16 @@ class SILogLoss(nn.Module):
         ``log(p) - log1p(-p)``; sigmoid of that reproduces ``p`` to 1 ulp, and autograd chains the
         kernel's d/dlogit back through it.
         """
-        if mask is not None:
-            raise NotImplementedError("explicit masks are not used by the reference pipeline")
         md = self.min_depth if min_depth is None else min_depth
-        p = pred.reshape(pred.shape[0], 1, -1, 1)
+        tgt = target.reshape(-1)
+        if mask is not None:
+            # losses.py:29-33 with an explicit mask: every selected pixel counts, whatever its depth.  The kernel
+            # masks by `target > min_depth`, so deselected pixels get a target below a zero threshold.  (Selected
+            # pixels with target <= 0 make the reference's log NaN; here they drop out.)
+            tgt = torch.where(mask.reshape(-1).to(torch.bool), tgt, torch.full_like(tgt, -1.0))
+            md = 0.0
+        # fp32 sigmoid saturates to exactly 0 / 1: keep the recovered logit (and its derivative) finite
+        p = pred.reshape(pred.shape[0], 1, -1, 1).clamp(1e-37, 1.0 - 2.0 ** -24)
         logit = torch.log(p) - torch.log1p(-p)
-        silog, _, _, _ = ops.head_silog(logit, None, None, target.reshape(-1), md, want_pred=False)
+        silog, _, _, _ = ops.head_silog(logit, None, None, tgt, md, want_pred=False)
         return silog

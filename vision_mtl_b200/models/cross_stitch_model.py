@@ -105,10 +105,25 @@ class CSNet(nn.Module):
                 idx = int(m.group(1))
                 plan.append(("cat_skip", idx) if self.consider_decoder_layer_at_idx(idx) else ("upsample2", None))
             layer = get_module_by_name(proto, name)
-            if next(layer.children(), None) is None:
+            # the reference's leaf test (cross_stitch_model.py:136-140) is module TRUTHINESS: an empty container
+            # child (len 0) does not count as a child
+            if not any(bool(child) for child in layer.children()):
                 plan.append(("leaf", name))
             if name in stitch_after:
                 plan.append(("stitch", name.replace(".", "_")))
+        # The reference clones the input per task and every saved skip (cross_stitch_model.py:105,118-120); here the
+        # tasks share x and the skips are aliases -- safe unless the NEXT leaf works in place (an nn.ReLU(inplace=True)
+        # at the start of a block would then overwrite the user's input / the saved skip): clone exactly there.
+        def next_leaf_inplace(i: int) -> bool:
+            for op, arg in plan[i:]:
+                if op == "leaf":
+                    return bool(getattr(get_module_by_name(proto, arg), "inplace", False))
+                if op in ("stitch", "cat_skip", "upsample2"):
+                    return False  # a fresh tensor is produced before any leaf runs
+            return False
+
+        self._clone_input = next_leaf_inplace(0)
+        plan = [("save_skip", next_leaf_inplace(i + 1)) if step[0] == "save_skip" else step for i, step in enumerate(plan)]
         # decoder sites: the tensor assembly in front of the stitch (zero-pad + cat with the skip, or nearest x2
         # up-sampling) is folded into the stitch kernel -- the assembled tensor is never materialised
         fused = []
@@ -123,7 +138,7 @@ class CSNet(nn.Module):
     def forward(self, x: torch.Tensor) -> dict:
         """Returns task name -> output tensor."""
         tasks = self.model_names
-        feats = [x for _ in tasks]
+        feats = [x.clone() if self._clone_input else x for _ in tasks]
         skips: t.List[list] = [[] for _ in tasks]
         leaf_cache = self.__dict__.setdefault("_leaf_cache", {})
         for op, arg in self._plan:
@@ -136,7 +151,7 @@ class CSNet(nn.Module):
                 feats = self.cross_stitch_layers[arg](feats)
             elif op == "save_skip":
                 for s, f in zip(skips, feats):
-                    s.append(f)
+                    s.append(f.clone() if arg else f)
             elif op == "cat_stitch":
                 idx, site = arg
                 layer = self.cross_stitch_layers[site]
