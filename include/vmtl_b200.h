@@ -317,8 +317,8 @@ int vmtl_seg_metrics(const int64_t* conf, int C, float* metrics, void* stream);
 int vmtl_head_supported(int kind, int Cin, int C);
 
 /* ------------------------------------------------------------------------------------
- * Multi-tensor Adam: torch.optim.Adam(params, lr) of training_lit.py:56 / lit_module.py:225-239,
- * stepped at training_lit.py:97 -- every tensor of a parameter group in one launch (28 bytes per parameter).
+ * Multi-tensor Adam: torch.optim.Adam(params, lr) of training_lit.py:51 / lit_module.py:194,
+ * stepped at training_lit.py:87 -- every tensor of a parameter group in one launch (28 bytes per parameter).
  * Arithmetic of torch's _single_tensor_adam (no amsgrad, not maximize; weight_decay is the L2 form g += wd * p).
  *   params / grads / numel / moment_offset: HOST arrays with n_tensors entries -- device pointers of the fp32
  *     parameter and gradient tensors, their element counts, and each tensor's element offset (a multiple of 4)

@@ -1,8 +1,10 @@
+# Round-2 evidence on one B200: GPU tests, per-site bench, the bench line, ncu launch lists and one --set full capture.
 set -u
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/r2_gpu_tests.log 2>&1; echo "pytest rc=$?" 
+python -m pytest tests -m gpu -q > gpurun_out/r2_gpu_tests.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r2_gpu_tests.log
 python tools/site_bench.py --json gpurun_out/r2_site_bench.json > gpurun_out/r2_site_bench.txt 2>&1; echo "site rc=$?"
 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_all.json 2> gpurun_out/r2_bench_all.err; echo "bench rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2_ncu_launches_site_bench.csv python tools/site_bench.py --once > gpurun_out/ncu1.log 2>&1; echo "ncu1 rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gate_tc_|head_ce_tc|xstitch_|bnrelu" -c 40 -o gpurun_out/r2_full python tools/site_bench.py --once --profile-set > gpurun_out/ncu2.log 2>&1; echo "ncu2 rc=$?"
-ls -la gpurun_out
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r2_ncu_launches_site_bench.csv python tools/site_bench.py --once > gpurun_out/ncu1.log 2>&1; echo "ncu site launches rc=$?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 16000 --csv --log-file gpurun_out/r2_ncu_launches_bench_mtan.csv python bench.py --workload mtan --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu3.log 2>&1; echo "ncu bench launches rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gate_tc_|head_ce_tc|xstitch_|bn_|adam_" -c 48 -o gpurun_out/r2_full python tools/site_bench.py --once --profile-set > gpurun_out/ncu2.log 2>&1; echo "ncu full rc=$?"
+ls -la gpurun_out | head -30

@@ -1,5 +1,5 @@
 """Multi-tensor Adam (vmtl_adam_step) against torch.optim.Adam -- the optimizer the reference builds at
-training_lit.py:56 -- on the same parameters and gradients: parameters and both moments after several steps,
+training_lit.py:51 -- on the same parameters and gradients: parameters and both moments after several steps,
 weight decay, a device learning rate changed between steps, parameters without gradients, channels_last
 parameters, state_dict round trip into torch.optim.Adam and back, and CUDA-graph capture."""
 import copy

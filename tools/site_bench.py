@@ -134,9 +134,10 @@ def main():
 
             timed("gate_folded", f"{site} N={N} M={M}", nb_f + 4 * M * 128, nb_b + 4 * M * 128 * 5, fwd_f, bwd_f)
 
-    if args.only in ("", "bn") and not args.profile_set:
+    if args.only in ("", "bn"):
         # DoubleConv / attention conv3 BatchNorm + ReLU (+ 2x2 max-pool) sites of the MTAN network, batch statistics
-        for Cc, down, pool in ((32, 1, False), (64, 2, False), (128, 4, False), (256, 8, False), (32, 1, True), (64, 2, True)):
+        bn_sites = ((32, 1, False), (64, 2, False), (128, 4, False), (256, 8, False), (32, 1, True), (64, 2, True))
+        for Cc, down, pool in (bn_sites[:1] if args.profile_set else bn_sites):
             h, w = H // down, W // down
             M = B * h * w
             x = cl(B, Cc, h, w).requires_grad_(True)

@@ -1,7 +1,7 @@
 // Multi-tensor Adam: every parameter tensor of a group in ONE launch -- SURVEY 8(f) row 4.
 //
-// Reference: torch.optim.Adam(params, lr) built at vision_mtl/training_lit.py:56 (and lit_module.py:225-239),
-// default betas / eps, no weight decay, no amsgrad; stepped once per batch (training_lit.py:97).  torch runs it as
+// Reference: torch.optim.Adam(params, lr) built at vision_mtl/training_lit.py:51 (and lit_module.py:194),
+// default betas / eps, no weight decay, no amsgrad; stepped once per batch (training_lit.py:87).  torch runs it as
 // a foreach / multi_tensor_apply sequence (tens of launches for the ~330 MTAN parameter tensors, each moving
 // a few KB); here the step is one HBM-bound pass: read p, g, m, v, write p, m, v = 28 bytes per parameter.
 //

@@ -108,11 +108,20 @@ __global__ void __launch_bounds__(kFinThreads)
                                 const double* __restrict__ gmoments /* NULL, or global [2][C] over M rows */) {
   pdl_wait();     // statistics pass complete, its partials visible
   pdl_trigger();  // the apply pass may be scheduled while this block reduces
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int c = blockIdx.x * kTallCols + (threadIdx.x & (kTallCols - 1));
+  const bool owner = threadIdx.x < kTallCols && c < C;
+  // the per-channel operands are fetched BEFORE the reduction, so their latency hides behind it
+  float g_c = 0.f, b_c = 0.f, rm_c = 0.f, rv_c = 0.f;
+  if (owner) {
+    g_c = gamma[c];
+    b_c = beta[c];
+    if (running_mean) rm_c = running_mean[c];
+    if (running_var) rv_c = running_var[c];
+  }
   double s = 0.0, q = 0.0;
   if (training && !gmoments)  // block-uniform branch: the reduction synchronises
-    block_colsum2(partial, nparts, 2 * (int64_t)C, c < C ? c : 0, C + (c < C ? c : 0), c < C, &s, &q);
-  if (threadIdx.x >= 32 || c >= C) return;
+    block_colsum2_tall(partial, nparts, 2 * (int64_t)C, c < C ? c : 0, C + (c < C ? c : 0), c < C, &s, &q);
+  if (!owner) return;
   if (training && gmoments) {
     s = gmoments[c];
     q = gmoments[C + c];
@@ -122,22 +131,22 @@ __global__ void __launch_bounds__(kFinThreads)
     mean = s / (double)M;
     var = q / (double)M - mean * mean;
     if (var < 0.0) var = 0.0;
-    if (running_mean) running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+    if (running_mean) running_mean[c] = (float)((1.0 - momentum) * rm_c + momentum * mean);
     if (running_var) {
       const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
-      running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+      running_var[c] = (float)((1.0 - momentum) * rv_c + momentum * unb);
     }
   } else {
-    mean = running_mean[c];
-    var = running_var[c];
+    mean = rm_c;
+    var = rv_c;
   }
   const double inv = 1.0 / sqrt(var + (double)eps);
   const float invf = (float)inv, meanf = (float)mean;
-  const float a = gamma[c] * invf;  // fp32, so that every consumer folds exactly the same coefficients
+  const float a = g_c * invf;  // fp32, so that every consumer folds exactly the same coefficients
   save_mean[c] = meanf;
   save_invstd[c] = invf;
   coef[c] = a;
-  coef[C + c] = beta[c] - meanf * a;
+  coef[C + c] = b_c - meanf * a;
 }
 
 template <bool RELU>
@@ -304,10 +313,10 @@ __global__ void __launch_bounds__(kFinThreads)
                                 const double* __restrict__ gmoments) {
   pdl_wait();
   pdl_trigger();
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int c = blockIdx.x * kTallCols + (threadIdx.x & (kTallCols - 1));
   double sb = 0.0, sg = 0.0;
-  if (!gmoments) block_colsum2(partial, nparts, 2 * (int64_t)C, c < C ? c : 0, C + (c < C ? c : 0), c < C, &sb, &sg);
-  if (threadIdx.x >= 32 || c >= C) return;
+  if (!gmoments) block_colsum2_tall(partial, nparts, 2 * (int64_t)C, c < C ? c : 0, C + (c < C ? c : 0), c < C, &sb, &sg);
+  if (threadIdx.x >= kTallCols || c >= C) return;
   if (gmoments) {
     sb = gmoments[c];
     sg = gmoments[C + c];
@@ -322,10 +331,10 @@ __global__ void __launch_bounds__(kFinThreads)
 // partial [nparts][2][C] -> fp64 moments [2][C] (fixed-order second stage), what a data-parallel caller all-reduces
 __global__ void __launch_bounds__(kFinThreads)
     bn_moments_finalize(const float* __restrict__ partial, int nparts, int C, double* __restrict__ moments) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int c = blockIdx.x * kTallCols + (threadIdx.x & (kTallCols - 1));
   double a, b;
-  block_colsum2(partial, nparts, 2 * (int64_t)C, c < C ? c : 0, C + (c < C ? c : 0), c < C, &a, &b);
-  if (threadIdx.x >= 32 || c >= C) return;
+  block_colsum2_tall(partial, nparts, 2 * (int64_t)C, c < C ? c : 0, C + (c < C ? c : 0), c < C, &a, &b);
+  if (threadIdx.x >= kTallCols || c >= C) return;
   moments[c] = a;
   moments[C + c] = b;
 }
@@ -440,7 +449,7 @@ static int bnrelu_fwd_impl(const float* x, const float* gamma, const float* beta
     const int np = bn_grid(M, C, blocks_per_sm(bn_stats_kernel, kBnThreads, 0, 8));
     bn_stats_kernel<<<np, kBnThreads, 0, st1>>>(x, M, C / 4, part);
     if ((rc = launch_status()) != VMTL_OK) return rc;
-    bn_moments_finalize<<<(C + 31) / 32, kFinThreads, 0, st1>>>(part, np, C, moments);
+    bn_moments_finalize<<<(C + kTallCols - 1) / kTallCols, kFinThreads, 0, st1>>>(part, np, C, moments);
     return launch_status();
   }
   if (phase == 2 && (!moments || Mstat < 1 || !training)) return VMTL_EINVAL;
@@ -458,7 +467,7 @@ static int bnrelu_fwd_impl(const float* x, const float* gamma, const float* beta
     if ((rc = launch_status()) != VMTL_OK) return rc;
   }
   // finalize and apply are programmatic dependents (vmtl_common.cuh): each is scheduled while its predecessor drains
-  launch_pdl(bn_fwd_finalize, (C + 31) / 32, kFinThreads, 0, st, (const float*)partial, nparts, phase == 2 ? Mstat : M, C, eps,
+  launch_pdl(bn_fwd_finalize, (C + kTallCols - 1) / kTallCols, kFinThreads, 0, st, (const float*)partial, nparts, phase == 2 ? Mstat : M, C, eps,
              momentum, training, gamma, beta, running_mean, running_var, save_mean, save_invstd, coef,
              (const double*)(phase == 2 ? moments : nullptr));
   if ((rc = launch_status()) != VMTL_OK) return rc;
@@ -541,10 +550,10 @@ static int bnrelu_bwd_impl(const float* dy, const float* x, const float* coef, c
     if ((rc = launch_status()) != VMTL_OK) return rc;
   }
   if (phase == 1) {
-    bn_moments_finalize<<<(C + 31) / 32, kFinThreads, 0, st>>>(partial, nparts, C, moments);
+    bn_moments_finalize<<<(C + kTallCols - 1) / kTallCols, kFinThreads, 0, st>>>(partial, nparts, C, moments);
     return launch_status();
   }
-  launch_pdl(bn_bwd_finalize, (C + 31) / 32, kFinThreads, 0, st, (const float*)partial, nparts, phase == 2 ? Mstat : M, C,
+  launch_pdl(bn_bwd_finalize, (C + kTallCols - 1) / kTallCols, kFinThreads, 0, st, (const float*)partial, nparts, phase == 2 ? Mstat : M, C,
              training, dgamma, dbeta, c12, (const double*)(phase == 2 ? moments : nullptr));
   if ((rc = launch_status()) != VMTL_OK) return rc;
   if (!dx) return VMTL_OK;

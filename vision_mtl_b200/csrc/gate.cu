@@ -248,10 +248,10 @@ __global__ void __launch_bounds__(kFinThreads)
 // (dbias is analytically zero under batch statistics: what is left is the round-off of sum zhat).
 // CTA b of pass 1 owned the column chunk b % nch: the partials of chunk c are rows c, c + nch, ... of each buffer.
 //
-// Blocks [0, N/4 * K/32): one [4 rows n x 32 k] patch of dW each.  1024 threads = 32 k-lanes x (4 rows x 8 part groups): every thread sums its share
+// Blocks [0, N * K/32): one [1 row n x 32 k] patch of dW each.  1024 threads = 32 k-lanes x (1 row x 32 part groups): every thread sums its share
 // of the partial rows (a handful of independent loads in flight), the 8 groups are combined in a fixed order.
 // The last ceil(N/32) blocks produce the per-channel outputs and the folded coefficients pass 2 needs.
-constexpr int kFinRows = 4, kFinGroups = 8;
+constexpr int kFinRows = 1, kFinGroups = 32;  // (4, 8) left 33 blocks walking 148 partial slices in 5-step chains: 11-17 us
 __global__ void __launch_bounds__(kFinThreads)
     gate_bwd_tc_finalize(const float* __restrict__ pw_partial, const float* __restrict__ hs_partial,
                          const float* __restrict__ col_partial, int nparts, int nch, int64_t M, int N, int K,

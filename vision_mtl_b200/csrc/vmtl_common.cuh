@@ -177,6 +177,64 @@ __device__ __forceinline__ void block_colsum2(const T* __restrict__ partial, int
   *out_b = tb;
 }
 
+// Tall variant for LONG partial lists (the streaming BatchNorm kernels leave 600-900 partial rows): 8 columns x 128
+// row groups per block, so a thread's dependent chain of row loads is 4x shorter than with 32 x 32 (the finalize
+// kernels are pure latency: ncu showed 14 us for 888 rows, most of it the 28-step chain).  Fixed summation order:
+// rows ly, ly+128, ... per thread, then groups 32q..32q+31 by four threads per column, then those four.
+// The result is valid in the threads with threadIdx.x < 8.
+constexpr int kTallCols = 8;
+template <typename T>
+__device__ __forceinline__ void block_colsum2_tall(const T* __restrict__ partial, int nparts, int64_t rowlen,
+                                                   int64_t col_a, int64_t col_b, bool valid, double* out_a,
+                                                   double* out_b) {
+  __shared__ double s_t[2][128][kTallCols + 1];
+  __shared__ double s_q[2][4][kTallCols + 1];
+  const int lx = threadIdx.x & (kTallCols - 1), ly = threadIdx.x >> 3;
+  double sa = 0.0, sb = 0.0;
+  if (valid) {
+    int k = ly;
+    for (; k + 384 < nparts; k += 512) {
+      T va[4], vb[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        va[q] = partial[(int64_t)(k + 128 * q) * rowlen + col_a];
+        vb[q] = partial[(int64_t)(k + 128 * q) * rowlen + col_b];
+      }
+      sa += ((double)va[0] + (double)va[1]) + ((double)va[2] + (double)va[3]);
+      sb += ((double)vb[0] + (double)vb[1]) + ((double)vb[2] + (double)vb[3]);
+    }
+    for (; k < nparts; k += 128) {
+      sa += (double)partial[(int64_t)k * rowlen + col_a];
+      sb += (double)partial[(int64_t)k * rowlen + col_b];
+    }
+  }
+  s_t[0][ly][lx] = sa;
+  s_t[1][ly][lx] = sb;
+  __syncthreads();
+  if (ly < 4) {
+    double ta = 0.0, tb = 0.0;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) {
+      ta += s_t[0][ly * 32 + q][lx];
+      tb += s_t[1][ly * 32 + q][lx];
+    }
+    s_q[0][ly][lx] = ta;
+    s_q[1][ly][lx] = tb;
+  }
+  __syncthreads();
+  double ta = 0.0, tb = 0.0;
+  if (ly == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      ta += s_q[0][q][lx];
+      tb += s_q[1][q][lx];
+    }
+  }
+  __syncthreads();
+  *out_a = ta;
+  *out_b = tb;
+}
+
 // MUFU forms (max rel. error 2^-22 on the normal range): the accurate expf/logf cost 10-20 instructions
 // each and the per-pixel loss kernels run one per class.
 constexpr float kLog2e = 1.4426950408889634f;

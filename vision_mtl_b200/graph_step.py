@@ -25,7 +25,7 @@ from .lit_module import STEP_KEYS, MTLModule
 
 
 def make_optimizer(params, lr: float, device) -> torch.optim.Optimizer:
-    """Adam as the reference builds it (training_lit.py:56) on the library's multi-tensor kernel
+    """Adam as the reference builds it (training_lit.py:51) on the library's multi-tensor kernel
     (``optim.Adam``: one launch per step, device-side step counter), with the learning rate held in a device
     tensor so schedulers (which ``fill_`` it) act on graph replays."""
     from .optim import Adam

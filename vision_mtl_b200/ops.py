@@ -264,8 +264,8 @@ class CrossStitchCatFunction(torch.autograd.Function):
         else:
             Cs, Ho, Wo = 0, (2 * Hi if up2 else Hi), (2 * Wi if up2 else Wi)
         C = Cs + Cx
-        ys = [torch.empty((B, C, Ho, Wo), dtype=torch.float32, device=xs[0].device).contiguous(
-            memory_format=torch.channels_last) for _ in range(T)]
+        ys = [torch.empty((B, C, Ho, Wo), dtype=torch.float32, device=xs[0].device, memory_format=torch.channels_last)
+              for _ in range(T)]
         cw = 1 if alpha.dim() == 3 else 0
         a = alpha.detach().contiguous()
         geom = (T, B, Ho, Wo, Cs, Hi, Wi, Cx, 1 if up2 else 0, cw, mode)
@@ -284,7 +284,7 @@ class CrossStitchCatFunction(torch.autograd.Function):
         skips, xs = rest[:n_skip], rest[n_skip:]
         T, B, Ho, Wo, Cs, Hi, Wi, Cx, up2, cw, mode = ctx.geom
         dev = xs[0].device
-        dys = [torch.zeros((B, Cs + Cx, Ho, Wo), device=dev).contiguous(memory_format=torch.channels_last)
+        dys = [torch.zeros((B, Cs + Cx, Ho, Wo), device=dev, memory_format=torch.channels_last)
                if d is None else _nhwc(d) for d in dys]
         a = alpha.detach().contiguous()
         dalpha = torch.empty_like(a)
@@ -423,8 +423,7 @@ class BNReLUFunction(torch.autograd.Function):
         B, C, H, W = x.shape
         dev = x.device
         if pool:
-            y = torch.empty((B, C, H // 2, W // 2), dtype=torch.float32, device=dev).contiguous(
-                memory_format=torch.channels_last)
+            y = torch.empty((B, C, H // 2, W // 2), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
         else:
             y = torch.empty_like(x)
         stats = torch.empty((4, C), dtype=torch.float32, device=dev)  # save_mean, save_invstd, A, B

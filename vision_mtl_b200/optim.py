@@ -1,5 +1,5 @@
-"""Adam as the reference builds it (``torch.optim.Adam(params, lr)``, training_lit.py:56 /
-lit_module.py:225-239), run by ONE multi-tensor kernel per parameter group (``vmtl_adam_step``).
+"""Adam as the reference builds it (``torch.optim.Adam(params, lr)``, training_lit.py:51 /
+lit_module.py:194), run by ONE multi-tensor kernel per parameter group (``vmtl_adam_step``).
 
 Drop-in for ``torch.optim.Adam`` where the reference uses it: same constructor keywords, ``param_groups``,
 ``state_dict()`` layout (per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq``), works with
