@@ -153,27 +153,34 @@ int vmtl_gate_bwd(const float* dy, const float* h, const float* h_coef, const fl
  *   coef [2][C]: A = gamma*invstd, B = beta - mean*A, the fp32 coefficients every consumer folds
  * pool variants: x [B,H,W,C] -> y [B,H/2,W/2,C], nn.MaxPool2d(2) after the ReLU.
  * Backward: dx [M,C] (NULL to skip), dgamma, dbeta [C]; dy has the shape of y.
+ *   conv_bias [C] (or NULL), training only: the bias of the convolution that produced x, which the caller did NOT
+ *     add (x = conv(.) without bias).  Batch statistics cancel a per-channel shift exactly, so y is unchanged and
+ *     only the running mean moves: running_mean <- (1-m) running_mean + m (mean(x) + conv_bias).  This removes the
+ *     reference's bias-add pass over x and, in the backward, its reduction of dx over all pixels:
+ *   dconv_bias [C] (or NULL): gradient of that bias = sum over pixels of dx = A (sum g - M c1), which is zero up to
+ *     round-off under batch statistics (as in the reference) and A sum g under running statistics.
  * ---------------------------------------------------------------------------------- */
 size_t vmtl_bnrelu_workspace_bytes(int64_t M, int C);
 
 int vmtl_bnrelu_fwd(const float* x, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, float momentum, float eps, int training, int relu, int64_t M, int C,
-                    float* y, float* save_mean, float* save_invstd, float* coef, void* workspace,
-                    size_t workspace_bytes, void* stream);
+                    float* y, float* save_mean, float* save_invstd, float* coef, const float* conv_bias,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 int vmtl_bnrelu_bwd(const float* dy, const float* x, const float* coef, const float* save_mean,
                     const float* save_invstd, int training, int relu, int64_t M, int C, float* dx,
-                    float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream);
+                    float* dgamma, float* dbeta, float* dconv_bias, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 int vmtl_bnrelu_pool_fwd(const float* x, const float* gamma, const float* beta, float* running_mean,
                          float* running_var, float momentum, float eps, int training, int relu, int B, int H,
                          int W, int C, float* y, float* save_mean, float* save_invstd, float* coef,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         const float* conv_bias, void* workspace, size_t workspace_bytes, void* stream);
 
 int vmtl_bnrelu_pool_bwd(const float* dy, const float* x, const float* coef, const float* save_mean,
                          const float* save_invstd, int training, int relu, int B, int H, int W, int C,
-                         float* dx, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
-                         void* stream);
+                         float* dx, float* dgamma, float* dbeta, float* dconv_bias, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Segmentation head fused with cross-entropy, argmax and the confusion matrix.
@@ -255,7 +262,8 @@ int vmtl_bn_moments(const float* x, int64_t M, int C, double* moments, void* wor
 int vmtl_bnrelu_fwd_global(const float* x, const float* gamma, const float* beta, float* running_mean,
                            float* running_var, float momentum, float eps, int relu, int pool, int B, int H, int W,
                            int C, const double* moments, int64_t M_global, float* y, float* save_mean,
-                           float* save_invstd, float* coef, void* workspace, size_t workspace_bytes, void* stream);
+                           float* save_invstd, float* coef, const float* conv_bias, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 int vmtl_bnrelu_bwd_moments(const float* dy, const float* x, const float* coef, const float* save_mean,
                             const float* save_invstd, int relu, int pool, int B, int H, int W, int C,

@@ -85,8 +85,8 @@ def gate_bwd(dy, h, h_coef, s, z, *a, **k):
     out = _gb(dy, h, h_coef, s, z, *a, **k)
     rec.append(("gate", dy.detach().clone(), None if out[0] is None else out[0].detach().clone(), out[1].detach().clone() if out[1] is not None else None))
     return out
-def bn_bwd(dy, x, stats, training, relu, pool, need_dx, world):
-    out = _bb(dy, x, stats, training, relu, pool, need_dx, world)
+def bn_bwd(dy, x, stats, training, relu, pool, need_dx, world, *extra):
+    out = _bb(dy, x, stats, training, relu, pool, need_dx, world, *extra)
     rec.append(("bn", dy.detach().clone(), None if out[0] is None else out[0].detach().clone(), out[2].detach().clone()))
     return out
 ops._gate_backward, ops._bn_backward = gate_bwd, bn_bwd
@@ -118,10 +118,10 @@ for i, (kind, dy, dx, extra) in enumerate(whole):
 ops._gate_backward, ops._bn_backward = _gb, _bb
 saved = {}
 _bf = ops._bn_forward
-def bn_fwd(x, gamma, beta, rm, rv, training, momentum, eps, relu, pool, y, stats, world):
-    _bf(x, gamma, beta, rm, rv, training, momentum, eps, relu, pool, y, stats, world)
+def bn_fwd(x, gamma, beta, rm, rv, training, momentum, eps, relu, pool, y, stats, world, *extra):
+    _bf(x, gamma, beta, rm, rv, training, momentum, eps, relu, pool, y, stats, world, *extra)
     saved[(x.data_ptr(), stats.data_ptr())] = (x.detach().clone(), stats.detach().clone())
-def bn_bwd2(dy, x, stats, training, relu, pool, need_dx, world):
+def bn_bwd2(dy, x, stats, training, relu, pool, need_dx, world, *extra):
     key = (x.data_ptr(), stats.data_ptr())
     if key in saved:
         x0, s0 = saved[key]
@@ -131,7 +131,7 @@ def bn_bwd2(dy, x, stats, training, relu, pool, need_dx, world):
                   [int(i) for i in range(stats.shape[0]) if float((s0[i] - stats[i]).abs().max()) > 0])
     else:
         print("  (no forward record)", x.shape)
-    return _bb(dy, x, stats, training, relu, pool, need_dx, world)
+    return _bb(dy, x, stats, training, relu, pool, need_dx, world, *extra)
 ops._bn_forward, ops._bn_backward = bn_fwd, bn_bwd2
 old_world = ops.stat_sync_world
 ops.stat_sync_world = lambda: 2

@@ -4,6 +4,8 @@ Bars (BASELINE.json north_star): confusion matrices bit-exact; losses, gradients
 metrics within 1e-4 relative in fp32.  The relative error is taken tensor-wise:
 max|got - ref| <= TOL * max|ref|.
 """
+import copy
+
 import numpy as np
 import pytest
 import torch
@@ -406,6 +408,51 @@ def test_bn_relu_pool_fwd_bwd(B, C, H, W, training, relu, pool):
 
 
 # ----------------------------------------------------------------------------- gate with the folded hidden layer
+@pytest.mark.parametrize("pool", [False, True])
+@pytest.mark.parametrize("cin,cout,k,H,W", [(8, 32, 3, 16, 24), (12, 128, 1, 10, 14), (16, 64, 3, 9, 13)])
+def test_conv_bias_folded_into_batchnorm(cin, cout, k, H, W, pool):
+    """conv (with bias) -> BatchNorm2d (batch statistics) -> ReLU [-> MaxPool2d(2)] as the reference runs it
+    (mtan_model.py:77-81, :141-142, :165-167) against the convolution WITHOUT its bias + the BatchNorm kernels
+    that take the bias: same output, same running statistics, same gradients; the bias gradient is the
+    round-off-sized number it analytically is."""
+    from vision_mtl_b200 import ops
+
+    if pool and (H % 2 or W % 2):
+        pytest.skip("pooled case uses even sizes")
+    torch.manual_seed(3)
+    conv = torch.nn.Conv2d(cin, cout, k, padding=k // 2).to(dev())
+    with torch.no_grad():
+        conv.bias.mul_(20.0).add_(1.0)  # a bias far from zero: a kernel that forgot it would show
+    bn = torch.nn.BatchNorm2d(cout).to(dev())
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_()
+    conv_r, bn_r = copy.deepcopy(conv), copy.deepcopy(bn)
+    x = to_cl(torch.randn(3, cin, H, W))
+    xr = x.clone().requires_grad_(True)
+    xd = x.clone().requires_grad_(True)
+    act, mp = torch.nn.ReLU(), torch.nn.MaxPool2d(2)
+    yr = act(bn_r(conv_r(xr)))
+    yr = mp(yr) if pool else yr
+    dy = torch.randn_like(yr) + 0.3
+    yr.backward(dy)
+    y0, cb = ops.conv_without_bias(conv, xd, bn)
+    assert cb is conv.bias
+    y = ops.batch_norm_relu(y0, bn, relu=True, pool=pool, conv_bias=cb)
+    y.backward(dy)
+    assert_rel(y, yr, what="y")
+    assert_rel(bn.running_mean, bn_r.running_mean, what="running_mean")
+    assert_rel(bn.running_var, bn_r.running_var, what="running_var")
+    assert int(bn.num_batches_tracked) == 1
+    assert_rel(xd.grad, xr.grad, what="dx")
+    assert_rel(conv.weight.grad, conv_r.weight.grad, what="dW")
+    assert_rel(bn.weight.grad, bn_r.weight.grad, what="dgamma")
+    assert_rel(bn.bias.grad, bn_r.bias.grad, what="dbeta")
+    # analytically zero: both sides hold round-off on the scale of dbeta
+    scale = float(bn_r.bias.grad.abs().max())
+    assert float(conv.bias.grad.abs().max()) <= 1e-4 * scale and float(conv_r.bias.grad.abs().max()) <= 1e-4 * scale
+
+
 @pytest.mark.parametrize("B,N,H,W", [(2, 32, 16, 24), (1, 64, 9, 13), (2, 128, 8, 8), (1, 256, 4, 8), (2, 32, 128, 256),
                                      (1, 128, 160, 256)])
 @pytest.mark.parametrize("training", [True, False])

@@ -34,11 +34,11 @@ SIGNATURES = {
                               _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "vmtl_bnrelu_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "vmtl_bnrelu_fwd": (c_int, [_P, _P, _P, _P, _P, c_float, c_float, c_int, c_int, c_int64, c_int, _P, _P, _P, _P,
-                                _P, c_size_t, _P]),
-    "vmtl_bnrelu_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int64, c_int, _P, _P, _P, _P, c_size_t, _P]),
+                                _P, _P, c_size_t, _P]),
+    "vmtl_bnrelu_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "vmtl_bnrelu_pool_fwd": (c_int, [_P, _P, _P, _P, _P, c_float, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
-                                     _P, _P, _P, _P, _P, c_size_t, _P]),
-    "vmtl_bnrelu_pool_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P,
+                                     _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "vmtl_bnrelu_pool_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P,
                                      c_size_t, _P]),
     "vmtl_loss_workspace_bytes": (c_size_t, [c_int64]),
     "vmtl_head_ce_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int64, _P, _P, _P, _P, _P,
@@ -57,7 +57,7 @@ SIGNATURES = {
     # global-batch statistics: the two halves of every op with a batch reduction in its middle
     "vmtl_bn_moments": (c_int, [_P, c_int64, c_int, _P, _P, c_size_t, _P]),
     "vmtl_bnrelu_fwd_global": (c_int, [_P, _P, _P, _P, _P, c_float, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
-                                       _P, c_int64, _P, _P, _P, _P, _P, c_size_t, _P]),
+                                       _P, c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "vmtl_bnrelu_bwd_moments": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t,
                                         _P]),
     "vmtl_bnrelu_bwd_global": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P,

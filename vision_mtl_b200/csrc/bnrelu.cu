@@ -105,18 +105,20 @@ __global__ void __launch_bounds__(kFinThreads)
                                 const float* __restrict__ beta, float* __restrict__ running_mean,
                                 float* __restrict__ running_var, float* __restrict__ save_mean,
                                 float* __restrict__ save_invstd, float* __restrict__ coef /* [2][C] */,
-                                const double* __restrict__ gmoments /* NULL, or global [2][C] over M rows */) {
+                                const double* __restrict__ gmoments /* NULL, or global [2][C] over M rows */,
+                                const float* __restrict__ conv_bias /* NULL, or the un-added bias of the producing conv */) {
   pdl_wait();     // statistics pass complete, its partials visible
   pdl_trigger();  // the apply pass may be scheduled while this block reduces
   const int c = blockIdx.x * kTallCols + (threadIdx.x & (kTallCols - 1));
   const bool owner = threadIdx.x < kTallCols && c < C;
   // the per-channel operands are fetched BEFORE the reduction, so their latency hides behind it
-  float g_c = 0.f, b_c = 0.f, rm_c = 0.f, rv_c = 0.f;
+  float g_c = 0.f, b_c = 0.f, rm_c = 0.f, rv_c = 0.f, cb_c = 0.f;
   if (owner) {
     g_c = gamma[c];
     b_c = beta[c];
     if (running_mean) rm_c = running_mean[c];
     if (running_var) rv_c = running_var[c];
+    if (conv_bias) cb_c = conv_bias[c];
   }
   double s = 0.0, q = 0.0;
   if (training && !gmoments)  // block-uniform branch: the reduction synchronises
@@ -131,7 +133,8 @@ __global__ void __launch_bounds__(kFinThreads)
     mean = s / (double)M;
     var = q / (double)M - mean * mean;
     if (var < 0.0) var = 0.0;
-    if (running_mean) running_mean[c] = (float)((1.0 - momentum) * rm_c + momentum * mean);
+    // the batch mean of the tensor the reference normalises (x + conv_bias); y itself does not depend on the shift
+    if (running_mean) running_mean[c] = (float)((1.0 - momentum) * rm_c + momentum * (mean + (double)cb_c));
     if (running_var) {
       const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
       running_var[c] = (float)((1.0 - momentum) * rv_c + momentum * unb);
@@ -310,7 +313,8 @@ __global__ void __launch_bounds__(kBnThreads)
 __global__ void __launch_bounds__(kFinThreads)
     bn_bwd_finalize(const float* __restrict__ partial, int nparts, int64_t Mnorm, int C, int training,
                                 float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c12,
-                                const double* __restrict__ gmoments) {
+                                const double* __restrict__ gmoments, const float* __restrict__ coef,
+                                float* __restrict__ dconv_bias /* NULL, or [C]: sum over pixels of dx */) {
   pdl_wait();
   pdl_trigger();
   const int c = blockIdx.x * kTallCols + (threadIdx.x & (kTallCols - 1));
@@ -324,8 +328,11 @@ __global__ void __launch_bounds__(kFinThreads)
     dbeta[c] = (float)sb;
     dgamma[c] = (float)sg;
   }
-  c12[c] = training ? (float)(sb / (double)Mnorm) : 0.f;
+  const double k1 = training ? sb / (double)Mnorm : 0.0;
+  c12[c] = (float)k1;
   c12[C + c] = training ? (float)(sg / (double)Mnorm) : 0.f;
+  // sum_pixels dx = A (sum g - M c1 - c2 sum xhat): zero up to round-off under batch statistics (sum xhat = 0)
+  if (dconv_bias && !gmoments) dconv_bias[c] = (float)((double)coef[c] * (sb - (double)Mnorm * k1));
 }
 
 // partial [nparts][2][C] -> fp64 moments [2][C] (fixed-order second stage), what a data-parallel caller all-reduces
@@ -437,9 +444,10 @@ static int bnrelu_fwd_impl(const float* x, const float* gamma, const float* beta
                            float* running_var, float momentum, float eps, int training, int relu, int64_t M, int C,
                            int B, int H, int W, int pool, float* y, float* save_mean, float* save_invstd, float* coef,
                            void* workspace, size_t workspace_bytes, void* stream, int phase = 0,
-                           double* moments = nullptr, int64_t Mstat = 0) {
+                           double* moments = nullptr, int64_t Mstat = 0, const float* conv_bias = nullptr) {
   int rc = bn_check(M, C);
   if (rc != VMTL_OK) return rc;
+  if (conv_bias && !training) return VMTL_EINVAL;  // running statistics: the caller keeps the bias in x
   if (phase == 1) {
     if (!x || !moments || !workspace) return VMTL_EINVAL;
     if (!aligned16(x) || !aligned16(workspace)) return VMTL_EALIGN;
@@ -469,7 +477,7 @@ static int bnrelu_fwd_impl(const float* x, const float* gamma, const float* beta
   // finalize and apply are programmatic dependents (vmtl_common.cuh): each is scheduled while its predecessor drains
   launch_pdl(bn_fwd_finalize, (C + kTallCols - 1) / kTallCols, kFinThreads, 0, st, (const float*)partial, nparts, phase == 2 ? Mstat : M, C, eps,
              momentum, training, gamma, beta, running_mean, running_var, save_mean, save_invstd, coef,
-             (const double*)(phase == 2 ? moments : nullptr));
+             (const double*)(phase == 2 ? moments : nullptr), conv_bias);
   if ((rc = launch_status()) != VMTL_OK) return rc;
   if (!y) return VMTL_OK;
   if (pool) {
@@ -496,19 +504,20 @@ static int bnrelu_fwd_impl(const float* x, const float* gamma, const float* beta
 
 extern "C" int vmtl_bnrelu_fwd(const float* x, const float* gamma, const float* beta, float* running_mean,
                                float* running_var, float momentum, float eps, int training, int relu, int64_t M,
-                               int C, float* y, float* save_mean, float* save_invstd, float* coef, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+                               int C, float* y, float* save_mean, float* save_invstd, float* coef,
+                               const float* conv_bias, void* workspace, size_t workspace_bytes, void* stream) {
   return bnrelu_fwd_impl(x, gamma, beta, running_mean, running_var, momentum, eps, training, relu, M, C, 0, 0, 0, 0, y,
-                         save_mean, save_invstd, coef, workspace, workspace_bytes, stream);
+                         save_mean, save_invstd, coef, workspace, workspace_bytes, stream, 0, nullptr, 0, conv_bias);
 }
 
 extern "C" int vmtl_bnrelu_pool_fwd(const float* x, const float* gamma, const float* beta, float* running_mean,
                                     float* running_var, float momentum, float eps, int training, int relu, int B,
                                     int H, int W, int C, float* y, float* save_mean, float* save_invstd, float* coef,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+                                    const float* conv_bias, void* workspace, size_t workspace_bytes, void* stream) {
   if (B < 1 || H < 2 || W < 2 || !y) return VMTL_EINVAL;
   return bnrelu_fwd_impl(x, gamma, beta, running_mean, running_var, momentum, eps, training, relu, (int64_t)B * H * W,
-                         C, B, H, W, 1, y, save_mean, save_invstd, coef, workspace, workspace_bytes, stream);
+                         C, B, H, W, 1, y, save_mean, save_invstd, coef, workspace, workspace_bytes, stream, 0, nullptr, 0,
+                         conv_bias);
 }
 
 // phase 0: whole op; phase 1: statistics pass -> LOCAL fp64 moments [2][C] = (sum g, sum g xhat) (also the
@@ -516,7 +525,8 @@ extern "C" int vmtl_bnrelu_pool_fwd(const float* x, const float* gamma, const fl
 static int bnrelu_bwd_impl(const float* dy, const float* x, const float* coef, const float* save_mean,
                            const float* save_invstd, int training, int relu, int64_t M, int C, int B, int H, int W,
                            int pool, float* dx, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
-                           void* stream, int phase = 0, double* moments = nullptr, int64_t Mstat = 0) {
+                           void* stream, int phase = 0, double* moments = nullptr, int64_t Mstat = 0,
+                           float* dconv_bias = nullptr) {
   int rc = bn_check(M, C);
   if (rc != VMTL_OK) return rc;
   if (phase != 0 && !moments) return VMTL_EINVAL;
@@ -554,7 +564,7 @@ static int bnrelu_bwd_impl(const float* dy, const float* x, const float* coef, c
     return launch_status();
   }
   launch_pdl(bn_bwd_finalize, (C + kTallCols - 1) / kTallCols, kFinThreads, 0, st, (const float*)partial, nparts, phase == 2 ? Mstat : M, C,
-             training, dgamma, dbeta, c12, (const double*)(phase == 2 ? moments : nullptr));
+             training, dgamma, dbeta, c12, (const double*)(phase == 2 ? moments : nullptr), coef, dconv_bias);
   if ((rc = launch_status()) != VMTL_OK) return rc;
   if (!dx) return VMTL_OK;
 #define VMTL_BN_LAUNCH_PDL(KERN, ROWS, ...)                                                \
@@ -575,18 +585,19 @@ static int bnrelu_bwd_impl(const float* dy, const float* x, const float* coef, c
 
 extern "C" int vmtl_bnrelu_bwd(const float* dy, const float* x, const float* coef, const float* save_mean,
                                const float* save_invstd, int training, int relu, int64_t M, int C, float* dx,
-                               float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream) {
+                               float* dgamma, float* dbeta, float* dconv_bias, void* workspace, size_t workspace_bytes,
+                               void* stream) {
   return bnrelu_bwd_impl(dy, x, coef, save_mean, save_invstd, training, relu, M, C, 0, 0, 0, 0, dx, dgamma, dbeta,
-                         workspace, workspace_bytes, stream);
+                         workspace, workspace_bytes, stream, 0, nullptr, 0, dconv_bias);
 }
 
 extern "C" int vmtl_bnrelu_pool_bwd(const float* dy, const float* x, const float* coef, const float* save_mean,
                                     const float* save_invstd, int training, int relu, int B, int H, int W, int C,
-                                    float* dx, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
-                                    void* stream) {
+                                    float* dx, float* dgamma, float* dbeta, float* dconv_bias, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
   if (B < 1 || H < 2 || W < 2) return VMTL_EINVAL;
   return bnrelu_bwd_impl(dy, x, coef, save_mean, save_invstd, training, relu, (int64_t)B * H * W, C, B, H, W, 1, dx,
-                         dgamma, dbeta, workspace, workspace_bytes, stream);
+                         dgamma, dbeta, workspace, workspace_bytes, stream, 0, nullptr, 0, dconv_bias);
 }
 
 // ---- global-batch statistics: the two halves of each op around the caller's all-reduce -------------
@@ -599,12 +610,12 @@ extern "C" int vmtl_bn_moments(const float* x, int64_t M, int C, double* moments
 extern "C" int vmtl_bnrelu_fwd_global(const float* x, const float* gamma, const float* beta, float* running_mean,
                                       float* running_var, float momentum, float eps, int relu, int pool, int B, int H,
                                       int W, int C, const double* moments, int64_t M_global, float* y,
-                                      float* save_mean, float* save_invstd, float* coef, void* workspace,
-                                      size_t workspace_bytes, void* stream) {
+                                      float* save_mean, float* save_invstd, float* coef, const float* conv_bias,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
   if (B < 1 || H < 1 || W < 1 || (pool && (H < 2 || W < 2 || !y))) return VMTL_EINVAL;
   return bnrelu_fwd_impl(x, gamma, beta, running_mean, running_var, momentum, eps, 1, relu, (int64_t)B * H * W, C, B, H,
                          W, pool, y, save_mean, save_invstd, coef, workspace, workspace_bytes, stream, 2,
-                         const_cast<double*>(moments), M_global);
+                         const_cast<double*>(moments), M_global, conv_bias);
 }
 
 extern "C" int vmtl_bnrelu_bwd_moments(const float* dy, const float* x, const float* coef, const float* save_mean,

@@ -43,11 +43,27 @@ class _GatedAttention(nn.Module):
         y = act(bn(x))
         return y if pool is None else pool(y)
 
+    @classmethod
+    def _conv_bn_relu(cls, x: torch.Tensor, conv: nn.Conv2d, bn: nn.BatchNorm2d, act: nn.Module,
+                      pool: t.Optional[nn.Module] = None) -> torch.Tensor:
+        """``[pool(] act(bn(conv(x))) [)]``.  Under batch statistics the convolution runs WITHOUT its bias (the
+        normalisation cancels it; ``ops.conv_without_bias``) and the BatchNorm kernels take the bias for the
+        running mean and return its (analytically zero) gradient: no bias-add pass, no bias-gradient reduction."""
+        y, cb = ops.conv_without_bias(conv, x, bn) if isinstance(act, nn.ReLU) else (conv(x), None)
+        if cb is not None:
+            return ops.batch_norm_relu(y, bn, relu=True, pool=pool is not None, conv_bias=cb)
+        return cls._bn_relu(y, bn, act, pool)
+
     def _gate(self, merged: torch.Tensor, shared: torch.Tensor) -> torch.Tensor:
+        folded = (isinstance(self.relu1, nn.ReLU) and merged.is_cuda and self.conv1.out_channels % 4 == 0
+                  and ops.folded_gate_supported(torch.empty((0, self.conv1.out_channels, 1, 1), device=merged.device),
+                                                shared, self.bn1, self.bn2, self.gate_precision))
+        if folded:
+            # bn1 + relu1 are folded into the gate kernels: the hidden activation never reaches HBM; conv1's bias is
+            # folded into bn1 (batch statistics)
+            squeezed, cb = ops.conv_without_bias(self.conv1, merged, self.bn1)
+            return ops.attention_gate_folded(squeezed, self.bn1, shared, self.conv2, self.bn2, self.gate_precision, cb)
         squeezed = self.conv1(merged)
-        if isinstance(self.relu1, nn.ReLU) and ops.folded_gate_supported(squeezed, shared, self.bn1, self.bn2, self.gate_precision):
-            # bn1 + relu1 are folded into the gate kernels: the hidden activation never reaches HBM
-            return ops.attention_gate_folded(squeezed, self.bn1, shared, self.conv2, self.bn2, self.gate_precision)
         hidden = self._bn_relu(squeezed, self.bn1, self.relu1)
         bn = self.bn2
         use_batch_stats = bn.training or bn.running_mean is None
@@ -91,7 +107,7 @@ class AttentionModuleEncoder(_GatedAttention):
                 raise ValueError("prev_layer_outs must be provided for a non-first AttentionModuleEncoder")
             merged = torch.cat((conv1_shared, prev_layer_outs), dim=1)
         gated = self._gate(merged, conv2_shared)
-        return self._bn_relu(self.conv3(gated), self.bn3, self.relu2, self.maxpool)
+        return self._conv_bn_relu(gated, self.conv3, self.bn3, self.relu2, self.maxpool)
 
 
 class AttentionModuleDecoder(_GatedAttention):
@@ -121,13 +137,13 @@ class AttentionModuleDecoder(_GatedAttention):
         self.relu_out = nn.ReLU()
 
     def forward(self, conv1_shared, prev_layer_outs, conv2_shared):
-        prev = self._bn_relu(self.conv3(prev_layer_outs), self.bn3, self.relu2)
+        prev = self._conv_bn_relu(prev_layer_outs, self.conv3, self.bn3, self.relu2)
         if conv1_shared.shape[2:] != prev.shape[2:]:
             prev = self.up(prev)
         if conv1_shared.shape[2:] != conv2_shared.shape[2:]:
             raise ValueError("conv1_shared and conv2_shared must share their spatial size")
         gated = self._gate(torch.cat((conv1_shared, prev), dim=1), conv2_shared)
-        return self._bn_relu(self.conv_out(gated), self.bn_out, self.relu_out)
+        return self._conv_bn_relu(gated, self.conv_out, self.bn_out, self.relu_out)
 
 
 class MTANDown(nn.Module):

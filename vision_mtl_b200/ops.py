@@ -349,8 +349,12 @@ def _bump_batch_counter(bn) -> None:
         bn.num_batches_tracked.add_(1)
 
 
-def _bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, pool, y, stats, world):
-    """Statistics + finalize (+ apply when ``y`` is given) of one BatchNorm; ``world > 1`` all-reduces the moments."""
+def _bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, pool, y, stats, world,
+                conv_bias=None):
+    """Statistics + finalize (+ apply when ``y`` is given) of one BatchNorm; ``world > 1`` all-reduces the moments.
+    ``conv_bias`` (batch statistics only): the bias the producing convolution did NOT add -- it only moves the
+    running mean."""
+    cb = _p(conv_bias.detach()) if conv_bias is not None else _p(None)
     B, C, H, W = x.shape
     M = B * H * W
     dev = x.device
@@ -362,8 +366,8 @@ def _bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, e
         _allreduce_moments(mom)
         _call("bnrelu_fwd_global", 4 * C * (M + out_rows) if y is not None else 0, _p(x), _p(gamma.detach()),
               _p(beta.detach()), _p(running_mean), _p(running_var), float(momentum), float(eps), 1 if relu else 0,
-              1 if pool else 0, B, H, W, C, _p(mom), M * world, _p(y), _p(stats[0]), _p(stats[1]), _p(stats[2:]), _p(ws),
-              ws.numel(), _stream())
+              1 if pool else 0, B, H, W, C, _p(mom), M * world, _p(y), _p(stats[0]), _p(stats[1]), _p(stats[2:]), cb,
+              _p(ws), ws.numel(), _stream())
         if y is None:
             _Prof.launches -= 1
         return
@@ -371,16 +375,17 @@ def _bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, e
     if pool:
         _call("bnrelu_pool_fwd", nbytes, _p(x), _p(gamma.detach()), _p(beta.detach()), _p(running_mean),
               _p(running_var), float(momentum), float(eps), 1 if training else 0, 1 if relu else 0, B, H, W, C,
-              _p(y), _p(stats[0]), _p(stats[1]), _p(stats[2:]), _p(ws), ws.numel(), _stream())
+              _p(y), _p(stats[0]), _p(stats[1]), _p(stats[2:]), cb, _p(ws), ws.numel(), _stream())
     else:
         _call("bnrelu_fwd", nbytes, _p(x), _p(gamma.detach()), _p(beta.detach()), _p(running_mean),
               _p(running_var), float(momentum), float(eps), 1 if training else 0, 1 if relu else 0, M, C,
-              _p(y), _p(stats[0]), _p(stats[1]), _p(stats[2:]), _p(ws), ws.numel(), _stream())
+              _p(y), _p(stats[0]), _p(stats[1]), _p(stats[2:]), cb, _p(ws), ws.numel(), _stream())
     _Prof.launches -= (0 if training else 1) + (0 if y is not None else 1)  # no statistics / no apply pass
 
 
-def _bn_backward(dy, x, stats, training, relu, pool, need_dx, world):
-    """-> (dx | None, dgamma, dbeta) of one BatchNorm (+ReLU, +pool); ``world > 1``: global normalisation terms."""
+def _bn_backward(dy, x, stats, training, relu, pool, need_dx, world, want_dconv_bias=False):
+    """-> (dx | None, dgamma, dbeta[, dconv_bias]) of one BatchNorm (+ReLU, +pool); ``world > 1``: global
+    normalisation terms.  ``dconv_bias`` = sum over pixels of dx, the gradient of a folded convolution bias."""
     B, C, H, W = x.shape
     M = B * H * W
     dev = x.device
@@ -397,19 +402,25 @@ def _bn_backward(dy, x, stats, training, relu, pool, need_dx, world):
             _call("bnrelu_bwd_global", 4 * C * (2 * M + dy_rows), _p(dy), _p(x), _p(stats[2:]), _p(stats[0]),
                   _p(stats[1]), 1 if relu else 0, 1 if pool else 0, B, H, W, C, _p(mom), M * world, _p(dx), _p(ws),
                   ws.numel(), _stream())
+        if want_dconv_bias:  # this replica's sum of dx: A (sum_local g - M_local c1_global); sums to zero over replicas
+            dcb = stats[2] * (local[0] - (mom[0] * (float(M) / float(M * world))).to(torch.float32))
+            return dx, local[1], local[0], dcb
         return dx, local[1], local[0]
-    dgb = torch.empty((2, C), dtype=torch.float32, device=dev)
+    dgb = torch.empty((3 if want_dconv_bias else 2, C), dtype=torch.float32, device=dev)
+    dcb_p = _p(dgb[2]) if want_dconv_bias else _p(None)
     nbytes = 4 * C * (2 * (M + dy_rows) + (M if need_dx else 0))
     if pool:
         _call("bnrelu_pool_bwd", nbytes, _p(dy), _p(x), _p(stats[2:]), _p(stats[0]), _p(stats[1]),
-              1 if training else 0, 1 if relu else 0, B, H, W, C, _p(dx), _p(dgb[0]), _p(dgb[1]), _p(ws),
+              1 if training else 0, 1 if relu else 0, B, H, W, C, _p(dx), _p(dgb[0]), _p(dgb[1]), dcb_p, _p(ws),
               ws.numel(), _stream())
     else:
         _call("bnrelu_bwd", nbytes, _p(dy), _p(x), _p(stats[2:]), _p(stats[0]), _p(stats[1]),
-              1 if training else 0, 1 if relu else 0, M, C, _p(dx), _p(dgb[0]), _p(dgb[1]), _p(ws), ws.numel(),
+              1 if training else 0, 1 if relu else 0, M, C, _p(dx), _p(dgb[0]), _p(dgb[1]), dcb_p, _p(ws), ws.numel(),
               _stream())
     if not need_dx:
         _Prof.launches -= 1
+    if want_dconv_bias:
+        return dx, dgb[0], dgb[1], dgb[2]
     return dx, dgb[0], dgb[1]
 
 
@@ -417,7 +428,8 @@ class BNReLUFunction(torch.autograd.Function):
     """``[maxpool2(] relu( batch_norm(x) ) [)]`` in NHWC: statistics pass + apply pass (+ their backward)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, pool):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, pool, conv_bias=None):
+        """``conv_bias``: bias of the convolution that produced ``x`` WITHOUT adding it (batch statistics only)."""
         x = _nhwc(x)
         _need_cuda(x, gamma, beta)
         B, C, H, W = x.shape
@@ -428,17 +440,21 @@ class BNReLUFunction(torch.autograd.Function):
             y = torch.empty_like(x)
         stats = torch.empty((4, C), dtype=torch.float32, device=dev)  # save_mean, save_invstd, A, B
         world = stat_sync_world() if training else 1
-        _bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, pool, y, stats, world)
-        ctx.cfg = (bool(training), bool(relu), bool(pool), world)
+        if conv_bias is not None and not training:
+            raise ValueError("a folded convolution bias needs batch statistics (keep the bias in the convolution otherwise)")
+        _bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, pool, y, stats, world,
+                    conv_bias)
+        ctx.cfg = (bool(training), bool(relu), bool(pool), world, conv_bias is not None)
         ctx.save_for_backward(x, stats)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, stats = ctx.saved_tensors
-        training, relu, pool, world = ctx.cfg
-        dx, dgamma, dbeta = _bn_backward(_nhwc(dy), x, stats, training, relu, pool, ctx.needs_input_grad[0], world)
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None
+        training, relu, pool, world, has_cb = ctx.cfg
+        out = _bn_backward(_nhwc(dy), x, stats, training, relu, pool, ctx.needs_input_grad[0], world, has_cb)
+        dx, dgamma, dbeta = out[:3]
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, (out[3] if has_cb else None)
 
 
 def bn_supported(bn: torch.nn.Module, x: torch.Tensor) -> bool:
@@ -447,9 +463,23 @@ def bn_supported(bn: torch.nn.Module, x: torch.Tensor) -> bool:
             and x.shape[1] % 4 == 0 and 4 <= x.shape[1] <= 1024 and (bn.training or bn.running_mean is not None))
 
 
-def batch_norm_relu(x: torch.Tensor, bn: torch.nn.BatchNorm2d, relu: bool = True, pool: bool = False) -> torch.Tensor:
+def conv_without_bias(conv: torch.nn.Conv2d, x: torch.Tensor, bn: torch.nn.Module):
+    """``(conv(x) without its bias, bias)`` when ``bn`` -- which consumes the result next -- normalises with batch
+    statistics: those cancel a per-channel shift exactly, so the reference's bias-add pass over the output and its
+    backward reduction over all pixels are dead work; the BatchNorm kernels account for the bias where it matters (the
+    running mean; its gradient).  Otherwise ``(conv(x), None)``."""
+    C = getattr(conv, "out_channels", 0)
+    if (isinstance(conv, torch.nn.Conv2d) and conv.bias is not None and isinstance(bn, torch.nn.BatchNorm2d) and bn.affine
+            and (bn.training or bn.running_mean is None) and x.is_cuda and x.dtype == torch.float32
+            and C % 4 == 0 and 4 <= C <= 1024 and bn.num_features == C):
+        return conv._conv_forward(x, conv.weight, None), conv.bias
+    return conv(x), None
+
+
+def batch_norm_relu(x: torch.Tensor, bn: torch.nn.BatchNorm2d, relu: bool = True, pool: bool = False,
+                    conv_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``maxpool2(relu(bn(x)))`` (each optional) with ``bn``'s parameters, mode and running statistics
-    (updated in place like ``nn.BatchNorm2d.forward``)."""
+    (updated in place like ``nn.BatchNorm2d.forward``).  ``conv_bias``: see ``conv_without_bias``."""
     use_batch_stats = bn.training or bn.running_mean is None
     _bump_batch_counter(bn)
     if bn.momentum is None:  # cumulative moving average
@@ -458,7 +488,7 @@ def batch_norm_relu(x: torch.Tensor, bn: torch.nn.BatchNorm2d, relu: bool = True
         momentum = bn.momentum
     return BNReLUFunction.apply(x, bn.weight, bn.bias, bn.running_mean if bn.track_running_stats else None,
                                 bn.running_var if bn.track_running_stats else None, use_batch_stats, momentum,
-                                bn.eps, relu, pool)
+                                bn.eps, relu, pool, conv_bias)
 
 
 # --------------------------------------------------------------------------------------
@@ -593,7 +623,7 @@ class FoldedGateFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, c, g1, b1, rm1, rv1, train1, mom1, eps1, s, weight, bias, g2, b2, rm2, rv2, train2, mom2, eps2,
-                precision):
+                precision, conv1_bias=None):
         c = _nhwc(c)
         s = _nhwc(s)
         _need_cuda(c, s, weight)
@@ -601,27 +631,31 @@ class FoldedGateFunction(torch.autograd.Function):
         world1 = stat_sync_world() if train1 else 1
         world2 = stat_sync_world() if train2 else 1
         stats1 = torch.empty((4, K), dtype=torch.float32, device=c.device)  # mean1, invstd1, A1, B1
-        _bn_forward(c, g1, b1, rm1, rv1, train1, mom1, eps1, True, False, None, stats1, world1)
+        if conv1_bias is not None and not train1:
+            raise ValueError("a folded convolution bias needs batch statistics")
+        _bn_forward(c, g1, b1, rm1, rv1, train1, mom1, eps1, True, False, None, stats1, world1, conv1_bias)
         w2 = weight.detach().reshape(N, K).contiguous()
         need_z = train2 or any(ctx.needs_input_grad)
         y, z, mean2, invstd2 = _gate_forward(c, stats1[2:], s, w2, bias, g2, b2, rm2, rv2, train2, mom2, eps2,
                                              precision, need_z, world2)
-        ctx.cfg = (bool(train1), bool(train2), precision, weight.shape, world1, world2)
+        ctx.cfg = (bool(train1), bool(train2), precision, weight.shape, world1, world2, conv1_bias is not None)
         ctx.save_for_backward(c, stats1, s, z, w2, g2, b2, mean2, invstd2)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         c, stats1, s, z, w2, g2, b2, mean2, invstd2 = ctx.saved_tensors
-        train1, train2, precision, wshape, world1, world2 = ctx.cfg
-        need_dc = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        train1, train2, precision, wshape, world1, world2, has_cb = ctx.cfg
+        need_dc = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or has_cb
         dh, ds, dW, dbias, dg2, db2 = _gate_backward(_nhwc(dy), c, stats1[2:], s, z, w2, g2, b2, mean2, invstd2, train2,
                                                      precision, need_dc, ctx.needs_input_grad[8], world2)
-        dc = dg1 = db1 = None
+        dc = dg1 = db1 = dcb = None
         if need_dc:  # relu + bn1 backward over (dh, c): statistics pass, finalize, apply pass
-            dc, dg1, db1 = _bn_backward(dh, c, stats1, train1, True, False, ctx.needs_input_grad[0], world1)
+            out = _bn_backward(dh, c, stats1, train1, True, False, ctx.needs_input_grad[0], world1, has_cb)
+            dc, dg1, db1 = out[:3]
+            dcb = out[3] if has_cb else None
         return (dc, dg1, db1, None, None, None, None, None, ds, dW.reshape(wshape), dbias, dg2, db2,
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, dcb)
 
 
 def _bn_mode(bn):
@@ -642,16 +676,17 @@ def folded_gate_supported(c: torch.Tensor, s: torch.Tensor, bn1, bn2, precision:
             and bool(_lib.load().vmtl_gate_tc_supported(c.shape[1], s.shape[1])))
 
 
-def attention_gate_folded(c, bn1, s, conv2, bn2, precision: Optional[str] = None):
+def attention_gate_folded(c, bn1, s, conv2, bn2, precision: Optional[str] = None, conv1_bias=None):
     """The whole tail of an MTAN attention module after its 1x1 squeeze ``c = conv1(merged)``:
-    ``s * sigmoid(bn2(conv2(relu(bn1(c)))))`` (mtan_model.py:66-75 / :153-162)."""
+    ``s * sigmoid(bn2(conv2(relu(bn1(c)))))`` (mtan_model.py:66-75 / :153-162).  ``conv1_bias``: ``c`` was produced
+    without its bias (``conv_without_bias``)."""
     t1, m1 = _bn_mode(bn1)
     t2, m2 = _bn_mode(bn2)
     rs = lambda bn, name: getattr(bn, name) if bn.track_running_stats else None  # noqa: E731
     return FoldedGateFunction.apply(c, bn1.weight, bn1.bias, rs(bn1, "running_mean"), rs(bn1, "running_var"), t1, m1,
                                     bn1.eps, s, conv2.weight, conv2.bias, bn2.weight, bn2.bias, rs(bn2, "running_mean"),
                                     rs(bn2, "running_var"), t2, m2, bn2.eps,
-                                    _GATE_PRECISIONS[precision or default_gate_precision])
+                                    _GATE_PRECISIONS[precision or default_gate_precision], conv1_bias)
 
 
 def attention_gate(h, s, weight, bias, gamma, beta, running_mean, running_var, training: bool,
