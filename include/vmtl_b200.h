@@ -319,6 +319,18 @@ int vmtl_depth_err_sums(const float* pred, const float* target, int64_t P, float
  * from an int64 [C,C] confusion matrix (lit_module.py:48-67 configuration). */
 int vmtl_seg_metrics(const int64_t* conf, int C, float* metrics, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Bilinear x2 up-sampling, align_corners = True, NHWC -- nn.Upsample(scale_factor=2, mode="bilinear",
+ * align_corners=True) of the decoder attention modules (vision_mtl/models/mtan_model.py:125, applied at :143-144
+ * in front of torch.cat((conv1_shared, prev), dim=1), :145).  ATen's arithmetic (UpSampleBilinear2d.cu).
+ *   x [B,Hi,Wi,C] dense (C % 4 == 0); the up-sampled side is addressed with a row stride (floats between consecutive
+ *   pixels, >= C, % 4 == 0): y / dy may be the channel slice of a wider (concatenated) NHWC tensor, so the
+ *   concatenation never copies the up-sampled half and its backward never repacks the slice.
+ *   forward:  y[(b,oy,ox)*ldy + c], oy < 2 Hi, ox < 2 Wi.   backward: dx [B,Hi,Wi,C] dense, a deterministic gather.
+ * ---------------------------------------------------------------------------------- */
+int vmtl_up2_bilinear_fwd(const float* x, float* y, int B, int Hi, int Wi, int C, int64_t ldy, void* stream);
+int vmtl_up2_bilinear_bwd(const float* dy, int64_t lddy, float* dx, int B, int Hi, int Wi, int C, void* stream);
+
 /* Shape coverage of the fused heads: kind 0 = vmtl_head_ce_* (Cin, C), 1 = vmtl_head_silog_* (Cin),
  * 2 = vmtl_ce_logits_* (C).  Returns 1 when the sm_100a kernels cover the shape (else the calls return
  * VMTL_EUNSUPPORTED and the host side runs the 1x1 projection through cuDNN and the loss on its logits). */

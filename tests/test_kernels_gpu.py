@@ -407,6 +407,31 @@ def test_bn_relu_pool_fwd_bwd(B, C, H, W, training, relu, pool):
         assert torch.equal(bnd.running_mean.cpu(), bn.running_mean) and int(bnd.num_batches_tracked) == 0
 
 
+# ----------------------------------------------------------------------------- bilinear x2 up-sampling + cat
+@pytest.mark.parametrize("B,C1,Cx,Hi,Wi", [(2, 32, 128, 8, 16), (1, 64, 128, 1, 1), (3, 8, 4, 5, 7), (2, 128, 128, 16, 32),
+                                           (1, 4, 12, 2, 3), (2, 32, 128, 64, 128)])
+def test_upsample2_bilinear_cat(B, C1, Cx, Hi, Wi):
+    """``torch.cat((first, nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)(x)), 1)`` as the
+    decoder attention modules run it (mtan_model.py:125,143-145) against the fused op: output and both gradients."""
+    from vision_mtl_b200 import ops
+
+    g = torch.Generator().manual_seed(17)
+    first = to_cl(torch.randn(B, C1, 2 * Hi, 2 * Wi, generator=g))
+    x = to_cl(torch.randn(B, Cx, Hi, Wi, generator=g))
+    dy = to_cl(torch.randn(B, C1 + Cx, 2 * Hi, 2 * Wi, generator=g))
+    fr, xr = first.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    up = torch.nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+    yr = torch.cat((fr, up(xr)), dim=1)
+    yr.backward(dy)
+    fd, xd = first.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y = ops.upsample2_cat(fd, xd)
+    y.backward(dy)
+    assert y.is_contiguous(memory_format=torch.channels_last) or min(y.shape[1:]) == 1
+    assert_rel(y, yr, tol=2e-6, what="y")
+    assert torch.equal(fd.grad, fr.grad)
+    assert_rel(xd.grad, xr.grad, tol=2e-6, what="dx")
+
+
 # ----------------------------------------------------------------------------- gate with the folded hidden layer
 @pytest.mark.parametrize("pool", [False, True])
 @pytest.mark.parametrize("cin,cout,k,H,W", [(8, 32, 3, 16, 24), (12, 128, 1, 10, 14), (16, 64, 3, 9, 13)])

@@ -70,6 +70,8 @@ SIGNATURES = {
     "vmtl_gate_bwd_global": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, _P,
                                      c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "vmtl_silog_finalize": (c_int, [_P, _P, _P]),
+    "vmtl_up2_bilinear_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int64, _P]),
+    "vmtl_up2_bilinear_bwd": (c_int, [_P, c_int64, _P, c_int, c_int, c_int, c_int, _P]),
     "vmtl_head_supported": (c_int, [c_int, c_int, c_int]),
     "vmtl_adam_max_tensors_per_launch": (c_int, []),
     "vmtl_adam_step": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, c_double, _P, _P, c_double, c_double, c_double,

@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(REPO_DIR, "include")
 LIB_PATH = os.path.join(PKG_DIR, "libvmtl_b200.so")
 
-SOURCES = ["capi.cu", "adam.cu", "bnrelu.cu", "xstitch.cu", "metrics.cu", "head_loss.cu", "head_tc.cu", "head_tc_bwd.cu", "gate.cu", "gate_tc.cu"]
+SOURCES = ["capi.cu", "adam.cu", "bnrelu.cu", "xstitch.cu", "metrics.cu", "head_loss.cu", "head_tc.cu", "head_tc_bwd.cu", "gate.cu", "gate_tc.cu", "upsample.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

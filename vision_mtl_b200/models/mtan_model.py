@@ -138,11 +138,17 @@ class AttentionModuleDecoder(_GatedAttention):
 
     def forward(self, conv1_shared, prev_layer_outs, conv2_shared):
         prev = self._conv_bn_relu(prev_layer_outs, self.conv3, self.bn3, self.relu2)
-        if conv1_shared.shape[2:] != prev.shape[2:]:
-            prev = self.up(prev)
         if conv1_shared.shape[2:] != conv2_shared.shape[2:]:
             raise ValueError("conv1_shared and conv2_shared must share their spatial size")
-        gated = self._gate(torch.cat((conv1_shared, prev), dim=1), conv2_shared)
+        up = self.up
+        if (conv1_shared.shape[2:] != prev.shape[2:] and isinstance(up, nn.Upsample) and up.mode == "bilinear"
+                and up.align_corners and up.scale_factor == 2 and ops.upsample2_cat_supported(conv1_shared, prev)):
+            merged = ops.upsample2_cat(conv1_shared, prev)  # up-sampled straight into its slice of the concatenation
+        else:
+            if conv1_shared.shape[2:] != prev.shape[2:]:
+                prev = up(prev)
+            merged = torch.cat((conv1_shared, prev), dim=1)
+        gated = self._gate(merged, conv2_shared)
         return self._conv_bn_relu(gated, self.conv_out, self.bn_out, self.relu_out)
 
 

@@ -492,6 +492,54 @@ def batch_norm_relu(x: torch.Tensor, bn: torch.nn.BatchNorm2d, relu: bool = True
 
 
 # --------------------------------------------------------------------------------------
+# Bilinear x2 up-sampling fused with the concatenation behind it
+# --------------------------------------------------------------------------------------
+class UpsampleCatFunction(torch.autograd.Function):
+    """``torch.cat((first, upsample2_bilinear_align_corners(x)), dim=1)`` in NHWC (mtan_model.py:143-145): the
+    up-sampled half is written straight into its channel slice of the result, and in the backward its gradient is
+    gathered straight out of that slice (no repacking copy); ``first`` gets its slice of the gradient as a view."""
+
+    @staticmethod
+    def forward(ctx, first, x):
+        first, x = _nhwc(first), _nhwc(x)
+        _need_cuda(first, x)
+        B, C1, Ho, Wo = first.shape
+        _, Cx, Hi, Wi = x.shape
+        if (Ho, Wo) != (2 * Hi, 2 * Wi) or C1 % 4 or Cx % 4:
+            raise ValueError("upsample_cat needs first [B,C1,2H,2W], x [B,Cx,H,W] with C1, Cx multiples of 4")
+        out = torch.empty((B, C1 + Cx, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+        out[:, :C1].copy_(first)
+        _call("up2_bilinear_fwd", 20 * x.numel(), _p(x), ctypes.c_void_p(out.data_ptr() + 4 * C1), B, Hi, Wi, Cx,
+              C1 + Cx, _stream())
+        ctx.geom = (B, C1, Cx, Hi, Wi)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, C1, Cx, Hi, Wi = ctx.geom
+        dout = _nhwc(dout)
+        dfirst = dout[:, :C1] if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[1]:
+            dx = torch.empty((B, Cx, Hi, Wi), dtype=torch.float32, device=dout.device, memory_format=torch.channels_last)
+            _call("up2_bilinear_bwd", 20 * dx.numel(), ctypes.c_void_p(dout.data_ptr() + 4 * C1), C1 + Cx, _p(dx), B, Hi,
+                  Wi, Cx, _stream())
+        return dfirst, dx
+
+
+def upsample2_cat(first: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """``cat((first, bilinear_x2(x, align_corners=True)), dim=1)``; see ``UpsampleCatFunction``."""
+    return UpsampleCatFunction.apply(first, x)
+
+
+def upsample2_cat_supported(first: torch.Tensor, x: torch.Tensor) -> bool:
+    return (first.is_cuda and x.is_cuda and first.dtype == torch.float32 and x.dtype == torch.float32
+            and first.dim() == 4 and x.dim() == 4 and first.shape[0] == x.shape[0]
+            and first.shape[2] == 2 * x.shape[2] and first.shape[3] == 2 * x.shape[3]
+            and first.shape[1] % 4 == 0 and x.shape[1] % 4 == 0)
+
+
+# --------------------------------------------------------------------------------------
 # MTAN attention gate
 # --------------------------------------------------------------------------------------
 def _gate_bwd_passes(M: int, N: int):
