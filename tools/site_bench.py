@@ -5,7 +5,7 @@ CUDA events around the replay (device time of all launches of the call, no host 
 flush (write of a 256 MiB buffer) before every replay and between forward and backward, and reported
 as algorithmic GB/s against MEASURED_PEAKS.json.  Also the target command for the ncu captures kept under profiles/.
 
-    python tools/site_bench.py [--iters 5] [--only gate|bn|xstitch|heads|metrics] [--once] [--json out.json]
+    python tools/site_bench.py [--iters 5] [--only gate|bn|up|xstitch|heads|metrics] [--once] [--json out.json]
 """
 from __future__ import annotations
 
@@ -154,6 +154,26 @@ def main():
 
             timed("bnrelu_pool" if pool else "bnrelu", f"C={Cc} M={M}", 4 * Cc * (2 * M + out_rows),
                   4 * Cc * (2 * (M + out_rows) + M), fwd_b, bwd_b)
+
+    if args.only in ("", "up"):
+        # decoder attention modules: cat((conv1_shared, bilinear_x2(prev)), 1) -- dec3 / dec2 / dec1 of the MTAN network
+        up_sites = ((64, 128, 1), (128, 128, 2), (256, 128, 4))
+        for C1, Cx, down in (up_sites[:1] if args.profile_set else up_sites):
+            h, w = H // down, W // down
+            first = cl(B, C1, h, w).requires_grad_(True)
+            xin = cl(B, Cx, h // 2, w // 2).requires_grad_(True)
+            dyu = cl(B, C1 + Cx, h, w)
+
+            def fwd_u():
+                return ops.upsample2_cat(first, xin)
+
+            def bwd_u(y):
+                first.grad = xin.grad = None
+                y.backward(dyu)
+
+            # algorithmic: the up-sampling itself (R x, W 4x) + the copy of `first` into the concatenation (R + W)
+            nb = 20 * xin.numel() + 8 * first.numel()
+            timed("up2_cat", f"C1={C1} Cx={Cx} {h}x{w}", nb, 20 * xin.numel(), fwd_u, bwd_u)
 
     if args.only in ("", "xstitch"):
         for Cc, h, w in (XS_SITES[-1:] if args.profile_set else XS_SITES):

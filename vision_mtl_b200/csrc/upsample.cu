@@ -35,26 +35,38 @@ __device__ __forceinline__ Src up_src(float r, int dst, int in) {
   return s;
 }
 
+// Thread layout (both kernels): `cpl` lanes walk the float4 channel groups of a pixel (each lane takes every cpl-th
+// group: 4 groups per lane for the 128-channel maps, so the per-pixel index / weight arithmetic -- the kernels are
+// issue-bound, ncu: 63-72 % issue-slot use at 1 group per thread -- is paid once per 64 bytes), the other 256 / cpl
+// thread rows take consecutive pixels; 8 lanes x 16 B = one full 128-byte line.  All index arithmetic is 32-bit.
+__host__ __device__ inline unsigned up_lanes(int C4) {
+  return C4 >= 32 ? (unsigned)C4 / 4 : (C4 >= 8 ? 8u : (unsigned)C4);
+}
 __global__ void __launch_bounds__(kUpThreads)
     up2_bilinear_fwd_kernel(const float4* __restrict__ x, float* __restrict__ y, int B, int Hi, int Wi, int C4,
                             int64_t ldy /* floats between consecutive output pixels */, float ry, float rx) {
-  const int Ho = 2 * Hi, Wo = 2 * Wi;
-  const int64_t total = (int64_t)B * Ho * Wo * C4;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(idx % C4);
-    const int64_t pix = idx / C4;
-    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((int64_t)Wo * Ho));
-    const Src sy = up_src(ry, oy, Hi), sx = up_src(rx, ox, Wi);
-    const float4* row0 = x + ((int64_t)(b * Hi + sy.i1) * Wi) * C4 + c4;
-    const float4* row1 = row0 + (int64_t)sy.i1p * Wi * C4;
-    const float4 p00 = __ldg(row0 + (int64_t)sx.i1 * C4), p01 = __ldg(row0 + (int64_t)(sx.i1 + sx.i1p) * C4);
-    const float4 p10 = __ldg(row1 + (int64_t)sx.i1 * C4), p11 = __ldg(row1 + (int64_t)(sx.i1 + sx.i1p) * C4);
-    float4 o;
-    o.x = sy.l0 * (sx.l0 * p00.x + sx.l1 * p01.x) + sy.l1 * (sx.l0 * p10.x + sx.l1 * p11.x);
-    o.y = sy.l0 * (sx.l0 * p00.y + sx.l1 * p01.y) + sy.l1 * (sx.l0 * p10.y + sx.l1 * p11.y);
-    o.z = sy.l0 * (sx.l0 * p00.z + sx.l1 * p01.z) + sy.l1 * (sx.l0 * p10.z + sx.l1 * p11.z);
-    o.w = sy.l0 * (sx.l0 * p00.w + sx.l1 * p01.w) + sy.l1 * (sx.l0 * p10.w + sx.l1 * p11.w);
-    stg_stream(reinterpret_cast<float4*>(y + pix * ldy) + c4, o);
+  const unsigned Ho = 2u * Hi, Wo = 2u * Wi;
+  const unsigned npix = (unsigned)B * Ho * Wo;
+  const unsigned cpl = up_lanes(C4), rows = kUpThreads / cpl;
+  const unsigned lane = threadIdx.x % cpl, r = threadIdx.x / cpl;
+  if (r >= rows) return;
+  for (unsigned pix = blockIdx.x * rows + r; pix < npix; pix += gridDim.x * rows) {
+    const unsigned q = pix / Wo, ox = pix - q * Wo, b = q / Ho, oy = q - b * Ho;
+    const Src sy = up_src(ry, (int)oy, Hi), sx = up_src(rx, (int)ox, Wi);
+    const float4* row0 = x + (size_t)((b * Hi + sy.i1) * (unsigned)Wi) * C4;
+    const float4* row1 = row0 + (size_t)sy.i1p * Wi * C4;
+    const size_t c0 = (size_t)sx.i1 * C4, c1 = (size_t)(sx.i1 + sx.i1p) * C4;
+    float4* out = reinterpret_cast<float4*>(y + (size_t)pix * ldy);
+    for (unsigned c4 = lane; c4 < (unsigned)C4; c4 += cpl) {
+      const float4 p00 = __ldg(row0 + c0 + c4), p01 = __ldg(row0 + c1 + c4);
+      const float4 p10 = __ldg(row1 + c0 + c4), p11 = __ldg(row1 + c1 + c4);
+      float4 o;  // ATen's association: l0y (l0x a + l1x b) + l1y (l0x c + l1x d)
+      o.x = sy.l0 * (sx.l0 * p00.x + sx.l1 * p01.x) + sy.l1 * (sx.l0 * p10.x + sx.l1 * p11.x);
+      o.y = sy.l0 * (sx.l0 * p00.y + sx.l1 * p01.y) + sy.l1 * (sx.l0 * p10.y + sx.l1 * p11.y);
+      o.z = sy.l0 * (sx.l0 * p00.z + sx.l1 * p01.z) + sy.l1 * (sx.l0 * p10.z + sx.l1 * p11.z);
+      o.w = sy.l0 * (sx.l0 * p00.w + sx.l1 * p01.w) + sy.l1 * (sx.l0 * p10.w + sx.l1 * p11.w);
+      stg_stream(out + c4, o);
+    }
   }
 }
 
@@ -68,37 +80,42 @@ __global__ void __launch_bounds__(kUpThreads)
     up2_bilinear_bwd_kernel(const float* __restrict__ dy, int64_t lddy, float4* __restrict__ dx, int B, int Hi, int Wi,
                             int C4, float ry, float rx) {
   const int Ho = 2 * Hi, Wo = 2 * Wi;
-  const int64_t total = (int64_t)B * Hi * Wi * C4;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(idx % C4);
-    const int64_t pix = idx / C4;
-    const int ix = (int)(pix % Wi), iy = (int)((pix / Wi) % Hi), b = (int)(pix / ((int64_t)Wi * Hi));
-    float wy[6], wx[6];
+  const unsigned npix = (unsigned)B * Hi * Wi;
+  const unsigned cpl = up_lanes(C4), rows = kUpThreads / cpl;
+  const unsigned lane = threadIdx.x % cpl, r = threadIdx.x / cpl;
+  if (r >= rows) return;
+  for (unsigned pix = blockIdx.x * rows + r; pix < npix; pix += gridDim.x * rows) {
+    const unsigned q = pix / (unsigned)Wi, b = q / (unsigned)Hi;
+    const int ix = (int)(pix - q * Wi), iy = (int)(q - b * Hi);
+    float wx[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-      const int oy = 2 * iy - 2 + k, ox = 2 * ix - 2 + k;
-      wy[k] = (oy >= 0 && oy < Ho) ? up_weight(ry, oy, Hi, iy) : 0.f;
+      const int ox = 2 * ix - 2 + k;
       wx[k] = (ox >= 0 && ox < Wo) ? up_weight(rx, ox, Wi, ix) : 0.f;
     }
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (unsigned c4 = lane; c4 < (unsigned)C4; c4 += cpl) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1  // rows one at a time (fully unrolled, the 6 x 6 gather needs ~200 registers: one block per SM)
+      for (int ky = 0; ky < 6; ++ky) {
+        const int oy = 2 * iy - 2 + ky;
+        if (oy < 0 || oy >= Ho) continue;
+        const float wyv = up_weight(ry, oy, Hi, iy);
+        if (wyv == 0.f) continue;
+        const float* row = dy + ((size_t)(b * Ho + oy) * Wo) * lddy + 4 * c4;
 #pragma unroll
-    for (int ky = 0; ky < 6; ++ky) {
-      if (wy[ky] == 0.f) continue;
-      const int oy = 2 * iy - 2 + ky;
-      const float* row = dy + ((int64_t)(b * Ho + oy) * Wo) * lddy + 4 * c4;
-#pragma unroll
-      for (int kx = 0; kx < 6; ++kx) {
-        if (wx[kx] == 0.f) continue;
-        const int ox = 2 * ix - 2 + kx;
-        const float4 g = __ldg(reinterpret_cast<const float4*>(row + (int64_t)ox * lddy));
-        const float w = wy[ky] * wx[kx];
-        acc.x = fmaf(w, g.x, acc.x);
-        acc.y = fmaf(w, g.y, acc.y);
-        acc.z = fmaf(w, g.z, acc.z);
-        acc.w = fmaf(w, g.w, acc.w);
+        for (int kx = 0; kx < 6; ++kx) {
+          if (wx[kx] == 0.f) continue;
+          const int ox = 2 * ix - 2 + kx;
+          const float4 g = __ldg(reinterpret_cast<const float4*>(row + (size_t)ox * lddy));
+          const float w = wyv * wx[kx];
+          acc.x = fmaf(w, g.x, acc.x);
+          acc.y = fmaf(w, g.y, acc.y);
+          acc.z = fmaf(w, g.z, acc.z);
+          acc.w = fmaf(w, g.w, acc.w);
+        }
       }
+      stg_stream(dx + (size_t)pix * C4 + c4, acc);
     }
-    stg_stream(dx + idx, acc);
   }
 }
 
@@ -108,8 +125,9 @@ static int up_check(int B, int Hi, int Wi, int C, int64_t ld) {
   if ((int64_t)B * Hi * Wi * 4 >= (1ll << 31)) return VMTL_EUNSUPPORTED;  // 32-bit pixel arithmetic
   return VMTL_OK;
 }
-static int up_grid(int64_t work, int (*occ)(void)) {
-  int64_t want = (work + kUpThreads - 1) / kUpThreads;
+static int up_grid(int64_t npix, int C4, int (*occ)(void)) {
+  const int cpl = (int)up_lanes(C4), rows = kUpThreads / cpl;
+  int64_t want = (npix + rows - 1) / rows;
   const int64_t cap = (int64_t)sm_count() * occ();
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
@@ -126,8 +144,7 @@ extern "C" int vmtl_up2_bilinear_fwd(const float* x, float* y, int B, int Hi, in
   int rc = up_check(B, Hi, Wi, C, ldy);
   if (rc != VMTL_OK) return rc;
   if (!aligned16(x) || !aligned16(y)) return VMTL_EALIGN;
-  const int64_t work = (int64_t)B * Hi * Wi * 4 * (C / 4);
-  up2_bilinear_fwd_kernel<<<up_grid(work, occ_fwd), kUpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  up2_bilinear_fwd_kernel<<<up_grid((int64_t)B * Hi * Wi * 4, C / 4, occ_fwd), kUpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(x), y, B, Hi, Wi, C / 4, ldy, up_ratio(Hi), up_ratio(Wi));
   return launch_status();
 }
@@ -138,8 +155,7 @@ extern "C" int vmtl_up2_bilinear_bwd(const float* dy, int64_t lddy, float* dx, i
   int rc = up_check(B, Hi, Wi, C, lddy);
   if (rc != VMTL_OK) return rc;
   if (!aligned16(dy) || !aligned16(dx)) return VMTL_EALIGN;
-  const int64_t work = (int64_t)B * Hi * Wi * (C / 4);
-  up2_bilinear_bwd_kernel<<<up_grid(work, occ_bwd), kUpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  up2_bilinear_bwd_kernel<<<up_grid((int64_t)B * Hi * Wi, C / 4, occ_bwd), kUpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       dy, lddy, reinterpret_cast<float4*>(dx), B, Hi, Wi, C / 4, up_ratio(Hi), up_ratio(Wi));
   return launch_status();
 }
