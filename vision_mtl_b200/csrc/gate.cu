@@ -251,7 +251,11 @@ __global__ void __launch_bounds__(kFinThreads)
 // Blocks [0, N * K/32): one [1 row n x 32 k] patch of dW each.  1024 threads = 32 k-lanes x (1 row x 32 part groups): every thread sums its share
 // of the partial rows (a handful of independent loads in flight), the 8 groups are combined in a fixed order.
 // The last ceil(N/32) blocks produce the per-channel outputs and the folded coefficients pass 2 needs.
-constexpr int kFinRows = 1, kFinGroups = 32;  // (4, 8) left 33 blocks walking 148 partial slices in 5-step chains: 11-17 us
+// ROWS rows of dW per block, 32 / ROWS part groups.  Narrow gates (N <= 64: every CTA of pass 1 holds the whole N, 148
+// partial slices per dW element) want ROWS = 1: with 4 rows the launch was 33-66 blocks walking 5-step chains (17 us in
+// ncu); wide gates (column chunks split the CTAs: 37-74 slices per element) want ROWS = 4, else the launch is a thousand
+// mostly idle 1024-thread blocks (26 us at N = 256 against 14).
+template <int kFinRows>
 __global__ void __launch_bounds__(kFinThreads)
     gate_bwd_tc_finalize(const float* __restrict__ pw_partial, const float* __restrict__ hs_partial,
                          const float* __restrict__ col_partial, int nparts, int nch, int64_t M, int N, int K,
@@ -262,6 +266,7 @@ __global__ void __launch_bounds__(kFinThreads)
                          float* __restrict__ coefB, float* __restrict__ mean_out, float* __restrict__ invstd_out,
                          const double* __restrict__ gmoments /* NULL, or global (sum du, sum du zhat) [2][N] */,
                          int64_t Mstat /* rows behind gmoments */) {
+  constexpr int kFinGroups = 32 / kFinRows;
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const int Nc = N / nch, per_chunk = nparts / nch;
   const int kslabs = K / 32;
@@ -678,7 +683,13 @@ static int gate_bwd_impl(const float* dy, const float* h, const float* h_coef, c
       gate_bwd_tc_moments<<<(N + 31) / 32, kFinThreads, 0, st>>>(ws.partial, np1, nch, N, moments);
       return launch_status();
     }
-    gate_bwd_tc_finalize<<<(N / kFinRows) * (K / 32) + (N + 31) / 32, kFinThreads, 0, st>>>(
+    if (N <= 64)
+      gate_bwd_tc_finalize<1><<<N * (K / 32) + (N + 31) / 32, kFinThreads, 0, st>>>(
+        ws.gemm_partial, ws.hs_partial, ws.partial, np1, nch, M, N, K, training, gamma, beta, save_mean, save_invstd, dW,
+        dbias, dgamma, dbeta, ws.c1, ws.c2, ws.coefA, ws.coefB, ws.mean, ws.invstd, phase == 2 ? moments : nullptr,
+        Mstat);
+    else
+      gate_bwd_tc_finalize<4><<<(N / 4) * (K / 32) + (N + 31) / 32, kFinThreads, 0, st>>>(
         ws.gemm_partial, ws.hs_partial, ws.partial, np1, nch, M, N, K, training, gamma, beta, save_mean, save_invstd, dW,
         dbias, dgamma, dbeta, ws.c1, ws.c2, ws.coefA, ws.coefB, ws.mean, ws.invstd, phase == 2 ? moments : nullptr,
         Mstat);
