@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
     ap.add_argument("--conv-tf32", action="store_true", help="allow TF32 in the cuDNN 3x3 convs (default: strict fp32)")
+    ap.add_argument("--conv-3xtf32", action="store_true",
+                    help="EXPERIMENTAL: fp32-grade convolutions as channel-stacked 3xTF32 cuDNN calls (vision_mtl_b200/conv3x.py)")
     ap.add_argument("--gate-precision", default="tc_3xtf32", choices=["tc_3xtf32", "tc_tf32", "fp32_ffma"])
     ap.add_argument("--stitch-mode", default="reference_diag", choices=["reference_diag", "full_mix"])
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
@@ -479,7 +481,8 @@ def run_workload(args, name: str, rank: int, local_rank: int, world: int, with_p
             "config": {
                 "workload": workload_text(name, B),
                 "global_batch": B * world, "parallelism": f"dp{world}",
-                "conv_math": "tf32 (cuDNN)" if args.conv_tf32 else "fp32 (cuDNN, TF32 off)",
+                "conv_math": ("3xTF32 channel-stacked cuDNN tensor-core convolutions (fp32-grade, experimental)" if args.conv_3xtf32
+                              else "tf32 (cuDNN)" if args.conv_tf32 else "fp32 (cuDNN, TF32 off)"),
                 "gate_precision": args.gate_precision, "stitch_mode": args.stitch_mode,
                 "step_launch": "one CUDA graph per step (fwd + fused losses/metrics + bwd + Adam)" if graphed is not None else "eager",
                 "l2": "per-step working set (activations of a batch-%d step) >> 126 MB L2; no explicit flush" % B,
@@ -527,6 +530,10 @@ def main():
     torch.backends.cudnn.allow_tf32 = bool(args.conv_tf32)
     torch.backends.cuda.matmul.allow_tf32 = bool(args.conv_tf32)
     torch.backends.cudnn.benchmark = True
+    if args.conv_3xtf32:
+        from vision_mtl_b200 import conv3x
+
+        conv3x.enable(True)
     ops.default_gate_precision = args.gate_precision
 
     names = list(ALL_ORDER) if args.workload == "all" else [args.workload]
