@@ -114,3 +114,47 @@ def test_csnet_plan_and_state_dict_keys():
     # decoder site fused with its nearest x2 up-sampling
     assert ops_.count("stitch") == 6 and ops_.count("cat_stitch") == 4 and ops_.count("up_stitch") == 1
     assert ops_.count("save_skip") == 4 and ops_.count("cat_skip") == 0 and ops_.count("upsample2") == 0
+
+
+def test_host_side_rewrites_are_identities_off_gpu():
+    """The two host-side rewrites of the drop-in modules must leave CPU / eval behaviour
+    untouched: ``conv_without_bias`` keeps the bias unless a CUDA batch-statistics BatchNorm consumes the result, the
+    deferred BatchNorm step counters add up exactly once per call, and the optimizer's layout predicate only accepts
+    tensors whose elements pair up in memory."""
+    from vision_mtl_b200 import ops
+    from vision_mtl_b200.optim import _same_layout
+
+    conv, bn = torch.nn.Conv2d(8, 16, 3, padding=1), torch.nn.BatchNorm2d(16)
+    x = torch.randn(2, 8, 5, 7)
+    y, cb = ops.conv_without_bias(conv, x, bn)  # CPU tensor: stock path
+    assert cb is None and torch.equal(y, conv(x))
+    bn.eval()
+    y, cb = ops.conv_without_bias(conv, x, bn)
+    assert cb is None
+    bn.train()
+    bn2 = torch.nn.BatchNorm2d(16, momentum=None)  # cumulative average: needs its count at call time
+    with ops.deferred_batch_counters():
+        ops._bump_batch_counter(bn)
+        ops._bump_batch_counter(bn)
+        ops._bump_batch_counter(bn2)
+        assert int(bn.num_batches_tracked) == 0 and int(bn2.num_batches_tracked) == 1
+    assert int(bn.num_batches_tracked) == 2 and int(bn2.num_batches_tracked) == 1
+    ops._bump_batch_counter(bn)
+    assert int(bn.num_batches_tracked) == 3
+    a = torch.randn(8, 4, 3, 3)
+    b = a.contiguous(memory_format=torch.channels_last)
+    assert _same_layout(a, a.clone()) and _same_layout(b, b.clone()) and not _same_layout(a, b)
+    c = torch.randn(8, 4, 1, 1)
+    assert _same_layout(c, c.contiguous(memory_format=torch.channels_last))  # size-1 dimensions do not matter
+    assert not _same_layout(a, a[:, ::2])
+
+
+def test_conv3x_split_is_exact():
+    """The hi / lo split behind the opt-in 3xTF32 convolutions: hi has 13 zero low mantissa bits, hi + lo == x exactly."""
+    from vision_mtl_b200.conv3x import tf32_split
+
+    x = torch.randn(10000) * torch.logspace(-20, 20, 10000)
+    hi, lo = tf32_split(x)
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert torch.equal(hi + lo, x)
+    assert float((lo.abs() / x.abs().clamp_min(1e-38)).max()) <= 2.0 ** -11
