@@ -20,6 +20,7 @@
 namespace vmtl {
 
 constexpr int kUpThreads = 256;
+constexpr int kUpGroups = 4;  // channel groups a lane of the backward kernel carries per pixel
 
 struct Src {
   int i1, i1p;
@@ -93,28 +94,42 @@ __global__ void __launch_bounds__(kUpThreads)
       const int ox = 2 * ix - 2 + k;
       wx[k] = (ox >= 0 && ox < Wo) ? up_weight(rx, ox, Wi, ix) : 0.f;
     }
-    for (unsigned c4 = lane; c4 < (unsigned)C4; c4 += cpl) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // up to kUpGroups channel groups per lane share the row / column weights of the pixel
+    for (unsigned cb = lane; cb < (unsigned)C4; cb += kUpGroups * cpl) {
+      float4 acc[kUpGroups];
+#pragma unroll
+      for (int j = 0; j < kUpGroups; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1  // rows one at a time (fully unrolled, the 6 x 6 gather needs ~200 registers: one block per SM)
       for (int ky = 0; ky < 6; ++ky) {
         const int oy = 2 * iy - 2 + ky;
         if (oy < 0 || oy >= Ho) continue;
         const float wyv = up_weight(ry, oy, Hi, iy);
         if (wyv == 0.f) continue;
-        const float* row = dy + ((size_t)(b * Ho + oy) * Wo) * lddy + 4 * c4;
+        const float* row = dy + ((size_t)(b * Ho + oy) * Wo) * lddy;
 #pragma unroll
         for (int kx = 0; kx < 6; ++kx) {
           if (wx[kx] == 0.f) continue;
           const int ox = 2 * ix - 2 + kx;
-          const float4 g = __ldg(reinterpret_cast<const float4*>(row + (size_t)ox * lddy));
+          const float4* src = reinterpret_cast<const float4*>(row + (size_t)ox * lddy);
           const float w = wyv * wx[kx];
-          acc.x = fmaf(w, g.x, acc.x);
-          acc.y = fmaf(w, g.y, acc.y);
-          acc.z = fmaf(w, g.z, acc.z);
-          acc.w = fmaf(w, g.w, acc.w);
+#pragma unroll
+          for (int j = 0; j < kUpGroups; ++j) {
+            const unsigned c4 = cb + j * cpl;
+            if (c4 < (unsigned)C4) {
+              const float4 g = __ldg(src + c4);
+              acc[j].x = fmaf(w, g.x, acc[j].x);
+              acc[j].y = fmaf(w, g.y, acc[j].y);
+              acc[j].z = fmaf(w, g.z, acc[j].z);
+              acc[j].w = fmaf(w, g.w, acc[j].w);
+            }
+          }
         }
       }
-      stg_stream(dx + (size_t)pix * C4 + c4, acc);
+#pragma unroll
+      for (int j = 0; j < kUpGroups; ++j) {
+        const unsigned c4 = cb + j * cpl;
+        if (c4 < (unsigned)C4) stg_stream(dx + (size_t)pix * C4 + c4, acc[j]);
+      }
     }
   }
 }
