@@ -1,4 +1,5 @@
-"""The whole-step CUDA graph must do exactly what the eager step does."""
+"""The whole-step CUDA graph must do exactly what the eager step does: with cuDNN pinned to deterministic algorithms
+the replays are bit-equal to eager steps (every kernel of the library is deterministic)."""
 import pytest
 import torch
 
@@ -17,6 +18,22 @@ def test_graphed_step_equals_eager(model_name):
 
     dev = torch.device("cuda:0")
     C = 19
+    # deterministic cuDNN algorithms: every kernel of the library is deterministic, so with cuDNN pinned the graph
+    # replays must reproduce the eager steps to round-off instead of to "cuDNN run-to-run noise"
+    prev = (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32)
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32 = True, False, False
+    try:
+        _graph_vs_eager(model_name, dev, C)
+    finally:
+        torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32 = prev
+
+
+def _graph_vs_eager(model_name, dev, C):
+    from vision_mtl_b200.graph_step import GraphedTrainStep
+    from vision_mtl_b200.lit_module import MTLModule
+    from vision_mtl_b200.models import CSNet
+    from vision_mtl_b200.models.mtan_model import MTANMiniUnet
+    from vision_mtl_b200.utils.model_utils import get_model_with_dense_preds
 
     def build():
         torch.manual_seed(3)
@@ -73,9 +90,12 @@ def test_graphed_step_equals_eager(model_name):
     assert len(mod_g.step_outputs["train"]["loss"]) == 0  # capture leaves no stale records behind
     # same weights, same batch -> the first replay reproduces the eager loss
     for le, lg in zip(losses_e[3:], losses_g):
-        assert abs(le - lg) <= 5e-3 * abs(le), (losses_e, losses_g)
+        assert abs(le - lg) <= 1e-6 * abs(le), (losses_e, losses_g)  # measured: bit-equal
     rel = param_diffs(net_e, net_g)
     med, worst = rel[len(rel) // 2][0], rel[-1][0]
-    assert med <= max(1e-5, 4 * noise[len(noise) // 2][0]), (rel[len(rel) // 2], noise[len(noise) // 2])
-    assert worst <= max(1e-3, 4 * noise[-1][0]), (rel[-4:], noise[-4:])
+    print(f"[{model_name}] graph vs eager: losses {losses_e[3:]} / {losses_g}; params median {med:.2e} worst {rel[-1]}; "
+          f"eager vs eager worst {noise[-1]}")
+    # measured on B200: median and worst are exactly 0.0 (the replays are bit-equal to the eager steps)
+    assert med <= max(1e-7, 4 * noise[len(noise) // 2][0]), (rel[len(rel) // 2], noise[len(noise) // 2])
+    assert worst <= max(1e-6, 4 * noise[-1][0]), (rel[-4:], noise[-4:])
     assert torch.equal(mod_g.last_confusion.sum(), torch.tensor(2 * 64 * 64, device=dev))
