@@ -295,6 +295,15 @@ def test_module_api_compat_paths():
     assert preds["segm"].shape == (2, 32, 32) and preds["depth"].shape == (2, 32, 32, 1)
     ep = module.on_predict_epoch_end()
     assert set(ep) == {"predict/loss", "predict/accuracy", "predict/jaccard_index", "predict/fbeta_score", "predict/mae"}
+    # debug label check: labels outside [0, C) that are not ignore_index are dropped by the kernels -- and counted
+    dbg = MTLModule(net, num_classes=C, device=dev(), check_labels=True)
+    bad = batch["mask"].clone()
+    bad[0, 0, :5] = C + 3
+    bad[1, 1, :2] = -100  # ignore_index: legal
+    with torch.no_grad():
+        out_bad = dbg.fused_losses_and_metrics(batch["img"], bad, batch["depth"])
+    assert int(dbg.last_bad_label_count) == 5
+    assert int(dbg.last_confusion.sum()) == 2 * 32 * 32 - 7 and torch.isfinite(out_bad["loss"])
 
 
 @pytest.mark.parametrize("model_name", ["mtan", "csnet", "basic"])

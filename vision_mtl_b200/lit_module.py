@@ -39,8 +39,15 @@ class MTLModule(nn.Module):
         loss_segm_weight: float = 1.0,
         loss_depth_weight: float = 1.0,
         ignore_index: int = -100,
+        check_labels: bool = False,
     ):
+        """``check_labels`` (debug): count, per step and on the device, the segmentation labels that are neither
+        ``ignore_index`` nor in ``[0, num_classes)`` into ``last_bad_label_count``.  The fused kernels drop such
+        pixels from the loss mean and the confusion matrix, where ``nn.CrossEntropyLoss`` / torchmetrics in the
+        reference would raise: a ``num_classes`` / label-map mismatch is otherwise silent."""
         super().__init__()
+        self.check_labels = bool(check_labels)
+        self.last_bad_label_count: t.Optional[torch.Tensor] = None
         self.hparams = {"num_classes": num_classes, "lr": lr, "device": device,
                         "loss_segm_weight": loss_segm_weight, "loss_depth_weight": loss_depth_weight}
         self.num_classes = num_classes
@@ -75,6 +82,8 @@ class MTLModule(nn.Module):
     def fused_losses_and_metrics(self, img, gt_mask, gt_depth, want_preds: bool = False) -> dict:
         """Model forward + fused heads/losses/metrics.  Returns device scalars (no host sync)."""
         C = self.num_classes
+        if self.check_labels:
+            self.last_bad_label_count = ((gt_mask != self.ignore_index) & ((gt_mask < 0) | (gt_mask >= C))).sum()
         conf = torch.zeros((C, C), dtype=torch.int64, device=img.device)
         inner = self._inner_model()
         if hasattr(inner, "forward_features"):
