@@ -109,7 +109,7 @@ class Adam(torch.optim.Optimizer):
             live = []
             for i, p in enumerate(group["params"]):
                 g = p.grad
-                if g is None:
+                if g is None or p.numel() == 0:
                     continue
                 if g.is_sparse or g.dtype != torch.float32 or not g.is_cuda:
                     raise _lib.VmtlError("vision_mtl_b200.optim.Adam needs dense fp32 CUDA gradients")
