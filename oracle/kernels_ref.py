@@ -82,11 +82,13 @@ def depth_predictions(depth_logits: torch.Tensor) -> torch.Tensor:
     return torch.sigmoid(depth_logits).permute(0, 2, 3, 1)
 
 
-def silog(pred: torch.Tensor, target: torch.Tensor, min_depth: float = 1e-3) -> torch.Tensor:
+def silog(pred: torch.Tensor, target: torch.Tensor, min_depth: float = 1e-3, mask=None) -> torch.Tensor:
     """SILog loss (losses.py:22-36).  The bilinear ``interpolate`` call at
     losses.py:24-27 resizes ``pred`` to its own trailing two dims for the
-    (B,H,W,1) layout, i.e. it is the identity, and is skipped here."""
-    mask = target > min_depth
+    (B,H,W,1) layout, i.e. it is the identity, and is skipped here.  An explicit ``mask``
+    replaces the ``target > min_depth`` one (losses.py:29-30)."""
+    if mask is None:
+        mask = target > min_depth
     g = torch.log(pred[mask]) - torch.log(target[mask])
     dg = torch.var(g) + 0.15 * torch.pow(torch.mean(g), 2)
     return 10 * torch.sqrt(dg)

@@ -69,6 +69,12 @@ def gen_xstitch(ref, out):
         out[f"xs/{name}/dw"] = _np(layer.weights.grad)
 
 
+def silog_explicit_mask(depth: torch.Tensor) -> torch.Tensor:
+    """Deterministic boolean mask over positive-depth pixels (every third of them dropped)."""
+    idx = torch.arange(depth.numel()).reshape(depth.shape)
+    return (depth > 1e-3) & (idx % 3 != 1)
+
+
 def gen_silog(ref, out):
     crit = ref["SILogLoss"]()
     logit = FX.tensor((2, 8, 16, 1), "silog/logit", 2.0).requires_grad_(True)
@@ -78,6 +84,13 @@ def gen_silog(ref, out):
     loss.backward()
     out["silog/loss"] = _np(loss)
     out["silog/dlogit"] = _np(logit.grad)
+    # explicit mask (losses.py:29-33): a subset of the positive-depth pixels
+    logit2 = FX.tensor((2, 8, 16, 1), "silog/logit", 2.0).requires_grad_(True)
+    mask = silog_explicit_mask(b["depth"])
+    loss2 = crit(torch.sigmoid(logit2), b["depth"], mask=mask)
+    loss2.backward()
+    out["silog_masked/loss"] = _np(loss2)
+    out["silog_masked/dlogit"] = _np(logit2.grad)
 
 
 def _flip_margin(net, img):

@@ -5,6 +5,7 @@ metrics within 1e-4 relative in fp32.  The relative error is taken tensor-wise:
 max|got - ref| <= TOL * max|ref|.
 """
 import copy
+import os
 
 import numpy as np
 import pytest
@@ -291,6 +292,17 @@ def test_silog_loss_module_mask_and_saturation():
     loss.backward()
     assert_rel(loss, loss_r, what="masked silog")
     assert_rel(pd.grad, pr.grad, what="masked silog d/dpred")
+    # ... and against the output of the UNMODIFIED reference SILogLoss(mask=...) (tests/golden/kernels.npz)
+    from oracle import fixtures as FX
+    from oracle.make_golden import silog_explicit_mask
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "kernels.npz"))
+    bg = FX.image_batch(2, 8, 16, 19, "silog")
+    lg = FX.tensor((2, 8, 16, 1), "silog/logit", 2.0).to(dev()).requires_grad_(True)
+    loss_g = SILogLoss()(torch.sigmoid(lg), bg["depth"].to(dev()), mask=silog_explicit_mask(bg["depth"]).to(dev()))
+    loss_g.backward()
+    assert_rel(loss_g, torch.tensor(float(gold["silog_masked/loss"])), what="masked silog vs reference golden")
+    assert_rel(lg.grad.cpu(), torch.from_numpy(gold["silog_masked/dlogit"]), what="masked silog dlogit vs reference golden")
     # saturation: logits down to -100 (sigmoid flushes to 0 in the fast form) and up to +40 (sigmoid == 1.0f)
     zs = torch.linspace(-100.0, 40.0, B * H * W).reshape(B, 1, H, W)
     ts = torch.full((B, H, W, 1), 0.25)
